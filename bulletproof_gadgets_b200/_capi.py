@@ -1,0 +1,93 @@
+"""ctypes loader for libbpg.so and the prototypes of include/bpg.h."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbpg.so")
+
+OK, E_FORMAT, E_VERIFY, E_GENS_LEN, E_MISSING_ASSIGNMENT, E_CUDA, E_ARG, E_GADGET = 0, -1, -2, -3, -4, -5, -6, -7
+_NAMES = {E_FORMAT: "FormatError", E_VERIFY: "VerificationError", E_GENS_LEN: "InvalidGeneratorsLength",
+          E_MISSING_ASSIGNMENT: "MissingAssignment", E_CUDA: "CudaError", E_ARG: "ArgumentError",
+          E_GADGET: "GadgetError"}
+
+
+class BpgError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__("%s (%d): %s" % (_NAMES.get(code, "Error"), code, msg))
+
+
+class ProofArtifacts(ctypes.Structure):
+    _fields_ = [("commitments", c_char_p), ("proof", POINTER(c_uint8)), ("proof_len", c_size_t),
+                ("num_constraints", c_uint64)]
+
+
+_lib = None
+
+_u8p = POINTER(c_uint8)
+_u32p = POINTER(c_uint32)
+
+PROTOTYPES = {
+    "bpg_last_error": (c_char_p, []),
+    "bpg_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "bpg_ctx_destroy": (None, [c_void_p]),
+    "bpg_ctx_set": (c_int, [c_void_p, c_char_p, c_int64]),
+    "bpg_ctx_get": (c_int64, [c_void_p, c_char_p]),
+    "bpg_gens_ensure": (c_int, [c_void_p, c_uint64]),
+    "bpg_gens_compressed": (c_int, [c_void_p, c_int, c_uint64, c_uint64, c_char_p]),
+    "bpg_msm_gens": (c_int, [c_void_p, c_char_p, c_uint64, c_char_p, c_uint64, c_char_p, c_char_p, c_char_p]),
+    "bpg_msm_gens_dev": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_void_p, c_char_p]),
+    "bpg_msm": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_char_p]),
+    "bpg_pedersen_commit_batch": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_char_p]),
+    "bpg_transcript_new": (c_void_p, [c_char_p, c_size_t]),
+    "bpg_transcript_clone": (c_void_p, [c_void_p]),
+    "bpg_transcript_free": (None, [c_void_p]),
+    "bpg_transcript_append_message": (None, [c_void_p, c_char_p, c_size_t, c_char_p, c_size_t]),
+    "bpg_transcript_challenge_bytes": (None, [c_void_p, c_char_p, c_size_t, c_char_p, c_size_t]),
+    "bpg_prover_new": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
+    "bpg_prover_free": (None, [c_void_p]),
+    "bpg_prover_commit": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, _u32p]),
+    "bpg_prover_commit_batch": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_char_p, _u32p]),
+    "bpg_prover_allocate_multiplier": (c_int, [c_void_p, c_char_p, c_char_p, _u32p]),
+    "bpg_prover_multiply": (c_int, [c_void_p, _u32p, c_char_p, c_size_t, _u32p, c_char_p, c_size_t, _u32p]),
+    "bpg_prover_constrain": (c_int, [c_void_p, _u32p, c_char_p, c_size_t]),
+    "bpg_prover_num_constraints": (c_uint64, [c_void_p]),
+    "bpg_prover_num_multipliers": (c_uint64, [c_void_p]),
+    "bpg_prover_prove": (c_int, [c_void_p, c_char_p, c_char_p, c_size_t, POINTER(c_size_t)]),
+    "bpg_verifier_new": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
+    "bpg_verifier_free": (None, [c_void_p]),
+    "bpg_verifier_commit": (c_int, [c_void_p, c_char_p, _u32p]),
+    "bpg_verifier_allocate_multiplier": (c_int, [c_void_p, _u32p]),
+    "bpg_verifier_multiply": (c_int, [c_void_p, _u32p, c_char_p, c_size_t, _u32p, c_char_p, c_size_t, _u32p]),
+    "bpg_verifier_constrain": (c_int, [c_void_p, _u32p, c_char_p, c_size_t]),
+    "bpg_verifier_num_vars": (c_uint64, [c_void_p]),
+    "bpg_verifier_verify": (c_int, [c_void_p, c_char_p, c_size_t, c_char_p]),
+    "bpg_prove": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, c_char_p, c_char_p, c_char_p,
+                          POINTER(POINTER(ProofArtifacts))]),
+    "bpg_verify": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, c_char_p, c_char_p, c_size_t, c_char_p,
+                           POINTER(c_int)]),
+    "bpg_free_proof": (None, [POINTER(ProofArtifacts)]),
+}
+
+
+def lib():
+    """Loads libbpg.so (built in-tree by bulletproof_gadgets_b200.build).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BpgError(E_CUDA, "libbpg.so is not built (run `python -m bulletproof_gadgets_b200.build`); "
+                                   "there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise BpgError(rc, (lib().bpg_last_error() or b"").decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,319 @@
+"""Python mirror of the reference-facing API, bound to the C ABI (include/bpg.h).
+
+Names follow dalek `bulletproofs::r1cs` as used by the reference's gadgets
+(/root/reference/src/gadget.rs:7-60): Prover.commit / multiply / allocate_multiplier / constrain /
+prove, Verifier.commit / ... / verify, LinearCombination, Variable, merlin Transcript.
+Scalars are ints (or 32-byte little-endian `bytes`); compressed points are 32-byte `bytes`.
+"""
+import ctypes
+from ctypes import byref, c_int, c_size_t, c_uint32, c_void_p
+
+from . import _capi
+from ._capi import BpgError, check, lib
+
+L_ORDER = 2**252 + 27742317777372353535851937790883648493
+
+
+def _sb(x):
+    """Scalar -> 32 bytes LE.  ints are taken as given when < 2^255 (Scalar::from_bits semantics)."""
+    if isinstance(x, (bytes, bytearray)):
+        assert len(x) == 32
+        return bytes(x)
+    x = int(x)
+    if x < 0:
+        x %= L_ORDER
+    return x.to_bytes(32, "little")
+
+
+class Context:
+    """One per GPU: device streams, cached generator tables, work buffers (bpg_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = c_void_p()
+        check(lib().bpg_ctx_create(device, byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().bpg_ctx_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, key, value):
+        check(lib().bpg_ctx_set(self._h, key.encode(), int(value)))
+
+    def get(self, key):
+        return lib().bpg_ctx_get(self._h, key.encode())
+
+    def gens_ensure(self, capacity):
+        """BulletproofGens::new(capacity, 1) + PedersenGens::default()."""
+        check(lib().bpg_gens_ensure(self._h, capacity))
+
+    def gens_compressed(self, which, start=0, count=1):
+        idx = {"G": 0, "H": 1, "B": 2, "B_blinding": 3}[which]
+        buf = ctypes.create_string_buffer(32 * count)
+        check(lib().bpg_gens_compressed(self._h, idx, start, count, buf))
+        return [buf.raw[32 * i: 32 * i + 32] for i in range(count)]
+
+    def msm_gens(self, sG=(), sH=(), sB=None, sBb=None):
+        """sum sG_i G_i + sum sH_i H_i + sB B + sBb B_blinding -> compressed ristretto."""
+        bG = b"".join(_sb(s) for s in sG)
+        bH = b"".join(_sb(s) for s in sH)
+        out = ctypes.create_string_buffer(32)
+        check(lib().bpg_msm_gens(self._h, bG or None, len(bG) // 32, bH or None, len(bH) // 32,
+                                 _sb(sB) if sB is not None else None, _sb(sBb) if sBb is not None else None, out))
+        return out.raw
+
+    def msm_gens_bytes(self, bG=b"", bH=b"", sB=None, sBb=None):
+        out = ctypes.create_string_buffer(32)
+        check(lib().bpg_msm_gens(self._h, bG or None, len(bG) // 32, bH or None, len(bH) // 32, sB, sBb, out))
+        return out.raw
+
+    def msm_gens_dev(self, d_sG, nG, d_sH, nH, d_sB=None, d_sBb=None):
+        """Device-pointer flavour (ints from torch .data_ptr())."""
+        out = ctypes.create_string_buffer(32)
+        check(lib().bpg_msm_gens_dev(self._h, d_sG, nG, d_sH, nH, d_sB, d_sBb, out))
+        return out.raw
+
+    def msm(self, scalars, points):
+        """vartime_multiscalar_mul over arbitrary compressed points."""
+        bs = b"".join(_sb(s) for s in scalars)
+        bp = b"".join(points)
+        assert len(bs) == len(bp)
+        out = ctypes.create_string_buffer(32)
+        check(lib().bpg_msm(self._h, bs, bp, len(bs) // 32, out))
+        return out.raw
+
+    def pedersen_commit_batch(self, vs, rs):
+        k = len(vs)
+        out = ctypes.create_string_buffer(32 * max(k, 1))
+        check(lib().bpg_pedersen_commit_batch(self._h, b"".join(_sb(v) for v in vs), b"".join(_sb(r) for r in rs), k,
+                                              out))
+        return [out.raw[32 * i: 32 * i + 32] for i in range(k)]
+
+
+class Transcript:
+    """merlin::Transcript (host side)."""
+
+    def __init__(self, label=None, _h=None):
+        self._h = _h if _h is not None else c_void_p(lib().bpg_transcript_new(label, len(label)))
+
+    def clone(self):
+        return Transcript(_h=c_void_p(lib().bpg_transcript_clone(self._h)))
+
+    def append_message(self, label, msg):
+        lib().bpg_transcript_append_message(self._h, label, len(label), msg, len(msg))
+
+    def append_u64(self, label, x):
+        self.append_message(label, int(x).to_bytes(8, "little"))
+
+    def challenge_bytes(self, label, n):
+        buf = ctypes.create_string_buffer(n)
+        lib().bpg_transcript_challenge_bytes(self._h, label, len(label), buf, n)
+        return buf.raw
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bpg_transcript_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+COMMITTED, MUL_LEFT, MUL_RIGHT, MUL_OUT, ONE = 0, 1, 2, 3, 4
+
+
+class Variable(int):
+    """uint32 tag kind<<29 | index (dalek r1cs::Variable)."""
+
+    @staticmethod
+    def make(kind, idx=0):
+        return Variable((kind << 29) | idx)
+
+    @staticmethod
+    def One():
+        return Variable(ONE << 29)
+
+    kind = property(lambda s: int(s) >> 29)
+    idx = property(lambda s: int(s) & ((1 << 29) - 1))
+
+
+class LinearCombination:
+    """Term list; + and - concatenate (no merging), like dalek's LinearCombination."""
+
+    __slots__ = ("terms",)
+
+    def __init__(self, terms=None):
+        self.terms = list(terms) if terms else []
+
+    @staticmethod
+    def of(x):
+        if isinstance(x, LinearCombination):
+            return x
+        if isinstance(x, Variable):
+            return LinearCombination([(x, 1)])
+        if isinstance(x, int):
+            return LinearCombination([(Variable.One(), x)])
+        raise TypeError(type(x))
+
+    def __add__(self, o):
+        return LinearCombination(self.terms + LinearCombination.of(o).terms)
+
+    def __sub__(self, o):
+        return LinearCombination(self.terms + [(v, (-c) % L_ORDER) for v, c in LinearCombination.of(o).terms])
+
+    def __neg__(self):
+        return LinearCombination([(v, (-c) % L_ORDER) for v, c in self.terms])
+
+    def scale(self, s):
+        return LinearCombination([(v, (c * s) % L_ORDER) for v, c in self.terms])
+
+    def _pack(self):
+        n = len(self.terms)
+        vars_ = (c_uint32 * max(n, 1))(*[int(v) for v, _ in self.terms])
+        coef = b"".join(_sb(c) for _, c in self.terms)
+        return vars_, coef, n
+
+
+class _CS:
+    def _vars3(self, arr):
+        return Variable(arr[0]), Variable(arr[1]), Variable(arr[2])
+
+
+class Prover(_CS):
+    """bulletproofs::r1cs::Prover (GPU-backed)."""
+
+    def __init__(self, ctx, transcript):
+        self.ctx, self.transcript = ctx, transcript
+        self._h = c_void_p()
+        check(lib().bpg_prover_new(ctx._h, transcript._h, byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bpg_prover_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def commit(self, v, v_blinding):
+        out = ctypes.create_string_buffer(32)
+        var = c_uint32()
+        check(lib().bpg_prover_commit(self._h, _sb(v), _sb(v_blinding), out, byref(var)))
+        return out.raw, Variable(var.value)
+
+    def commit_batch(self, vs, blindings):
+        k = len(vs)
+        out = ctypes.create_string_buffer(32 * max(k, 1))
+        first = c_uint32()
+        check(lib().bpg_prover_commit_batch(self._h, b"".join(_sb(v) for v in vs),
+                                            b"".join(_sb(b) for b in blindings), k, out, byref(first)))
+        return [(out.raw[32 * i: 32 * i + 32], Variable(first.value + i)) for i in range(k)]
+
+    def allocate_multiplier(self, assignment):
+        if assignment is None:
+            raise BpgError(_capi.E_MISSING_ASSIGNMENT, "allocate_multiplier(None) on a prover")
+        arr = (c_uint32 * 3)()
+        check(lib().bpg_prover_allocate_multiplier(self._h, _sb(assignment[0]), _sb(assignment[1]), arr))
+        return self._vars3(arr)
+
+    def multiply(self, left, right):
+        lv, lc, ln = LinearCombination.of(left)._pack()
+        rv, rc, rn = LinearCombination.of(right)._pack()
+        arr = (c_uint32 * 3)()
+        check(lib().bpg_prover_multiply(self._h, lv, lc, ln, rv, rc, rn, arr))
+        return self._vars3(arr)
+
+    def constrain(self, lc):
+        v, c, n = LinearCombination.of(lc)._pack()
+        check(lib().bpg_prover_constrain(self._h, v, c, n))
+
+    def num_constraints(self):
+        return lib().bpg_prover_num_constraints(self._h)
+
+    def num_multipliers(self):
+        return lib().bpg_prover_num_multipliers(self._h)
+
+    def prove(self, rng_seed=None):
+        """Prover::prove(&bp_gens).to_bytes(); rng_seed (32 bytes) pins merlin's external entropy."""
+        cap = 1 + 14 * 32 + (2 * 32 + 2) * 32
+        buf = ctypes.create_string_buffer(cap)
+        n = c_size_t()
+        check(lib().bpg_prover_prove(self._h, rng_seed, buf, cap, byref(n)))
+        return buf.raw[: n.value]
+
+
+class Verifier(_CS):
+    """bulletproofs::r1cs::Verifier (GPU-backed)."""
+
+    def __init__(self, ctx, transcript):
+        self.ctx, self.transcript = ctx, transcript
+        self._h = c_void_p()
+        check(lib().bpg_verifier_new(ctx._h, transcript._h, byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bpg_verifier_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def commit(self, V):
+        var = c_uint32()
+        check(lib().bpg_verifier_commit(self._h, bytes(V), byref(var)))
+        return Variable(var.value)
+
+    def allocate_multiplier(self, assignment=None):
+        arr = (c_uint32 * 3)()
+        check(lib().bpg_verifier_allocate_multiplier(self._h, arr))
+        return self._vars3(arr)
+
+    def multiply(self, left, right):
+        lv, lc, ln = LinearCombination.of(left)._pack()
+        rv, rc, rn = LinearCombination.of(right)._pack()
+        arr = (c_uint32 * 3)()
+        check(lib().bpg_verifier_multiply(self._h, lv, lc, ln, rv, rc, rn, arr))
+        return self._vars3(arr)
+
+    def constrain(self, lc):
+        v, c, n = LinearCombination.of(lc)._pack()
+        check(lib().bpg_verifier_constrain(self._h, v, c, n))
+
+    def num_vars(self):
+        return lib().bpg_verifier_num_vars(self._h)
+
+    def verify(self, proof, rng_seed=None):
+        """True = accepted, False = rejected (VerificationError); malformed proofs raise FormatError."""
+        rc = lib().bpg_verifier_verify(self._h, proof, len(proof), rng_seed)
+        if rc == _capi.OK:
+            return True
+        if rc == _capi.E_VERIFY:
+            return False
+        check(rc)
+
+
+def prove(ctx, name, instance, witness, gadgets, blinding_seed=None, rng_seed=None):
+    """prove() of /root/reference/src/prove.rs:37-43 -> (proof bytes, commitments text, #constraints)."""
+    out = ctypes.POINTER(_capi.ProofArtifacts)()
+    check(lib().bpg_prove(ctx._h, name.encode(), instance.encode(), witness.encode(), gadgets.encode(),
+                          blinding_seed, rng_seed, byref(out)))
+    try:
+        art = out.contents
+        proof = bytes(art.proof[: art.proof_len])
+        return proof, art.commitments.decode(), art.num_constraints
+    finally:
+        lib().bpg_free_proof(out)
+
+
+def verify(ctx, name, instance, proof, commitments, gadgets, rng_seed=None):
+    """verify() of /root/reference/src/verify.rs:36-42 -> bool."""
+    acc = c_int()
+    check(lib().bpg_verify(ctx._h, name.encode(), instance.encode(), gadgets.encode(), commitments.encode(), proof,
+                           len(proof), rng_seed, byref(acc)))
+    return bool(acc.value)

@@ -1,0 +1,80 @@
+"""Builds libbpg.so (CUDA kernels + C ABI + host protocol driver) in-tree for sm_100a.
+
+    python -m bulletproof_gadgets_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  Objects go to build/ (git-ignored); the .so is written next to
+this file so that it travels to the GPU box with the gpurun snapshot.
+"""
+import concurrent.futures
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libbpg.so")
+OBJDIR = os.path.join(ROOT, "build", "obj")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
+    "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+]
+
+
+def sources():
+    out = []
+    for dirpath, _, files in os.walk(CSRC):
+        for f in sorted(files):
+            if f.endswith((".cu", ".cpp")):
+                out.append(os.path.join(dirpath, f))
+    return sorted(out)
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for dirpath, _, files in os.walk(CSRC):
+        for f in sorted(files):
+            p = os.path.join(dirpath, f)
+            h.update(p.encode())
+            h.update(open(p, "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "bpg.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src):
+    obj = os.path.join(OBJDIR, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    return obj, r.stderr
+
+
+def build_lib(force=False, verbose=False):
+    stamp_file = OUT + ".stamp"
+    stamp = _stamp()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return OUT
+    os.makedirs(OBJDIR, exist_ok=True)
+    srcs = sources()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(_compile, srcs))
+    objs = [o for o, _ in results]
+    if verbose:
+        for _, err in results:
+            if err.strip():
+                print(err, file=sys.stderr)
+    cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    open(stamp_file, "w").write(stamp)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose=True))

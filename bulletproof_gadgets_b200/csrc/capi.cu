@@ -1,0 +1,218 @@
+// extern "C" surface of libbpg.so: context, generators, MSM and transcript entry points.
+// The R1CS prover/verifier entry points live in r1cs.cu, the statement front end in frontend.cpp.
+#include <stdarg.h>
+
+#include "ctx.hpp"
+#include "host_sc.hpp"
+#include "merlin.hpp"
+
+static thread_local char g_err[512] = "";
+
+void bpg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+void host_ristretto_compress(uint8_t out[32], const ge_ext& p) { ge_ristretto_compress(out, p); }
+bool host_is_ristretto_identity(const ge_ext& p) { return ge_is_ristretto_identity(p); }
+
+extern "C" {
+
+const char* bpg_last_error(void) { return g_err; }
+
+int bpg_ctx_create(int device, bpg_ctx** out) {
+    if (!out) return BPG_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        bpg_set_error("no CUDA device available (%s); this library has no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return BPG_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        bpg_set_error("device %d out of range (have %d)", device, ndev);
+        return BPG_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        bpg_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return BPG_E_CUDA;
+    }
+    bpg_ctx* ctx = new bpg_ctx();
+    ctx->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_a));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_b));
+    CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
+    *out = ctx;
+    return BPG_OK;
+}
+
+void bpg_ctx_destroy(bpg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->table.rows) cudaFree(ctx->table.rows);
+    if (ctx->gens_ext) cudaFree(ctx->gens_ext);
+    MsmWork& w = ctx->work;
+    w.hist.release();
+    w.bucket_off.release();
+    w.task_off.release();
+    w.entries.release();
+    w.tasks.release();
+    w.partials.release();
+    w.blockres.release();
+    w.result.release();
+    w.meta.release();
+    ctx->d_scalars.release();
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    cudaEventDestroy(ctx->ev_a);
+    cudaEventDestroy(ctx->ev_b);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return BPG_E_ARG;
+    std::string k(key);
+    if (k == "task_len") {
+        if (value < 1 || value > 255) return BPG_E_ARG;
+        ctx->task_len = (int)value;
+    } else if (k == "window_bits") {
+        if (value != 0 && (value < 4 || value > 16)) return BPG_E_ARG;
+        if (ctx->table.rows && value != ctx->window_bits) {  // force a rebuild on next ensure
+            cudaFree(ctx->table.rows);
+            ctx->table = FixedTable();
+        }
+        ctx->window_bits = (int)value;
+    } else if (k == "time_accum") {
+        ctx->time_accum = value != 0;
+    } else {
+        return BPG_E_ARG;
+    }
+    return BPG_OK;
+}
+
+int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key) {
+    if (!ctx || !key) return -1;
+    std::string k(key);
+    if (k == "launches") return (int64_t)ctx->launches;
+    if (k == "accum_us") return (int64_t)(ctx->last_accum_ms * 1000.0f);
+    if (k == "accum_ns") return (int64_t)((double)ctx->last_accum_ms * 1e6);
+    if (k == "accum_entries") return (int64_t)ctx->last_entries;
+    if (k == "capacity") return (int64_t)ctx->table.capacity;
+    if (k == "window_bits") return ctx->table.c;
+    if (k == "windows") return ctx->table.K;
+    if (k == "stream") return (int64_t)(intptr_t)ctx->stream;
+    return -1;
+}
+
+int bpg_gens_ensure(bpg_ctx* ctx, uint64_t capacity) {
+    if (!ctx) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return gens_build(ctx, capacity);
+}
+
+int bpg_gens_compressed(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out) {
+    if (!ctx || !out) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return gens_compress_range(ctx, which, start, count, out);
+}
+
+static int msm_gens_common(bpg_ctx* ctx, const uint32_t* d_sG, uint64_t nG, const uint32_t* d_sH, uint64_t nH,
+                           const uint32_t* d_sB, const uint32_t* d_sBb, uint8_t out32[32]) {
+    const uint64_t cap = ctx->table.capacity;
+    if (nG > cap || nH > cap) {
+        bpg_set_error("msm: %llu/%llu scalars exceed generator capacity %llu", (unsigned long long)nG,
+                      (unsigned long long)nH, (unsigned long long)cap);
+        return BPG_E_GENS_LEN;
+    }
+    MsmSegments segs;
+    memset(&segs, 0, sizeof segs);
+    auto push = [&](const uint32_t* p, uint64_t base, uint64_t n) {
+        if (!p || n == 0) return;
+        MsmSegment& s = segs.seg[segs.nseg++];
+        s.scalars = p;
+        s.point_base = (uint32_t)base;
+        s.count = (uint32_t)n;
+        s.set_id = 0;
+        s.mode = 0;
+        s.period = 1;
+        segs.total += (uint32_t)n;
+    };
+    push(d_sG, 0, nG);
+    push(d_sH, cap, nH);
+    push(d_sB, 2 * cap, 1);
+    push(d_sBb, 2 * cap + 1, 1);
+    int rc = msm_run(ctx, segs, 1, ctx->h_result);
+    if (rc) return rc;
+    host_ristretto_compress(out32, ctx->h_result[0]);
+    return BPG_OK;
+}
+
+static int check_scalars(const uint8_t* s, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++)
+        if (s[32 * i + 31] & 0x80) {
+            bpg_set_error("scalar %llu has bit 255 set (not a valid Scalar)", (unsigned long long)i);
+            return BPG_E_ARG;
+        }
+    return BPG_OK;
+}
+
+int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH, uint64_t nH, const uint8_t* sB,
+                 const uint8_t* sBb, uint8_t out32[32]) {
+    if (!ctx || !out32) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!sG) nG = 0;
+    if (!sH) nH = 0;
+    int rc;
+    if ((rc = check_scalars(sG, nG)) || (rc = check_scalars(sH, nH)) || (sB && (rc = check_scalars(sB, 1))) ||
+        (sBb && (rc = check_scalars(sBb, 1))))
+        return rc;
+    uint64_t need = nG > nH ? nG : nH;
+    if ((rc = gens_build(ctx, need ? need : 1))) return rc;
+    const uint64_t total = nG + nH + 2;
+    if ((rc = ctx->d_scalars.ensure(total * 8))) return rc;
+    uint32_t* d = ctx->d_scalars.p;
+    cudaStream_t st = ctx->stream;
+    if (nG) CUDA_TRY(cudaMemcpyAsync(d, sG, 32 * nG, cudaMemcpyHostToDevice, st));
+    if (nH) CUDA_TRY(cudaMemcpyAsync(d + 8 * nG, sH, 32 * nH, cudaMemcpyHostToDevice, st));
+    if (sB) CUDA_TRY(cudaMemcpyAsync(d + 8 * (nG + nH), sB, 32, cudaMemcpyHostToDevice, st));
+    if (sBb) CUDA_TRY(cudaMemcpyAsync(d + 8 * (nG + nH + 1), sBb, 32, cudaMemcpyHostToDevice, st));
+    return msm_gens_common(ctx, nG ? d : nullptr, nG, nH ? d + 8 * nG : nullptr, nH, sB ? d + 8 * (nG + nH) : nullptr,
+                           sBb ? d + 8 * (nG + nH + 1) : nullptr, out32);
+}
+
+int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH, const void* d_sB,
+                     const void* d_sBb, uint8_t out32[32]) {
+    if (!ctx || !out32) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!d_sG) nG = 0;
+    if (!d_sH) nH = 0;
+    uint64_t need = nG > nH ? nG : nH;
+    int rc;
+    if ((rc = gens_build(ctx, need ? need : 1))) return rc;
+    return msm_gens_common(ctx, (const uint32_t*)d_sG, nG, (const uint32_t*)d_sH, nH, (const uint32_t*)d_sB,
+                           (const uint32_t*)d_sBb, out32);
+}
+
+// ---------------------------------------------------------------------------- transcript
+bpg_transcript* bpg_transcript_new(const uint8_t* label, size_t len) { return new bpg_transcript(label, len); }
+bpg_transcript* bpg_transcript_clone(const bpg_transcript* t) { return t ? new bpg_transcript(*t) : nullptr; }
+void bpg_transcript_free(bpg_transcript* t) { delete t; }
+void bpg_transcript_append_message(bpg_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg,
+                                   size_t msg_len) {
+    t->t.append_message(label, label_len, msg, msg_len);
+}
+void bpg_transcript_challenge_bytes(bpg_transcript* t, const uint8_t* label, size_t label_len, uint8_t* out,
+                                    size_t out_len) {
+    t->t.challenge_bytes(label, label_len, out, out_len);
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Per-GPU context: streams, generator tables, MSM work buffers.  One context per GPU; contexts
+// are independent (thread-per-GPU safe); a single context is not re-entrant.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bpg.h"
+#include "ge25519.cuh"
+#include "sc25519.cuh"
+
+void bpg_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            bpg_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            return BPG_E_CUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int ensure(size_t n) {
+        if (n <= cap) return BPG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        CUDA_TRY(cudaMalloc((void**)&p, want * sizeof(T)));
+        cap = want;
+        return BPG_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// One segment of an MSM: `count` scalars (32 B LE each, canonical) multiplying table points
+// point_base .. point_base+count-1.  The bucket set an element goes to is
+//   mode 0: set_id
+//   mode 1: set_id + ((i mod period) >= period/2 ? 0 : 1)      (IPP G rule: G_R -> L, G_L -> R)
+//   mode 2: set_id + ((i mod period) <  period/2 ? 0 : 1)      (IPP H rule: H_L -> L, H_R -> R)
+struct MsmSegment {
+    const uint32_t* scalars;
+    uint32_t point_base;
+    uint32_t count;
+    uint32_t set_id;
+    uint32_t mode;
+    uint32_t period;
+};
+#define MSM_MAX_SEGMENTS 8
+struct MsmSegments {
+    MsmSegment seg[MSM_MAX_SEGMENTS];
+    uint32_t nseg;
+    uint32_t total;  // sum of counts
+};
+
+// Fixed-base table: rows[w][i] = affine Niels form of 2^(c*w) * P_i, i < n_points (row stride = n_points)
+struct FixedTable {
+    ge_niels* rows = nullptr;
+    uint32_t n_points = 0;
+    int c = 0, K = 0;
+    uint64_t capacity = 0;  // generator capacity: points are [G_0..G_cap-1, H_0..H_cap-1, B, B_blinding]
+};
+
+struct MsmWork {
+    DevBuf<uint32_t> hist;       // [nsets*nb] counts, then reused as scatter cursors
+    DevBuf<uint32_t> bucket_off; // [nsets*nb]
+    DevBuf<uint32_t> task_off;   // [nsets*nb]
+    DevBuf<uint32_t> entries;    // [K*N]
+    DevBuf<uint2> tasks;         // {start, bucket<<8 | count}
+    DevBuf<ge_ext> partials;     // one per task
+    DevBuf<ge_ext> blockres;     // [nsets][REDUCE_BLOCKS]
+    DevBuf<ge_ext> result;       // [nsets]
+    DevBuf<uint32_t> meta;       // [0]=ntasks total, [1+s]=task start of set s, ... see msm.cu
+};
+
+struct bpg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    FixedTable table;
+    ge_ext* gens_ext = nullptr;  // untabulated generators (extended), same order as the table
+    MsmWork work;
+    ge_ext* h_result = nullptr;  // pinned
+    uint8_t* h_stage = nullptr;  // pinned staging
+    size_t h_stage_cap = 0;
+    DevBuf<uint32_t> d_scalars;  // staging for host-provided scalars
+    int task_len = 32;
+    int window_bits = 0;  // 0 = auto
+    // counters for bench.py ("gpu_launches")
+    uint64_t launches = 0;
+    // timing of the dominant kernel (accumulate), CUDA events on ctx stream
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    float last_accum_ms = 0.f;
+    uint64_t last_entries = 0;
+    bool time_accum = false;
+};
+
+// msm.cu
+int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* h_out /*pinned or pageable, nsets*/);
+// gens.cu
+int gens_build(bpg_ctx* ctx, uint64_t capacity);
+int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out);
+// host_fe.cpp
+void host_ristretto_compress(uint8_t out[32], const ge_ext& p);
+bool host_is_ristretto_identity(const ge_ext& p);

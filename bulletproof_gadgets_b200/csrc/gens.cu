@@ -1,0 +1,162 @@
+// Generator derivation and the device-resident fixed-base window tables.
+//
+// Replaces bulletproofs `BulletproofGens::new(capacity, 1)` / `GeneratorsChain` / `PedersenGens::default`
+// (generators.rs of the FairAds fork, /root/reference/Cargo.lock:78-80, not vendored) as called at
+// /root/reference/src/prove.rs:46,78 and /root/reference/src/verify.rs:45,70 (SURVEY.md rows a2, K8,
+// K9, f1).  The SHAKE256 stream is sequential and stays on the host; the 4*capacity Elligator maps,
+// the window multiples 2^(c*w)*P and the affine-Niels normalisation run on the GPU.  The reference
+// rebuilds the generators on every run; here they are cached per context.
+#include "ctx.hpp"
+#include "merlin.hpp"
+
+__global__ void __launch_bounds__(128) k_uniform_to_ext(const uint8_t* __restrict__ uniform, ge_ext* __restrict__ out,
+                                                        uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __align__(16) uint8_t b[64];
+    const uint4* src = reinterpret_cast<const uint4*>(uniform + 64 * (size_t)i);
+    uint4* dst = reinterpret_cast<uint4*>(b);
+#pragma unroll
+    for (int k = 0; k < 4; k++) dst[k] = src[k];
+    out[i] = ge_from_uniform_bytes(b);
+}
+
+__global__ void __launch_bounds__(128) k_decompress(const uint8_t* __restrict__ in, ge_ext* __restrict__ out,
+                                                    uint32_t n, uint32_t* __restrict__ fail) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    for (int k = 0; k < 32; k++) b[k] = in[32 * (size_t)i + k];
+    ge_ext p;
+    if (!ge_ristretto_decompress(&p, b)) {
+        atomicAdd(fail, 1u);
+        p = ge_identity();
+    }
+    out[i] = p;
+}
+
+__global__ void __launch_bounds__(128) k_compress(const ge_ext* __restrict__ in, uint8_t* __restrict__ out,
+                                                  uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    ge_ristretto_compress(b, in[i]);
+    for (int k = 0; k < 32; k++) out[32 * (size_t)i + k] = b[k];
+}
+
+// tmp[w*n + i] = 2^(c*w) * P_i
+__global__ void __launch_bounds__(128) k_window_multiples(const ge_ext* __restrict__ pts, ge_ext* __restrict__ tmp,
+                                                          uint32_t n, int c, int K) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_ext p = pts[i];
+    for (int w = 0; w < K; w++) {
+        tmp[(size_t)w * n + i] = p;
+        if (w + 1 < K) {
+#pragma unroll 1
+            for (int k = 0; k < c; k++) p = ge_dbl(p);
+        }
+    }
+}
+
+// rows[e] = affine Niels of tmp[e]
+__global__ void __launch_bounds__(128) k_to_niels(const ge_ext* __restrict__ tmp, ge_niels* __restrict__ rows,
+                                                  uint64_t total) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    ge_ext p = tmp[e];
+    rows[e] = ge_to_niels(p, fe_invert(p.Z));
+}
+
+static const uint8_t BASEPOINT_COMPRESSED[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9,
+                                                 0x61, 0xc5, 0x00, 0x51, 0x5f, 0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82,
+                                                 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+
+int gens_build(bpg_ctx* ctx, uint64_t capacity) {
+    if (capacity == 0) capacity = 1;
+    if (ctx->table.rows && ctx->table.capacity >= capacity) return BPG_OK;
+    // grow geometrically so repeated small requests do not rebuild
+    uint64_t cap = ctx->table.capacity ? ctx->table.capacity : 1;
+    while (cap < capacity) cap *= 2;
+    const int c = ctx->window_bits ? ctx->window_bits : 16;
+    const int K = (256 + c - 1) / c;
+    const uint64_t n = 2 * cap + 2;
+    if ((uint64_t)K * n >= (1ull << 31)) {
+        bpg_set_error("gens_build: capacity %llu too large", (unsigned long long)cap);
+        return BPG_E_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+
+    // host: 64 uniform bytes per point.  [G chain | H chain | unused(B) | B_blinding]
+    std::vector<uint8_t> uni(64 * n, 0);
+    for (int which = 0; which < 2; which++) {
+        bpg::Sponge sh = bpg::shake256();
+        const uint8_t label[5] = {(uint8_t)(which ? 'H' : 'G'), 0, 0, 0, 0};  // party index 0, LE32
+        sh.absorb(reinterpret_cast<const uint8_t*>("GeneratorsChain"), 15);
+        sh.absorb(label, 5);
+        sh.squeeze(uni.data() + 64 * cap * which, 64 * cap);
+    }
+    bpg::sha3_512(BASEPOINT_COMPRESSED, 32, uni.data() + 64 * (2 * cap + 1));
+
+    uint8_t* d_uni = nullptr;
+    uint8_t* d_bp = nullptr;
+    uint32_t* d_fail = nullptr;
+    ge_ext* d_ext = nullptr;
+    ge_ext* d_tmp = nullptr;
+    ge_niels* d_rows = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_uni, uni.size()));
+    CUDA_TRY(cudaMalloc((void**)&d_bp, 32));
+    CUDA_TRY(cudaMalloc((void**)&d_fail, 4));
+    CUDA_TRY(cudaMalloc((void**)&d_ext, n * sizeof(ge_ext)));
+    CUDA_TRY(cudaMalloc((void**)&d_tmp, (size_t)K * n * sizeof(ge_ext)));
+    CUDA_TRY(cudaMalloc((void**)&d_rows, (size_t)K * n * sizeof(ge_niels)));
+    CUDA_TRY(cudaMemcpyAsync(d_uni, uni.data(), uni.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_bp, BASEPOINT_COMPRESSED, 32, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_fail, 0, 4, st));
+    const uint32_t n32 = (uint32_t)n;
+    k_uniform_to_ext<<<(n32 + 127) / 128, 128, 0, st>>>(d_uni, d_ext, n32);
+    k_decompress<<<1, 128, 0, st>>>(d_bp, d_ext + 2 * cap, 1, d_fail);  // B overwrites its placeholder
+    k_window_multiples<<<(n32 + 127) / 128, 128, 0, st>>>(d_ext, d_tmp, n32, c, K);
+    const uint64_t total = (uint64_t)K * n;
+    k_to_niels<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(d_tmp, d_rows, total);
+    ctx->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_uni);
+    cudaFree(d_bp);
+    cudaFree(d_fail);
+    cudaFree(d_tmp);
+    if (ctx->table.rows) cudaFree(ctx->table.rows);
+    if (ctx->gens_ext) cudaFree(ctx->gens_ext);
+    ctx->gens_ext = d_ext;
+    ctx->table.rows = d_rows;
+    ctx->table.n_points = n32;
+    ctx->table.c = c;
+    ctx->table.K = K;
+    ctx->table.capacity = cap;
+    return BPG_OK;
+}
+
+int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out) {
+    const uint64_t cap = ctx->table.capacity;
+    if (!ctx->gens_ext) return BPG_E_ARG;
+    uint64_t base;
+    if (which == 0 || which == 1) {
+        if (start + count > cap) return BPG_E_GENS_LEN;
+        base = (which ? cap : 0) + start;
+    } else if (which == 2 || which == 3) {
+        if (start != 0 || count != 1) return BPG_E_ARG;
+        base = 2 * cap + (which - 2);
+    } else {
+        return BPG_E_ARG;
+    }
+    if (count == 0) return BPG_OK;
+    uint8_t* d_out = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_out, 32 * count));
+    k_compress<<<(uint32_t)((count + 127) / 128), 128, 0, ctx->stream>>>(ctx->gens_ext + base, d_out, (uint32_t)count);
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, 32 * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_out);
+    return BPG_OK;
+}

@@ -1,0 +1,151 @@
+/* bpg.h -- C ABI of the B200-native Bulletproofs R1CS hot path (libbpg.so).
+ *
+ * Drop-in boundary for the path that `bulletproofs_gadgets` drives through dalek's
+ * `bulletproofs` crate.  Every entry point names the reference interface it replaces
+ * (paths under /root/reference; "dalek:" = the un-vendored crates pinned in Cargo.lock:78-80,
+ * 155-157, 403-405).  Plain C: pointers and sizes only, no exceptions; status codes mirror
+ * dalek's `R1CSError` variants.  All scalars and compressed points are 32-byte little-endian
+ * buffers owned by the caller.  One context per GPU; a context is not re-entrant.
+ *
+ * There is no CPU fallback: every call that needs arithmetic fails with BPG_E_CUDA when no
+ * sm_100a device is usable.
+ */
+#ifndef BPG_H
+#define BPG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPG_OK 0
+#define BPG_E_FORMAT (-1)             /* dalek: R1CSError::FormatError                */
+#define BPG_E_VERIFY (-2)             /* dalek: R1CSError::VerificationError          */
+#define BPG_E_GENS_LEN (-3)           /* dalek: R1CSError::InvalidGeneratorsLength    */
+#define BPG_E_MISSING_ASSIGNMENT (-4) /* dalek: R1CSError::MissingAssignment          */
+#define BPG_E_CUDA (-5)               /* device / driver failure (no CPU fallback)    */
+#define BPG_E_ARG (-6)                /* bad argument                                  */
+#define BPG_E_GADGET (-7)             /* dalek: R1CSError::GadgetError / front-end panic */
+
+typedef struct bpg_ctx bpg_ctx;
+typedef struct bpg_transcript bpg_transcript;
+typedef struct bpg_prover bpg_prover;
+typedef struct bpg_verifier bpg_verifier;
+
+/* thread-local message of the last failing call */
+const char* bpg_last_error(void);
+
+/* ---- context and generators ------------------------------------------------------------ */
+/* One context per GPU.  Replaces nothing in the reference (it has no device state). */
+int bpg_ctx_create(int device, bpg_ctx** out);
+void bpg_ctx_destroy(bpg_ctx* ctx);
+/* tuning knobs: "task_len" (entries per accumulate task), "window_bits" (0 = auto) */
+int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value);
+/* counters: "launches" (kernels launched so far), "accum_us" / "accum_entries" (last timed MSM) */
+int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key);
+
+/* BulletproofGens::new(capacity, 1) + PedersenGens::default()
+ *   -- /root/reference/src/prove.rs:46,78 ; /root/reference/src/verify.rs:45,70.
+ * Derives G_i, H_i (SHAKE256 "GeneratorsChain" stream on the host, Elligator on the GPU) and
+ * builds the device-resident fixed-base window tables.  Idempotent; grows when needed. */
+int bpg_gens_ensure(bpg_ctx* ctx, uint64_t capacity);
+/* Compressed generators for inspection: which = 0:G 1:H 2:B 3:B_blinding. */
+int bpg_gens_compressed(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out32n);
+
+/* ---- multiscalar multiplication ------------------------------------------------------- */
+/* sum sG[i]*G_i + sum sH[i]*H_i + sB*B + sBb*B_blinding, compressed.
+ * Replaces dalek RistrettoPoint::multiscalar_mul / vartime_multiscalar_mul over generator
+ * slices (bulletproofs r1cs/prover.rs A_I1/A_O1/S1, inner_product_proof.rs L/R) -- reached from
+ * /root/reference/src/prove.rs:79.  Host pointers; any of sG/sH/sB/sBb may be NULL. */
+int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH, uint64_t nH,
+                 const uint8_t* sB, const uint8_t* sBb, uint8_t out32[32]);
+/* Same with DEVICE pointers (scalars already resident in HBM, canonical). */
+int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH,
+                     const void* d_sB, const void* d_sBb, uint8_t out32[32]);
+/* sum s[i]*P_i over arbitrary compressed points (dalek vartime_multiscalar_mul /
+ * optional_multiscalar_mul).  Returns BPG_E_VERIFY if a point does not decode. */
+int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars32n, const uint8_t* points32n, uint64_t n, uint8_t out32[32]);
+
+/* PedersenGens::commit(v, r) = v*B + r*B_blinding for k pairs
+ *   -- /root/reference/src/gadget.rs:32 ; /root/reference/src/commitments.rs:28,40. */
+int bpg_pedersen_commit_batch(bpg_ctx* ctx, const uint8_t* v32k, const uint8_t* r32k, uint64_t k, uint8_t* out32k);
+
+/* ---- Merlin transcript (host) ---------------------------------------------------------- */
+/* merlin::Transcript::new -- /root/reference/src/prove.rs:45 ; /root/reference/src/verify.rs:44 */
+bpg_transcript* bpg_transcript_new(const uint8_t* label, size_t len);
+bpg_transcript* bpg_transcript_clone(const bpg_transcript* t);
+void bpg_transcript_free(bpg_transcript* t);
+void bpg_transcript_append_message(bpg_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
+void bpg_transcript_challenge_bytes(bpg_transcript* t, const uint8_t* label, size_t label_len, uint8_t* out, size_t out_len);
+
+/* ---- R1CS constraint system: prover --------------------------------------------------- */
+/* Variables are uint32 tags: kind<<29 | index, kind = 0 Committed, 1 MultiplierLeft,
+ * 2 MultiplierRight, 3 MultiplierOutput, 4 One  (dalek r1cs::Variable). */
+#define BPG_VAR_COMMITTED(i) ((uint32_t)(0u << 29) | (uint32_t)(i))
+#define BPG_VAR_LEFT(i) ((uint32_t)(1u << 29) | (uint32_t)(i))
+#define BPG_VAR_RIGHT(i) ((uint32_t)(2u << 29) | (uint32_t)(i))
+#define BPG_VAR_OUT(i) ((uint32_t)(3u << 29) | (uint32_t)(i))
+#define BPG_VAR_ONE ((uint32_t)(4u << 29))
+
+/* Prover::new(&pc_gens, &mut transcript) -- /root/reference/src/prove.rs:47.  The prover borrows
+ * the transcript until bpg_prover_free / bpg_prover_prove. */
+int bpg_prover_new(bpg_ctx* ctx, bpg_transcript* t, bpg_prover** out);
+void bpg_prover_free(bpg_prover* p);
+/* Prover::commit(v, v_blinding) -> (CompressedRistretto, Variable) -- /root/reference/src/gadget.rs:32 */
+int bpg_prover_commit(bpg_prover* p, const uint8_t v[32], const uint8_t v_blinding[32], uint8_t V_out[32], uint32_t* var_out);
+/* k commitments in one device launch; transcript appends stay in order */
+int bpg_prover_commit_batch(bpg_prover* p, const uint8_t* v32k, const uint8_t* vb32k, uint64_t k, uint8_t* V_out32k, uint32_t* first_var_out);
+/* ConstraintSystem::allocate_multiplier(Some((l, r))) -- /root/reference/src/cs_buffer.rs:100-104 */
+int bpg_prover_allocate_multiplier(bpg_prover* p, const uint8_t l[32], const uint8_t r[32], uint32_t vars_out[3]);
+/* ConstraintSystem::multiply(left, right): LCs as parallel arrays (var tag, 32-byte coeff)
+ *   -- /root/reference/src/cs_buffer.rs:94-97 */
+int bpg_prover_multiply(bpg_prover* p, const uint32_t* lvars, const uint8_t* lcoef32, size_t ln,
+                        const uint32_t* rvars, const uint8_t* rcoef32, size_t rn, uint32_t vars_out[3]);
+/* ConstraintSystem::constrain(lc) -- /root/reference/src/cs_buffer.rs:112-115 */
+int bpg_prover_constrain(bpg_prover* p, const uint32_t* vars, const uint8_t* coef32, size_t n);
+/* Prover::num_constraints / get_num_multiplications (FairAds fork) -- /root/reference/src/prove.rs:75,78 */
+uint64_t bpg_prover_num_constraints(const bpg_prover* p);
+uint64_t bpg_prover_num_multipliers(const bpg_prover* p);
+/* Prover::prove(&bp_gens) -> R1CSProof::to_bytes() -- /root/reference/src/prove.rs:79-81.
+ * rng_seed32 replaces the 32 bytes merlin's TranscriptRngBuilder::finalize draws from
+ * thread_rng(); NULL = draw from the OS.  Generators for round_pow2(n) are ensured. */
+int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
+/* ---- R1CS constraint system: verifier ------------------------------------------------- */
+/* Verifier::new(&mut transcript) -- /root/reference/src/verify.rs:46 */
+int bpg_verifier_new(bpg_ctx* ctx, bpg_transcript* t, bpg_verifier** out);
+void bpg_verifier_free(bpg_verifier* v);
+/* Verifier::commit(V) -> Variable -- /root/reference/src/lalrpop/assignment_parser.rs:138 */
+int bpg_verifier_commit(bpg_verifier* v, const uint8_t V[32], uint32_t* var_out);
+/* allocate_multiplier(None) / multiply / constrain -- /root/reference/src/cs_buffer.rs:173-199 */
+int bpg_verifier_allocate_multiplier(bpg_verifier* v, uint32_t vars_out[3]);
+int bpg_verifier_multiply(bpg_verifier* v, const uint32_t* lvars, const uint8_t* lcoef32, size_t ln,
+                          const uint32_t* rvars, const uint8_t* rcoef32, size_t rn, uint32_t vars_out[3]);
+int bpg_verifier_constrain(bpg_verifier* v, const uint32_t* vars, const uint8_t* coef32, size_t n);
+uint64_t bpg_verifier_num_vars(const bpg_verifier* v); /* Verifier::get_num_vars -- /root/reference/src/verify.rs:70 */
+/* R1CSProof::from_bytes + Verifier::verify(&proof, &pc_gens, &bp_gens) -- /root/reference/src/verify.rs:53,71.
+ * BPG_OK = accepted, BPG_E_VERIFY = rejected, BPG_E_FORMAT = malformed proof bytes. */
+int bpg_verifier_verify(bpg_verifier* v, const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32);
+
+/* ---- statement-level front end (mirrors the reference's own C ABI) ---------------------- */
+/* prove()/verify() of /root/reference/src/prove.rs:37-43 and /root/reference/src/verify.rs:36-42,
+ * shaped like c_prove/c_verify/free_proof of /root/reference/interfaces/ios/src/lib.rs:21,45,55.
+ * blinding_seed32 seeds the commitment blindings the reference draws from thread_rng()
+ * (/root/reference/src/commitments.rs:28,40, /root/reference/src/gadget.rs:32); NULL = OS entropy. */
+typedef struct bpg_proof_artifacts {
+    char* commitments;   /* .coms text, NUL terminated */
+    uint8_t* proof;      /* .proof bytes */
+    size_t proof_len;
+    uint64_t num_constraints; /* what the reference prover prints (src/prove.rs:75) */
+} bpg_proof_artifacts;
+int bpg_prove(bpg_ctx* ctx, const char* name, const char* instance, const char* witness, const char* gadgets,
+              const uint8_t* blinding_seed32, const uint8_t* rng_seed32, bpg_proof_artifacts** out);
+int bpg_verify(bpg_ctx* ctx, const char* name, const char* instance, const char* gadgets, const char* commitments,
+               const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32, int* accepted);
+void bpg_free_proof(bpg_proof_artifacts* a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPG_H */
