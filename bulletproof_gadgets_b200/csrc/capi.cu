@@ -16,6 +16,11 @@ void bpg_set_error(const char* fmt, ...) {
 }
 
 void host_ristretto_compress(uint8_t out[32], const ge_ext& p) { ge_ristretto_compress(out, p); }
+int fetch_points(bpg_ctx* ctx, const ge_ext* d_pts, uint32_t n, ge_ext* h_out) {
+    CUDA_TRY(cudaMemcpyAsync(h_out, d_pts, sizeof(ge_ext) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BPG_OK;
+}
 bool host_is_ristretto_identity(const ge_ext& p) { return ge_is_ristretto_identity(p); }
 
 extern "C" {
@@ -67,9 +72,11 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     w.tasks.release();
     w.partials.release();
     w.blockres.release();
-    w.result.release();
     w.meta.release();
     ctx->d_scalars.release();
+    ctx->d_points.release();
+    if (ctx->ped) cudaFree(ctx->ped);
+    r1cs_release_work(ctx);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaEventDestroy(ctx->ev_a);
@@ -93,6 +100,8 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
         ctx->window_bits = (int)value;
     } else if (k == "time_accum") {
         ctx->time_accum = value != 0;
+        ctx->sum_accum_ms = 0;
+        ctx->sum_entries = 0;
     } else {
         return BPG_E_ARG;
     }
@@ -106,6 +115,8 @@ int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key) {
     if (k == "accum_us") return (int64_t)(ctx->last_accum_ms * 1000.0f);
     if (k == "accum_ns") return (int64_t)((double)ctx->last_accum_ms * 1e6);
     if (k == "accum_entries") return (int64_t)ctx->last_entries;
+    if (k == "sum_accum_ns") return (int64_t)(ctx->sum_accum_ms * 1e6);
+    if (k == "sum_entries") return (int64_t)ctx->sum_entries;
     if (k == "capacity") return (int64_t)ctx->table.capacity;
     if (k == "window_bits") return ctx->table.c;
     if (k == "windows") return ctx->table.K;
@@ -150,8 +161,10 @@ static int msm_gens_common(bpg_ctx* ctx, const uint32_t* d_sG, uint64_t nG, cons
     push(d_sH, cap, nH);
     push(d_sB, 2 * cap, 1);
     push(d_sBb, 2 * cap + 1, 1);
-    int rc = msm_run(ctx, segs, 1, ctx->h_result);
-    if (rc) return rc;
+    int rc;
+    if ((rc = ctx->d_points.ensure(64))) return rc;
+    if ((rc = msm_run(ctx, segs, 1, ctx->d_points.p))) return rc;
+    if ((rc = fetch_points(ctx, ctx->d_points.p, 1, ctx->h_result))) return rc;
     host_ristretto_compress(out32, ctx->h_result[0]);
     return BPG_OK;
 }

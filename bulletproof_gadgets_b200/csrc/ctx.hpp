@@ -80,7 +80,6 @@ struct MsmWork {
     DevBuf<uint2> tasks;         // {start, bucket<<8 | count}
     DevBuf<ge_ext> partials;     // one per task
     DevBuf<ge_ext> blockres;     // [nsets][REDUCE_BLOCKS]
-    DevBuf<ge_ext> result;       // [nsets]
     DevBuf<uint32_t> meta;       // [0]=ntasks total, [1+s]=task start of set s, ... see msm.cu
 };
 
@@ -94,6 +93,10 @@ struct bpg_ctx {
     uint8_t* h_stage = nullptr;  // pinned staging
     size_t h_stage_cap = 0;
     DevBuf<uint32_t> d_scalars;  // staging for host-provided scalars
+    DevBuf<ge_ext> d_points;     // result slots of asynchronous MSMs
+    ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu)
+    uint64_t ped_capacity = 0;
+    struct ProofWork* pw = nullptr;  // reusable device vectors of the R1CS driver (r1cs.cu)
     int task_len = 32;
     int window_bits = 0;  // 0 = auto
     // counters for bench.py ("gpu_launches")
@@ -102,11 +105,18 @@ struct bpg_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     float last_accum_ms = 0.f;
     uint64_t last_entries = 0;
+    double sum_accum_ms = 0;  // accumulated over all MSMs since the last reset (time_accum mode)
+    uint64_t sum_entries = 0;
     bool time_accum = false;
 };
 
 // msm.cu
-int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* h_out /*pinned or pageable, nsets*/);
+// asynchronous on ctx->stream; writes nsets extended points to the DEVICE array d_out
+int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out);
+// copies n extended points from device to host and waits for the stream
+int fetch_points(bpg_ctx* ctx, const ge_ext* d_pts, uint32_t n, ge_ext* h_out);
+// r1cs.cu
+void r1cs_release_work(bpg_ctx* ctx);
 // gens.cu
 int gens_build(bpg_ctx* ctx, uint64_t capacity);
 int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out);

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(REDUCE_BLOCKS) k_reduce_final(const ge_ext* __
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* h_out) {
+int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out) {
     const FixedTable& tb = ctx->table;
     if (!tb.rows) {
         bpg_set_error("msm_run: generator table not built");
@@ -316,7 +316,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* h_out
     if ((rc = w.hist.ensure(G)) || (rc = w.bucket_off.ensure(G + 1)) || (rc = w.task_off.ensure(G + 1)) ||
         (rc = w.entries.ensure(max_entries + 1)) || (rc = w.tasks.ensure(max_tasks)) ||
         (rc = w.partials.ensure(max_tasks)) || (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS)) ||
-        (rc = w.result.ensure(nsets)) || (rc = w.meta.ensure(nsets + 3)))
+        (rc = w.meta.ensure(nsets + 3)))
         return rc;
 
     CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));
@@ -344,18 +344,17 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* h_out
     }
     k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.tasks.p, w.meta.p, nb,
                                                                           w.blockres.p);
-    k_reduce_final<<<nsets, REDUCE_BLOCKS, 0, st>>>(w.blockres.p, w.result.p);
+    k_reduce_final<<<nsets, REDUCE_BLOCKS, 0, st>>>(w.blockres.p, d_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
-    if (h_out) {
-        CUDA_TRY(cudaMemcpyAsync(h_out, w.result.p, sizeof(ge_ext) * nsets, cudaMemcpyDeviceToHost, st));
+    if (ctx->time_accum) {  // diagnostic mode: synchronous, reads back the entry count
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (ctx->time_accum) {
-            CUDA_TRY(cudaEventElapsedTime(&ctx->last_accum_ms, ctx->ev_a, ctx->ev_b));
-            uint32_t ne = 0;
-            CUDA_TRY(cudaMemcpy(&ne, w.bucket_off.p + G, 4, cudaMemcpyDeviceToHost));
-            ctx->last_entries = ne;
-        }
+        CUDA_TRY(cudaEventElapsedTime(&ctx->last_accum_ms, ctx->ev_a, ctx->ev_b));
+        uint32_t ne = 0;
+        CUDA_TRY(cudaMemcpy(&ne, w.bucket_off.p + G, 4, cudaMemcpyDeviceToHost));
+        ctx->last_entries = ne;
+        ctx->sum_accum_ms += ctx->last_accum_ms;
+        ctx->sum_entries += ne;
     }
     return BPG_OK;
 }

@@ -1,0 +1,165 @@
+// Point-side helper kernels of the R1CS driver: batched Pedersen commitments, batched ristretto
+// (de)compression and the small "dynamic point" MSM of the verifier (points that are not generators:
+// A_I1, A_O1, S1, V_j, T_k, L_k, R_k).
+//
+// Replaces dalek `PedersenGens::commit` (/root/reference/src/gadget.rs:32,
+// /root/reference/src/commitments.rs:28,40 -- row a1/f2), `CompressedRistretto::decompress` inside
+// `Verifier::verify` (/root/reference/src/verify.rs:71 -- row a12/K8) and the non-generator part of
+// `optional_multiscalar_mul`.  Latency-bound kernels (one thread per point): kept off the critical
+// path by running beside the fixed-base MSM.
+#include "kernels.hpp"
+
+// radix-16 signed digits, d[i] in [-8, 8], sum d[i] 16^i = s  (s < 2^255)
+__device__ __forceinline__ void sc_radix16(const sc& s, int8_t d[64]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[8 * i + k] = (int8_t)((s.v[i] >> (4 * k)) & 15u);
+    }
+    int carry = 0;
+    for (int i = 0; i < 63; i++) {
+        int v = d[i] + carry;
+        carry = (v + 8) >> 4;
+        d[i] = (int8_t)(v - (carry << 4));
+    }
+    d[63] = (int8_t)(d[63] + carry);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pedersen: table ped[(p*64 + w)*8 + (m-1)] = m * 16^w * P_p  (affine Niels), p in {B, B_blinding}
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pedersen_table(const ge_ext* __restrict__ gens_ext, uint32_t idxB,
+                                                        ge_niels* __restrict__ ped) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 128) return;
+    const uint32_t p = t >> 6, w = t & 63;
+    ge_ext base = gens_ext[idxB + p];
+#pragma unroll 1
+    for (uint32_t k = 0; k < 4 * w; k++) base = ge_dbl(base);
+    ge_ext m = base;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        ped[t * 8 + k] = ge_to_niels(m, fe_invert(m.Z));
+        m = ge_add(m, base);
+    }
+}
+
+__global__ void __launch_bounds__(64) k_pedersen(const ge_niels* __restrict__ ped, const sc* __restrict__ v,
+                                                 const sc* __restrict__ r, ge_ext* __restrict__ out, uint32_t k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    ge_ext acc = ge_identity();
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+        int8_t d[64];
+        sc_radix16(p ? r[i] : v[i], d);
+#pragma unroll 1
+        for (int w = 0; w < 64; w++) {
+            int dv = d[w];
+            if (dv != 0) {
+                int mag = dv < 0 ? -dv : dv;
+                acc = ge_madd(acc, ped[(p * 64 + w) * 8 + (mag - 1)], dv < 0);
+            }
+        }
+    }
+    out[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// codec batches
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_compress_batch(const ge_ext* __restrict__ in, uint8_t* __restrict__ out,
+                                                       uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    ge_ristretto_compress(b, in[i]);
+    for (int k = 0; k < 32; k++) out[32 * (size_t)i + k] = b[k];
+}
+__global__ void __launch_bounds__(64) k_decompress_batch(const uint8_t* __restrict__ in, ge_ext* __restrict__ out,
+                                                         uint32_t n, uint32_t* __restrict__ fail) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    for (int k = 0; k < 32; k++) b[k] = in[32 * (size_t)i + k];
+    ge_ext p;
+    if (!ge_ristretto_decompress(&p, b)) {
+        atomicAdd(fail, 1u);
+        p = ge_identity();
+    }
+    out[i] = p;
+}
+
+// ------------------------------------------------------------------------------------------
+// dynamic-point MSM: thread per point, radix-16 signed windows, 8-entry table in local memory
+// ------------------------------------------------------------------------------------------
+#define DYN_THREADS 64
+__device__ __forceinline__ void dyn_block_reduce(ge_ext* sh, const ge_ext& mine, uint32_t tid) {
+    sh[tid] = mine;
+    __syncthreads();
+    for (uint32_t s = DYN_THREADS >> 1; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] = ge_add(sh[tid], sh[tid + s]);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_mul(const ge_ext* __restrict__ pts, const sc* __restrict__ s,
+                                                         uint32_t n, ge_ext* __restrict__ blockres) {
+    __shared__ ge_ext sh[DYN_THREADS];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    ge_ext acc = ge_identity();
+    if (i < n) {
+        ge_ext tbl[8];
+        tbl[0] = pts[i];
+#pragma unroll 1
+        for (int k = 1; k < 8; k++) tbl[k] = ge_add(tbl[k - 1], tbl[0]);
+        int8_t d[64];
+        sc_radix16(s[i], d);
+#pragma unroll 1
+        for (int w = 63; w >= 0; w--) {
+            if (w != 63) {
+                acc = ge_dbl(acc);
+                acc = ge_dbl(acc);
+                acc = ge_dbl(acc);
+                acc = ge_dbl(acc);
+            }
+            int dv = d[w];
+            if (dv != 0) {
+                int mag = dv < 0 ? -dv : dv;
+                ge_ext q = tbl[mag - 1];
+                if (dv < 0) q = ge_neg(q);
+                acc = ge_add(acc, q);
+            }
+        }
+    }
+    dyn_block_reduce(sh, acc, threadIdx.x);
+    if (threadIdx.x == 0) blockres[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_final(const ge_ext* __restrict__ blockres, uint32_t nblocks,
+                                                           ge_ext* __restrict__ out) {
+    __shared__ ge_ext sh[DYN_THREADS];
+    ge_ext acc = ge_identity();
+    for (uint32_t b = threadIdx.x; b < nblocks; b += DYN_THREADS) acc = ge_add(acc, blockres[b]);
+    dyn_block_reduce(sh, acc, threadIdx.x);
+    if (threadIdx.x == 0) *out = sh[0];
+}
+__global__ void k_add2(const ge_ext* a, const ge_ext* b, ge_ext* out) { *out = ge_add(*a, *b); }
+
+// ------------------------------------------------------------------------------------------
+void pk_pedersen_table(cudaStream_t st, const ge_ext* gens_ext, uint32_t idxB, ge_niels* ped) {
+    k_pedersen_table<<<1, 128, 0, st>>>(gens_ext, idxB, ped);
+}
+void pk_pedersen(cudaStream_t st, const ge_niels* ped, const sc* v, const sc* r, ge_ext* out, uint32_t k) {
+    if (k) k_pedersen<<<(k + 63) / 64, 64, 0, st>>>(ped, v, r, out, k);
+}
+void pk_compress(cudaStream_t st, const ge_ext* in, uint8_t* out, uint32_t n) {
+    if (n) k_compress_batch<<<(n + 63) / 64, 64, 0, st>>>(in, out, n);
+}
+void pk_decompress(cudaStream_t st, const uint8_t* in, ge_ext* out, uint32_t n, uint32_t* fail) {
+    if (n) k_decompress_batch<<<(n + 63) / 64, 64, 0, st>>>(in, out, n, fail);
+}
+void pk_dyn_msm(cudaStream_t st, const ge_ext* pts, const sc* s, uint32_t n, ge_ext* blockres, ge_ext* out) {
+    uint32_t blocks = n ? (n + DYN_THREADS - 1) / DYN_THREADS : 1;
+    k_dyn_mul<<<blocks, DYN_THREADS, 0, st>>>(pts, s, n, blockres);
+    k_dyn_final<<<1, DYN_THREADS, 0, st>>>(blockres, blocks, out);
+}
+void pk_add2(cudaStream_t st, const ge_ext* a, const ge_ext* b, ge_ext* out) { k_add2<<<1, 1, 0, st>>>(a, b, out); }

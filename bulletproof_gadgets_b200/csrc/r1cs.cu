@@ -1,0 +1,960 @@
+// R1CS constraint system + the Bulletproofs prover / verifier protocol drivers.
+//
+// Replaces, from the FairAds fork of dalek bulletproofs 2.1.0 (/root/reference/Cargo.lock:78-80, not
+// vendored): r1cs::Prover::{new,commit,multiply,allocate_multiplier,constrain,prove},
+// r1cs::Verifier::{new,commit,...,verify}, InnerProductProof::{create,verification_scalars},
+// R1CSProof::{to_bytes,from_bytes} -- called from /root/reference/src/prove.rs:47,79-81,
+// /root/reference/src/verify.rs:46,53,71, /root/reference/src/gadget.rs:32 and
+// /root/reference/src/cs_buffer.rs:89-116,173-199.
+//
+// Division of labour: the Merlin transcript, the sequential TranscriptRng stream and a handful of
+// per-proof challenge scalars stay on the host; every vector (a_L.., s_L.., w_L.., l, r, IPP state)
+// lives in HBM and every group operation is a fixed-base MSM over [G | H | B | B_blinding].
+// The IPP never folds points: round k's L and R are ONE two-bucket-set MSM over the original
+// generators with scalars a_j * sG_i / b_j * sH_i, where sG/sH carry the folded challenge products.
+// Identical group elements, hence identical proof bytes.
+#include <stdlib.h>
+
+#include <array>
+#include <random>
+
+#include "ctx.hpp"
+#include "host_sc.hpp"
+#include "kernels.hpp"
+#include "merlin.hpp"
+
+using bpg::Scalar;
+
+enum { V_COMMITTED = 0, V_LEFT = 1, V_RIGHT = 2, V_OUT = 3, V_ONE = 4 };
+static inline uint32_t var_kind(uint32_t v) { return v >> 29; }
+static inline uint32_t var_idx(uint32_t v) { return v & ((1u << 29) - 1); }
+
+// ------------------------------------------------------------------------------------------
+// reusable device vectors
+// ------------------------------------------------------------------------------------------
+struct ProofWork {
+    DevBuf<sc> aL, aR, aO, sL, sR, w, ypow, yinv, zpow, l1, r0, r1, r3, lvec, rvec, sG, sH, mG, mH, partial, small;
+    DevBuf<sc> vbl, col_coef, dyn_s, ped_in;
+    DevBuf<uint32_t> col_start, col_row, fail;
+    DevBuf<uint8_t> wide, dyn_enc;
+    DevBuf<ge_ext> dyn_pts, dyn_blk;
+    uint8_t* h_pin = nullptr;  // pinned staging
+    size_t h_pin_cap = 0;
+    int pin(size_t n) {
+        if (n <= h_pin_cap) return BPG_OK;
+        if (h_pin) cudaFreeHost(h_pin);
+        h_pin = nullptr;
+        h_pin_cap = 0;
+        CUDA_TRY(cudaMallocHost((void**)&h_pin, n + n / 8 + 4096));
+        h_pin_cap = n + n / 8 + 4096;
+        return BPG_OK;
+    }
+};
+void r1cs_release_work(bpg_ctx* ctx) {
+    ProofWork* p = ctx->pw;
+    if (!p) return;
+    DevBuf<sc>* bs[] = {&p->aL, &p->aR, &p->aO, &p->sL, &p->sR, &p->w, &p->ypow, &p->yinv, &p->zpow, &p->l1, &p->r0,
+                        &p->r1, &p->r3, &p->lvec, &p->rvec, &p->sG, &p->sH, &p->mG, &p->mH, &p->partial, &p->small,
+                        &p->vbl, &p->col_coef, &p->dyn_s, &p->ped_in};
+    for (auto* b : bs) b->release();
+    p->col_start.release();
+    p->col_row.release();
+    p->fail.release();
+    p->wide.release();
+    p->dyn_enc.release();
+    p->dyn_pts.release();
+    p->dyn_blk.release();
+    if (p->h_pin) cudaFreeHost(p->h_pin);
+    delete p;
+    ctx->pw = nullptr;
+}
+static ProofWork* work(bpg_ctx* ctx) {
+    if (!ctx->pw) ctx->pw = new ProofWork();
+    return ctx->pw;
+}
+
+// wide (64-byte) draws -> canonical scalars on the device
+__global__ void __launch_bounds__(256) k_wide_reduce(const uint8_t* __restrict__ wide, sc* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* p = reinterpret_cast<const uint4*>(wide + 64 * (size_t)i);
+    uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+    sc lo, hi;
+    lo.v[0] = a.x, lo.v[1] = a.y, lo.v[2] = a.z, lo.v[3] = a.w, lo.v[4] = b.x, lo.v[5] = b.y, lo.v[6] = b.z, lo.v[7] = b.w;
+    hi.v[0] = c.x, hi.v[1] = c.y, hi.v[2] = c.z, hi.v[3] = c.w, hi.v[4] = d.x, hi.v[5] = d.y, hi.v[6] = d.z, hi.v[7] = d.w;
+    const uint32_t Rl[8] = SC_R_LIMBS;
+    out[i] = sc_add(sc_reduce(lo), sc_mul(hi, sc_const(Rl)));
+}
+
+// ------------------------------------------------------------------------------------------
+// constraint storage (host)
+// ------------------------------------------------------------------------------------------
+struct ConstraintStore {
+    std::vector<uint32_t> term_var;
+    std::vector<sc> term_coef;  // canonical
+    std::vector<uint32_t> row_start{0};
+    size_t num_constraints() const { return row_start.size() - 1; }
+    void begin() {}
+    void term(uint32_t var, const sc& coef) {
+        term_var.push_back(var);
+        term_coef.push_back(coef);
+    }
+    void end() { row_start.push_back((uint32_t)term_var.size()); }
+    int add_lc(const uint32_t* vars, const uint8_t* coef32, size_t n) {
+        for (size_t i = 0; i < n; i++) {
+            if (coef32[32 * i + 31] & 0x80) {
+                bpg_set_error("coefficient %zu has bit 255 set", i);
+                return BPG_E_ARG;
+            }
+            term(vars[i], Scalar::from_bytes_mod_order(coef32 + 32 * i).s);
+        }
+        return BPG_OK;
+    }
+};
+
+// transposed (by target) form of the constraints for the flatten kernel.
+// targets: [wL(n) | wR(n) | wO(n) | wV(m) | wc]
+struct Csc {
+    std::vector<uint32_t> col_start, col_row;
+    std::vector<sc> col_coef;
+    uint32_t nt = 0;
+};
+static int build_csc(const ConstraintStore& cs, uint32_t n, uint32_t m, bool with_one, Csc* out) {
+    const uint32_t nt = 3 * n + m + 1;
+    out->nt = nt;
+    out->col_start.assign(nt + 1, 0);
+    const size_t q = cs.num_constraints();
+    auto target = [&](uint32_t v, uint32_t* t) -> bool {
+        uint32_t k = var_kind(v), i = var_idx(v);
+        switch (k) {
+            case V_LEFT: if (i >= n) return false; *t = i; return true;
+            case V_RIGHT: if (i >= n) return false; *t = n + i; return true;
+            case V_OUT: if (i >= n) return false; *t = 2 * n + i; return true;
+            case V_COMMITTED: if (i >= m) return false; *t = 3 * n + i; return true;
+            case V_ONE: *t = 3 * n + m; return true;
+            default: return false;
+        }
+    };
+    for (size_t e = 0; e < cs.term_var.size(); e++) {
+        uint32_t t;
+        if (!target(cs.term_var[e], &t)) {
+            bpg_set_error("constraint term %zu references an unknown variable 0x%08x", e, cs.term_var[e]);
+            return BPG_E_ARG;
+        }
+        if (t == 3 * n + m && !with_one) continue;
+        out->col_start[t + 1]++;
+    }
+    for (uint32_t t = 0; t < nt; t++) out->col_start[t + 1] += out->col_start[t];
+    const uint32_t nnz = out->col_start[nt];
+    out->col_row.resize(nnz ? nnz : 1);
+    out->col_coef.resize(nnz ? nnz : 1);
+    std::vector<uint32_t> cur(out->col_start.begin(), out->col_start.end() - 1);
+    for (size_t j = 0; j < q; j++) {
+        for (uint32_t e = cs.row_start[j]; e < cs.row_start[j + 1]; e++) {
+            uint32_t t;
+            target(cs.term_var[e], &t);
+            if (t == 3 * n + m && !with_one) continue;
+            uint32_t pos = cur[t]++;
+            out->col_row[pos] = (uint32_t)j;
+            out->col_coef[pos] = cs.term_coef[e];
+        }
+    }
+    return BPG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// prover / verifier objects
+// ------------------------------------------------------------------------------------------
+struct bpg_prover {
+    bpg_ctx* ctx;
+    bpg::Transcript* T;
+    ConstraintStore cs;
+    std::vector<sc> aL, aR, aO, v, vbl;                // canonical
+    std::vector<std::array<uint8_t, 32>> vbl_raw;     // as given (rekeys the transcript rng)
+};
+struct bpg_verifier {
+    bpg_ctx* ctx;
+    bpg::Transcript* T;
+    ConstraintStore cs;
+    std::vector<std::array<uint8_t, 32>> V;
+    uint64_t num_vars = 0;
+};
+
+static void os_random(uint8_t out[32]) {
+    std::random_device rd;
+    for (int i = 0; i < 8; i++) {
+        uint32_t x = rd();
+        memcpy(out + 4 * i, &x, 4);
+    }
+}
+static Scalar rng_scalar(bpg::TranscriptRng& rng) {
+    uint8_t b[64];
+    rng.fill_bytes(b, 64);
+    return Scalar::from_bytes_wide(b);
+}
+static Scalar challenge_scalar(bpg::Transcript& T, const char* label) {
+    uint8_t b[64];
+    T.challenge_bytes(label, b, 64);
+    return Scalar::from_bytes_wide(b);
+}
+static void append_scalar(bpg::Transcript& T, const char* label, const Scalar& s) {
+    uint8_t b[32];
+    s.to_bytes(b);
+    T.append_message(label, b, 32);
+}
+static PowTable pow_table(const Scalar& base) {
+    PowTable t;
+    sc p = base.s;
+    for (int k = 0; k < 32; k++) {
+        t.p[k] = p;
+        p = sc_mul(p, p);
+    }
+    return t;
+}
+static uint32_t next_pow2(uint64_t n) {
+    uint32_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+static int ensure_pedersen_table(bpg_ctx* ctx) {
+    int rc = gens_build(ctx, 1);
+    if (rc) return rc;
+    if (ctx->ped && ctx->ped_capacity == ctx->table.capacity) return BPG_OK;
+    if (!ctx->ped) CUDA_TRY(cudaMalloc((void**)&ctx->ped, 1024 * sizeof(ge_niels)));
+    pk_pedersen_table(ctx->stream, ctx->gens_ext, (uint32_t)(2 * ctx->table.capacity), ctx->ped);
+    ctx->launches++;
+    ctx->ped_capacity = ctx->table.capacity;
+    return BPG_OK;
+}
+
+// k Pedersen commitments v_i*B + r_i*B_blinding -> compressed (host pointers, canonical scalars)
+static int pedersen_batch(bpg_ctx* ctx, const sc* v, const sc* r, uint64_t k, uint8_t* out32k) {
+    if (k == 0) return BPG_OK;
+    int rc;
+    if ((rc = ensure_pedersen_table(ctx))) return rc;
+    ProofWork* pw = work(ctx);
+    cudaStream_t st = ctx->stream;
+    if ((rc = pw->ped_in.ensure(2 * k)) || (rc = pw->dyn_pts.ensure(k)) || (rc = pw->dyn_enc.ensure(32 * k)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(pw->ped_in.p, v, 32 * k, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->ped_in.p + k, r, 32 * k, cudaMemcpyHostToDevice, st));
+    pk_pedersen(st, ctx->ped, pw->ped_in.p, pw->ped_in.p + k, pw->dyn_pts.p, (uint32_t)k);
+    ctx->launches++;
+    if (k <= 8) {  // latency path: finish the serial inverse-square-root chain on the host
+        ge_ext h[8];
+        if ((rc = fetch_points(ctx, pw->dyn_pts.p, (uint32_t)k, h))) return rc;
+        for (uint64_t i = 0; i < k; i++) host_ristretto_compress(out32k + 32 * i, h[i]);
+    } else {
+        pk_compress(st, pw->dyn_pts.p, pw->dyn_enc.p, (uint32_t)k);
+        ctx->launches++;
+        CUDA_TRY(cudaMemcpyAsync(out32k, pw->dyn_enc.p, 32 * k, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return BPG_OK;
+}
+
+static void seg_push(MsmSegments& segs, const sc* p, uint64_t base, uint64_t n, uint32_t set, uint32_t mode,
+                     uint32_t period) {
+    if (!p || n == 0) return;
+    MsmSegment& s = segs.seg[segs.nseg++];
+    s.scalars = reinterpret_cast<const uint32_t*>(p);
+    s.point_base = (uint32_t)base;
+    s.count = (uint32_t)n;
+    s.set_id = set;
+    s.mode = mode;
+    s.period = period;
+    segs.total += (uint32_t)n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Prover::prove
+// ------------------------------------------------------------------------------------------
+static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_t>* proof_out) {
+    bpg_ctx* ctx = P->ctx;
+    bpg::Transcript& T = *P->T;
+    cudaStream_t st = ctx->stream;
+    ProofWork* pw = work(ctx);
+    int rc;
+    const uint32_t n = (uint32_t)P->aL.size(), m = (uint32_t)P->v.size();
+    const uint32_t npad = next_pow2(n ? n : 1);
+    const uint32_t q = (uint32_t)P->cs.num_constraints();
+    uint32_t lg = 0;
+    while ((1u << lg) < npad) lg++;
+
+    T.append_u64("m", m);
+    uint8_t seed[32];
+    if (seed32) memcpy(seed, seed32, 32); else os_random(seed);
+    std::vector<const uint8_t*> wit;
+    wit.reserve(m);
+    for (auto& b : P->vbl_raw) wit.push_back(b.data());
+    bpg::TranscriptRng rng = T.build_rng(wit, seed);
+
+    if ((rc = gens_build(ctx, npad)) || (rc = ensure_pedersen_table(ctx))) return rc;
+    const uint64_t cap = ctx->table.capacity;
+    const uint64_t iB = 2 * cap, iBb = 2 * cap + 1;
+
+    // device vectors
+    const size_t nn = npad;
+    if ((rc = pw->aL.ensure(nn)) || (rc = pw->aR.ensure(nn)) || (rc = pw->aO.ensure(nn)) || (rc = pw->sL.ensure(nn)) ||
+        (rc = pw->sR.ensure(nn)) || (rc = pw->w.ensure(3 * (size_t)n + m + 1)) || (rc = pw->ypow.ensure(nn)) ||
+        (rc = pw->yinv.ensure(nn)) || (rc = pw->zpow.ensure(q + 1)) || (rc = pw->l1.ensure(nn)) ||
+        (rc = pw->r0.ensure(nn)) || (rc = pw->r1.ensure(nn)) || (rc = pw->r3.ensure(nn)) ||
+        (rc = pw->lvec.ensure(nn)) || (rc = pw->rvec.ensure(nn)) || (rc = pw->sG.ensure(nn)) ||
+        (rc = pw->sH.ensure(nn)) || (rc = pw->mG.ensure(nn)) || (rc = pw->mH.ensure(nn)) ||
+        (rc = pw->partial.ensure(SK_PARTIAL_SCALARS)) || (rc = pw->small.ensure(64)) ||
+        (rc = pw->vbl.ensure(m + 1)) || (rc = pw->wide.ensure(128 * (size_t)n + 64)) ||
+        (rc = ctx->d_points.ensure(64)))
+        return rc;
+    sc* small = pw->small.p;  // [0..2] blindings, [8..13] t1..t6, [16] t2_blinding, [20..21] cw, [24..25] a,b
+    ge_ext* slots = ctx->d_points.p;
+
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(pw->aL.p, P->aL.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pw->aR.p, P->aR.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pw->aO.p, P->aO.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    if (m) CUDA_TRY(cudaMemcpyAsync(pw->vbl.p, P->vbl.data(), 32 * (size_t)m, cudaMemcpyHostToDevice, st));
+
+    // rng order: i, o, s blindings, then s_L[0..n), s_R[0..n)
+    const Scalar i_bl = rng_scalar(rng), o_bl = rng_scalar(rng), s_bl = rng_scalar(rng);
+    sc bl[3] = {i_bl.s, o_bl.s, s_bl.s};
+    CUDA_TRY(cudaMemcpyAsync(small, bl, 96, cudaMemcpyHostToDevice, st));
+
+    MsmSegments segs;
+    memset(&segs, 0, sizeof segs);
+    seg_push(segs, pw->aL.p, 0, n, 0, 0, 1);
+    seg_push(segs, pw->aR.p, cap, n, 0, 0, 1);
+    seg_push(segs, small + 0, iBb, 1, 0, 0, 1);
+    if ((rc = msm_run(ctx, segs, 1, slots + 0))) return rc;  // A_I1
+    memset(&segs, 0, sizeof segs);
+    seg_push(segs, pw->aO.p, 0, n, 0, 0, 1);
+    seg_push(segs, small + 1, iBb, 1, 0, 0, 1);
+    if ((rc = msm_run(ctx, segs, 1, slots + 1))) return rc;  // A_O1
+
+    // the sequential STROBE stream runs on the host while the two MSMs above execute
+    if (n) {
+        if ((rc = pw->pin(128 * (size_t)n))) return rc;
+        for (uint32_t i = 0; i < 2 * n; i++) rng.fill_bytes(pw->h_pin + 64 * (size_t)i, 64);
+        CUDA_TRY(cudaMemcpyAsync(pw->wide.p, pw->h_pin, 128 * (size_t)n, cudaMemcpyHostToDevice, st));
+        k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p, pw->sL.p, n);
+        k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p + 64 * (size_t)n, pw->sR.p, n);
+        ctx->launches += 2;
+    }
+    memset(&segs, 0, sizeof segs);
+    seg_push(segs, pw->sL.p, 0, n, 0, 0, 1);
+    seg_push(segs, pw->sR.p, cap, n, 0, 0, 1);
+    seg_push(segs, small + 2, iBb, 1, 0, 0, 1);
+    if ((rc = msm_run(ctx, segs, 1, slots + 2))) return rc;  // S1
+
+    // transposed constraints (host work overlapping the S1 MSM)
+    Csc csc;
+    if ((rc = build_csc(P->cs, n, m, false, &csc))) return rc;
+    const uint32_t nnz = csc.col_start[csc.nt];
+    if ((rc = pw->col_start.ensure(csc.nt + 1)) || (rc = pw->col_row.ensure(nnz + 1)) ||
+        (rc = pw->col_coef.ensure(nnz + 1)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(pw->col_start.p, csc.col_start.data(), 4 * (size_t)(csc.nt + 1), cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CUDA_TRY(cudaMemcpyAsync(pw->col_row.p, csc.col_row.data(), 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pw->col_coef.p, csc.col_coef.data(), 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+
+    ge_ext hp[8];
+    if ((rc = fetch_points(ctx, slots, 3, hp))) return rc;
+    uint8_t A_I1[32], A_O1[32], S1[32];
+    host_ristretto_compress(A_I1, hp[0]);
+    host_ristretto_compress(A_O1, hp[1]);
+    host_ristretto_compress(S1, hp[2]);
+    static const uint8_t ZERO32[32] = {0};
+    T.append_message("A_I1", A_I1, 32);
+    T.append_message("A_O1", A_O1, 32);
+    T.append_message("S1", S1, 32);
+    T.append_message("dom-sep", reinterpret_cast<const uint8_t*>("r1cs-1phase"), 11);
+    T.append_message("A_I2", ZERO32, 32);
+    T.append_message("A_O2", ZERO32, 32);
+    T.append_message("S2", ZERO32, 32);
+    const Scalar y = challenge_scalar(T, "y"), z = challenge_scalar(T, "z");
+    const Scalar y_inv = y.invert();
+
+    sk_powers(st, pw->ypow.p, pow_table(y), npad, 0);
+    sk_powers(st, pw->yinv.p, pow_table(y_inv), npad, 0);
+    sk_powers(st, pw->zpow.p, pow_table(z), q, 1);
+    sc* wL = pw->w.p;
+    sc* wR = wL + n;
+    sc* wO = wR + n;
+    sc* wV = wO + n;
+    sk_flatten(st, pw->col_start.p, pw->col_row.p, pw->col_coef.p, pw->zpow.p, pw->w.p, csc.nt - 1, 3 * n);
+    sk_lr_poly(st, pw->aL.p, pw->aR.p, pw->aO.p, pw->sL.p, pw->sR.p, wL, wR, wO, pw->ypow.p, pw->yinv.p, pw->l1.p,
+               pw->r0.p, pw->r1.p, pw->r3.p, pw->partial.p, small + 8, n);
+    sk_dot(st, wV, pw->vbl.p, m, small + 16);
+    ctx->launches += 7;
+    sc th[9];
+    CUDA_TRY(cudaMemcpyAsync(th, small + 8, 9 * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const Scalar t1 = Scalar::from_sc(th[0]), t2 = Scalar::from_sc(th[1]), t3 = Scalar::from_sc(th[2]),
+                 t4 = Scalar::from_sc(th[3]), t5 = Scalar::from_sc(th[4]), t6 = Scalar::from_sc(th[5]);
+    const Scalar tb2 = Scalar::from_sc(th[8]);
+
+    const Scalar tb1 = rng_scalar(rng), tb3 = rng_scalar(rng), tb4 = rng_scalar(rng), tb5 = rng_scalar(rng),
+                 tb6 = rng_scalar(rng);
+    sc tv[5] = {t1.s, t3.s, t4.s, t5.s, t6.s}, tr[5] = {tb1.s, tb3.s, tb4.s, tb5.s, tb6.s};
+    uint8_t Tc[5][32];
+    if ((rc = pedersen_batch(ctx, tv, tr, 5, &Tc[0][0]))) return rc;
+    T.append_message("T_1", Tc[0], 32);
+    T.append_message("T_3", Tc[1], 32);
+    T.append_message("T_4", Tc[2], 32);
+    T.append_message("T_5", Tc[3], 32);
+    T.append_message("T_6", Tc[4], 32);
+    const Scalar u = challenge_scalar(T, "u"), x = challenge_scalar(T, "x");
+
+    auto poly6 = [&](const Scalar& c1, const Scalar& c2, const Scalar& c3, const Scalar& c4, const Scalar& c5,
+                     const Scalar& c6) { return x * (c1 + x * (c2 + x * (c3 + x * (c4 + x * (c5 + x * c6))))); };
+    const Scalar t_x = poly6(t1, t2, t3, t4, t5, t6);
+    const Scalar t_x_blinding = poly6(tb1, tb2, tb3, tb4, tb5, tb6);
+    const Scalar e_blinding = x * (i_bl + x * (o_bl + x * s_bl));
+
+    sk_eval_lr(st, pw->l1.p, pw->aO.p, pw->sL.p, pw->r0.p, pw->r1.p, pw->r3.p, pw->ypow.p, x.s, pw->lvec.p,
+               pw->rvec.p, n, npad);
+    append_scalar(T, "t_x", t_x);
+    append_scalar(T, "t_x_blinding", t_x_blinding);
+    append_scalar(T, "e_blinding", e_blinding);
+    const Scalar w = challenge_scalar(T, "w");
+
+    // ---- inner-product argument (InnerProductProof::create) ----
+    T.append_message("dom-sep", reinterpret_cast<const uint8_t*>("ipp v1"), 6);
+    T.append_u64("n", npad);
+    sk_ipp_init(st, pw->sG.p, pw->sH.p, pw->yinv.p, u.s, n, npad);
+    ctx->launches += 2;
+    std::vector<uint8_t> LR(64 * (size_t)lg);
+    uint32_t nk = npad;
+    for (uint32_t round = 0; round < lg; round++, nk >>= 1) {
+        sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
+                             small + 20, w.s, npad, nk);
+        ctx->launches += 3;
+        memset(&segs, 0, sizeof segs);
+        seg_push(segs, pw->mG.p, 0, npad, 0, 1, nk);
+        seg_push(segs, pw->mH.p, cap, npad, 0, 2, nk);
+        seg_push(segs, small + 20, iB, 1, 0, 0, 1);  // c_L * w on B  (Q = w*B)
+        seg_push(segs, small + 21, iB, 1, 1, 0, 1);  // c_R * w on B
+        if ((rc = msm_run(ctx, segs, 2, slots + 4))) return rc;
+        if ((rc = fetch_points(ctx, slots + 4, 2, hp))) return rc;
+        uint8_t* Lc = LR.data() + 64 * (size_t)round;
+        host_ristretto_compress(Lc, hp[0]);
+        host_ristretto_compress(Lc + 32, hp[1]);
+        T.append_message("L", Lc, 32);
+        T.append_message("R", Lc + 32, 32);
+        const Scalar uk = challenge_scalar(T, "u");
+        const Scalar uk_inv = uk.invert();
+        sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, npad, nk);
+        ctx->launches++;
+    }
+    sc ab[2];
+    CUDA_TRY(cudaMemcpyAsync(&ab[0], pw->lvec.p, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&ab[1], pw->rvec.p, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+
+    // ---- R1CSProof::to_bytes (1-phase) ----
+    std::vector<uint8_t>& o = *proof_out;
+    o.clear();
+    o.push_back(0);
+    auto put = [&](const uint8_t* b) { o.insert(o.end(), b, b + 32); };
+    auto puts = [&](const Scalar& s) {
+        uint8_t b[32];
+        s.to_bytes(b);
+        put(b);
+    };
+    put(A_I1);
+    put(A_O1);
+    put(S1);
+    for (int k = 0; k < 5; k++) put(Tc[k]);
+    puts(t_x);
+    puts(t_x_blinding);
+    puts(e_blinding);
+    o.insert(o.end(), LR.begin(), LR.end());
+    puts(Scalar::from_sc(ab[0]));
+    puts(Scalar::from_sc(ab[1]));
+    return BPG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Verifier::verify
+// ------------------------------------------------------------------------------------------
+struct ParsedProof {
+    uint8_t A_I1[32], A_O1[32], S1[32], A_I2[32], A_O2[32], S2[32], T1[32], T3[32], T4[32], T5[32], T6[32];
+    Scalar t_x, t_x_blinding, e_blinding, a, b;
+    std::vector<std::array<uint8_t, 32>> Lv, Rv;
+};
+static int parse_proof(const uint8_t* p, size_t len, ParsedProof* out) {
+    if (len == 0) return BPG_E_FORMAT;
+    const uint8_t version = p[0];
+    const uint8_t* body = p + 1;
+    size_t blen = len - 1;
+    if (blen % 32 != 0) return BPG_E_FORMAT;
+    size_t minlen;
+    if (version == 0) minlen = 11 * 32;
+    else if (version == 1) minlen = 14 * 32;
+    else return BPG_E_FORMAT;
+    if (blen < minlen) return BPG_E_FORMAT;
+    size_t pos = 0;
+    auto rd = [&](uint8_t* dst) {
+        memcpy(dst, body + pos, 32);
+        pos += 32;
+    };
+    auto rds = [&](Scalar* s) -> bool {
+        *s = Scalar::from_bytes_raw(body + pos);
+        pos += 32;
+        return s->is_canonical();
+    };
+    rd(out->A_I1);
+    rd(out->A_O1);
+    rd(out->S1);
+    if (version == 0) {
+        memset(out->A_I2, 0, 32);
+        memset(out->A_O2, 0, 32);
+        memset(out->S2, 0, 32);
+    } else {
+        rd(out->A_I2);
+        rd(out->A_O2);
+        rd(out->S2);
+    }
+    rd(out->T1);
+    rd(out->T3);
+    rd(out->T4);
+    rd(out->T5);
+    rd(out->T6);
+    if (!rds(&out->t_x) || !rds(&out->t_x_blinding) || !rds(&out->e_blinding)) return BPG_E_FORMAT;
+    const size_t ne = (blen - pos) / 32;
+    if (ne < 2 || (ne - 2) % 2 != 0) return BPG_E_FORMAT;
+    const size_t lg = (ne - 2) / 2;
+    if (lg >= 32) return BPG_E_FORMAT;
+    out->Lv.resize(lg);
+    out->Rv.resize(lg);
+    for (size_t k = 0; k < lg; k++) {
+        rd(out->Lv[k].data());
+        rd(out->Rv[k].data());
+    }
+    if (!rds(&out->a) || !rds(&out->b)) return BPG_E_FORMAT;
+    return BPG_OK;
+}
+static bool is_zero32(const uint8_t* b) {
+    uint8_t o = 0;
+    for (int i = 0; i < 32; i++) o |= b[i];
+    return o == 0;
+}
+
+static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_len, const uint8_t* seed32) {
+    bpg_ctx* ctx = Vf->ctx;
+    bpg::Transcript& T = *Vf->T;
+    cudaStream_t st = ctx->stream;
+    ProofWork* pw = work(ctx);
+    int rc;
+    ParsedProof pr;
+    if ((rc = parse_proof(proof, proof_len, &pr))) {
+        bpg_set_error("malformed proof bytes");
+        return rc;
+    }
+    const uint32_t n = (uint32_t)Vf->num_vars, m = (uint32_t)Vf->V.size();
+    const uint32_t npad = next_pow2(n ? n : 1);
+    const uint32_t q = (uint32_t)Vf->cs.num_constraints();
+    uint32_t lg = 0;
+    while ((1u << lg) < npad) lg++;
+
+    T.append_u64("m", m);
+#define VALIDATE_APPEND(label, pt)                     \
+    do {                                               \
+        if (is_zero32(pt)) return BPG_E_VERIFY;        \
+        T.append_message(label, pt, 32);               \
+    } while (0)
+    VALIDATE_APPEND("A_I1", pr.A_I1);
+    VALIDATE_APPEND("A_O1", pr.A_O1);
+    VALIDATE_APPEND("S1", pr.S1);
+    T.append_message("dom-sep", reinterpret_cast<const uint8_t*>("r1cs-1phase"), 11);
+    T.append_message("A_I2", pr.A_I2, 32);
+    T.append_message("A_O2", pr.A_O2, 32);
+    T.append_message("S2", pr.S2, 32);
+    const Scalar y = challenge_scalar(T, "y"), z = challenge_scalar(T, "z");
+    VALIDATE_APPEND("T_1", pr.T1);
+    VALIDATE_APPEND("T_3", pr.T3);
+    VALIDATE_APPEND("T_4", pr.T4);
+    VALIDATE_APPEND("T_5", pr.T5);
+    VALIDATE_APPEND("T_6", pr.T6);
+    const Scalar u = challenge_scalar(T, "u"), x = challenge_scalar(T, "x");
+    append_scalar(T, "t_x", pr.t_x);
+    append_scalar(T, "t_x_blinding", pr.t_x_blinding);
+    append_scalar(T, "e_blinding", pr.e_blinding);
+    const Scalar w = challenge_scalar(T, "w");
+
+    // InnerProductProof::verification_scalars
+    if (pr.Lv.size() != lg) return BPG_E_VERIFY;  // n != 1 << lg_n
+    T.append_message("dom-sep", reinterpret_cast<const uint8_t*>("ipp v1"), 6);
+    T.append_u64("n", npad);
+    std::vector<Scalar> uk(lg);
+    for (uint32_t k = 0; k < lg; k++) {
+        VALIDATE_APPEND("L", pr.Lv[k].data());
+        VALIDATE_APPEND("R", pr.Rv[k].data());
+        uk[k] = challenge_scalar(T, "u");
+    }
+    // batch inversion of [y, u_0 .. u_{lg-1}] (Montgomery's trick)
+    std::vector<Scalar> inv_in(lg + 1), pref(lg + 2), inv_out(lg + 1);
+    inv_in[0] = y;
+    for (uint32_t k = 0; k < lg; k++) inv_in[k + 1] = uk[k];
+    pref[0] = Scalar(1);
+    for (uint32_t k = 0; k <= lg; k++) pref[k + 1] = pref[k] * inv_in[k];
+    Scalar run = pref[lg + 1].invert();
+    for (int k = (int)lg; k >= 0; k--) {
+        inv_out[k] = run * pref[k];
+        run = run * inv_in[k];
+    }
+    const Scalar y_inv = inv_out[0];
+
+    uint8_t seed[32];
+    if (seed32) memcpy(seed, seed32, 32); else os_random(seed);
+    bpg::TranscriptRng rng = T.build_rng({}, seed);
+    const Scalar r = rng_scalar(rng);
+    const Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
+
+    if ((rc = gens_build(ctx, npad))) return rc;
+    const uint64_t cap = ctx->table.capacity;
+    const uint64_t iB = 2 * cap, iBb = 2 * cap + 1;
+
+    Csc csc;
+    if ((rc = build_csc(Vf->cs, n, m, true, &csc))) return rc;
+    const uint32_t nnz = csc.col_start[csc.nt];
+    const uint32_t ndyn = 6 + m + 5 + 2 * lg;
+    const size_t nn = npad;
+    if ((rc = pw->w.ensure(3 * (size_t)n + m + 1)) || (rc = pw->yinv.ensure(nn)) || (rc = pw->zpow.ensure(q + 1)) ||
+        (rc = pw->mG.ensure(nn)) || (rc = pw->mH.ensure(nn)) || (rc = pw->partial.ensure(SK_PARTIAL_SCALARS)) ||
+        (rc = pw->small.ensure(64)) || (rc = pw->col_start.ensure(csc.nt + 1)) || (rc = pw->col_row.ensure(nnz + 1)) ||
+        (rc = pw->col_coef.ensure(nnz + 1)) || (rc = pw->dyn_s.ensure(ndyn)) || (rc = pw->dyn_enc.ensure(32 * (size_t)ndyn)) ||
+        (rc = pw->dyn_pts.ensure(ndyn)) || (rc = pw->dyn_blk.ensure(ndyn / 64 + 2)) || (rc = pw->fail.ensure(1)) ||
+        (rc = ctx->d_points.ensure(64)))
+        return rc;
+    sc* small = pw->small.p;  // [0] delta, [1] sB, [2] sBb
+    CUDA_TRY(cudaMemcpyAsync(pw->col_start.p, csc.col_start.data(), 4 * (size_t)(csc.nt + 1), cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CUDA_TRY(cudaMemcpyAsync(pw->col_row.p, csc.col_row.data(), 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pw->col_coef.p, csc.col_coef.data(), 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+    sk_powers(st, pw->yinv.p, pow_table(y_inv), npad, 0);
+    sk_powers(st, pw->zpow.p, pow_table(z), q, 1);
+    sc* wL = pw->w.p;
+    sc* wR = wL + n;
+    sc* wO = wR + n;
+    sc* wV = wO + n;
+    sc* wc = wV + m;
+    sk_flatten(st, pw->col_start.p, pw->col_row.p, pw->col_coef.p, pw->zpow.p, pw->w.p, csc.nt, 3 * n);
+    VerChallenges ch;
+    memset(&ch, 0, sizeof ch);
+    for (uint32_t k = 0; k < lg; k++) {
+        ch.u[k] = uk[k].s;
+        ch.uinv[k] = inv_out[k + 1].s;
+    }
+    ch.x = x.s;
+    ch.a = pr.a.s;
+    ch.b = pr.b.s;
+    ch.u_pad = u.s;
+    sk_ver_scalars(st, ch, wL, wR, wO, pw->yinv.p, pw->mG.p, pw->mH.p, pw->partial.p, small + 0, n, npad, lg);
+    const Scalar w_tab = w * (pr.t_x - pr.a * pr.b);
+    const Scalar sBb = -pr.e_blinding - r * pr.t_x_blinding;
+    // dynamic scalars, in dalek's point order: A_I1 A_O1 S1 A_I2 A_O2 S2 | V | T_1 T_3 T_4 T_5 T_6 | L.. | R..
+    std::vector<sc> hs(ndyn);
+    std::vector<uint8_t> henc(32 * (size_t)ndyn);
+    {
+        const Scalar head[6] = {x, xx, xxx, u * x, u * xx, u * xxx};
+        const uint8_t* hp6[6] = {pr.A_I1, pr.A_O1, pr.S1, pr.A_I2, pr.A_O2, pr.S2};
+        for (int k = 0; k < 6; k++) {
+            hs[k] = head[k].s;
+            memcpy(&henc[32 * k], hp6[k], 32);
+        }
+        for (uint32_t j = 0; j < m; j++) {
+            hs[6 + j] = sc_zero();  // filled on the device (wV_j * r x^2)
+            memcpy(&henc[32 * (6 + j)], Vf->V[j].data(), 32);
+        }
+        const Scalar Ts[5] = {r * x, rxx * x, rxx * xx, rxx * xxx, rxx * xx * xx};
+        const uint8_t* Tp[5] = {pr.T1, pr.T3, pr.T4, pr.T5, pr.T6};
+        for (int k = 0; k < 5; k++) {
+            hs[6 + m + k] = Ts[k].s;
+            memcpy(&henc[32 * (6 + m + k)], Tp[k], 32);
+        }
+        for (uint32_t k = 0; k < lg; k++) {
+            hs[11 + m + k] = (uk[k] * uk[k]).s;
+            memcpy(&henc[32 * (11 + m + k)], pr.Lv[k].data(), 32);
+            hs[11 + m + lg + k] = (inv_out[k + 1] * inv_out[k + 1]).s;
+            memcpy(&henc[32 * (11 + m + lg + k)], pr.Rv[k].data(), 32);
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(pw->dyn_s.p, hs.data(), 32 * (size_t)ndyn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->dyn_enc.p, henc.data(), 32 * (size_t)ndyn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(small + 2, &sBb.s, 32, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(pw->fail.p, 0, 4, st));
+    sk_ver_head(st, wV, wc, small + 0, rxx.s, r.s, xx.s, w_tab.s, pr.t_x.s, pw->dyn_s.p + 6, small + 1, m);
+    pk_decompress(st, pw->dyn_enc.p, pw->dyn_pts.p, ndyn, pw->fail.p);
+    ge_ext* slots = ctx->d_points.p;
+    pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, ndyn, pw->dyn_blk.p, slots + 8);
+    ctx->launches += 10;
+    MsmSegments segs;
+    memset(&segs, 0, sizeof segs);
+    seg_push(segs, pw->mG.p, 0, npad, 0, 0, 1);
+    seg_push(segs, pw->mH.p, cap, npad, 0, 0, 1);
+    seg_push(segs, small + 1, iB, 1, 0, 0, 1);
+    seg_push(segs, small + 2, iBb, 1, 0, 0, 1);
+    if ((rc = msm_run(ctx, segs, 1, slots + 9))) return rc;
+    pk_add2(st, slots + 8, slots + 9, slots + 10);
+    ctx->launches++;
+    uint32_t fail = 0;
+    ge_ext res;
+    CUDA_TRY(cudaMemcpyAsync(&fail, pw->fail.p, 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = fetch_points(ctx, slots + 10, 1, &res))) return rc;
+    CUDA_TRY(cudaGetLastError());
+    if (fail) return BPG_E_VERIFY;  // a point did not decode
+    return host_is_ristretto_identity(res) ? BPG_OK : BPG_E_VERIFY;
+}
+
+// ------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------
+static sc eval_lc(const bpg_prover* p, const uint32_t* vars, const sc* coefs, size_t n, bool* ok) {
+    sc acc = sc_zero();
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t k = var_kind(vars[i]), idx = var_idx(vars[i]);
+        sc val;
+        switch (k) {
+            case V_LEFT: if (idx >= p->aL.size()) { *ok = false; return acc; } val = p->aL[idx]; break;
+            case V_RIGHT: if (idx >= p->aR.size()) { *ok = false; return acc; } val = p->aR[idx]; break;
+            case V_OUT: if (idx >= p->aO.size()) { *ok = false; return acc; } val = p->aO[idx]; break;
+            case V_COMMITTED: if (idx >= p->v.size()) { *ok = false; return acc; } val = p->v[idx]; break;
+            case V_ONE: val = sc_one(); break;
+            default: *ok = false; return acc;
+        }
+        acc = sc_add(acc, sc_mul(coefs[i], val));
+    }
+    return acc;
+}
+
+extern "C" {
+
+int bpg_pedersen_commit_batch(bpg_ctx* ctx, const uint8_t* v32k, const uint8_t* r32k, uint64_t k, uint8_t* out32k) {
+    if (!ctx || (k && (!v32k || !r32k || !out32k))) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<sc> v(k), r(k);
+    for (uint64_t i = 0; i < k; i++) {
+        if ((v32k[32 * i + 31] | r32k[32 * i + 31]) & 0x80) return BPG_E_ARG;
+        v[i] = Scalar::from_bytes_mod_order(v32k + 32 * i).s;
+        r[i] = Scalar::from_bytes_mod_order(r32k + 32 * i).s;
+    }
+    return pedersen_batch(ctx, v.data(), r.data(), k, out32k);
+}
+
+int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars32n, const uint8_t* points32n, uint64_t n, uint8_t out32[32]) {
+    if (!ctx || !out32 || (n && (!scalars32n || !points32n))) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ProofWork* pw = work(ctx);
+    cudaStream_t st = ctx->stream;
+    int rc;
+    std::vector<sc> s(n ? n : 1);
+    for (uint64_t i = 0; i < n; i++) {
+        if (scalars32n[32 * i + 31] & 0x80) return BPG_E_ARG;
+        s[i] = Scalar::from_bytes_mod_order(scalars32n + 32 * i).s;
+    }
+    if ((rc = pw->dyn_s.ensure(n + 1)) || (rc = pw->dyn_enc.ensure(32 * n + 32)) || (rc = pw->dyn_pts.ensure(n + 1)) ||
+        (rc = pw->dyn_blk.ensure(n / 64 + 2)) || (rc = pw->fail.ensure(1)) || (rc = ctx->d_points.ensure(64)))
+        return rc;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(pw->dyn_s.p, s.data(), 32 * n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pw->dyn_enc.p, points32n, 32 * n, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(pw->fail.p, 0, 4, st));
+    pk_decompress(st, pw->dyn_enc.p, pw->dyn_pts.p, (uint32_t)n, pw->fail.p);
+    pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, (uint32_t)n, pw->dyn_blk.p, ctx->d_points.p + 12);
+    ctx->launches += 3;
+    uint32_t fail = 0;
+    ge_ext res;
+    CUDA_TRY(cudaMemcpyAsync(&fail, pw->fail.p, 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = fetch_points(ctx, ctx->d_points.p + 12, 1, &res))) return rc;
+    if (fail) {
+        bpg_set_error("msm: %u point(s) failed to decompress", fail);
+        return BPG_E_VERIFY;
+    }
+    host_ristretto_compress(out32, res);
+    return BPG_OK;
+}
+
+int bpg_prover_new(bpg_ctx* ctx, bpg_transcript* t, bpg_prover** out) {
+    if (!ctx || !t || !out) return BPG_E_ARG;
+    bpg_prover* p = new bpg_prover();
+    p->ctx = ctx;
+    p->T = &t->t;
+    p->T->append_message("dom-sep", reinterpret_cast<const uint8_t*>("r1cs v1"), 7);
+    *out = p;
+    return BPG_OK;
+}
+void bpg_prover_free(bpg_prover* p) { delete p; }
+
+int bpg_prover_commit_batch(bpg_prover* p, const uint8_t* v32k, const uint8_t* vb32k, uint64_t k, uint8_t* V_out32k,
+                            uint32_t* first_var_out) {
+    if (!p || (k && (!v32k || !vb32k || !V_out32k))) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    std::vector<sc> v(k), r(k);
+    for (uint64_t i = 0; i < k; i++) {
+        if ((v32k[32 * i + 31] | vb32k[32 * i + 31]) & 0x80) {
+            bpg_set_error("commit: scalar with bit 255 set");
+            return BPG_E_ARG;
+        }
+        v[i] = Scalar::from_bytes_mod_order(v32k + 32 * i).s;
+        r[i] = Scalar::from_bytes_mod_order(vb32k + 32 * i).s;
+    }
+    int rc = pedersen_batch(p->ctx, v.data(), r.data(), k, V_out32k);
+    if (rc) return rc;
+    if (first_var_out) *first_var_out = (uint32_t)p->v.size();
+    for (uint64_t i = 0; i < k; i++) {
+        p->v.push_back(v[i]);
+        p->vbl.push_back(r[i]);
+        std::array<uint8_t, 32> raw;
+        memcpy(raw.data(), vb32k + 32 * i, 32);
+        p->vbl_raw.push_back(raw);
+        p->T->append_message("V", V_out32k + 32 * i, 32);
+    }
+    return BPG_OK;
+}
+int bpg_prover_commit(bpg_prover* p, const uint8_t v[32], const uint8_t v_blinding[32], uint8_t V_out[32],
+                      uint32_t* var_out) {
+    return bpg_prover_commit_batch(p, v, v_blinding, 1, V_out, var_out);
+}
+
+int bpg_prover_allocate_multiplier(bpg_prover* p, const uint8_t l[32], const uint8_t r[32], uint32_t vars_out[3]) {
+    if (!p || !vars_out) return BPG_E_ARG;
+    if (!l || !r) return BPG_E_MISSING_ASSIGNMENT;
+    if ((l[31] | r[31]) & 0x80) return BPG_E_ARG;
+    const sc ls = Scalar::from_bytes_mod_order(l).s, rs = Scalar::from_bytes_mod_order(r).s;
+    const uint32_t i = (uint32_t)p->aL.size();
+    p->aL.push_back(ls);
+    p->aR.push_back(rs);
+    p->aO.push_back(sc_mul(ls, rs));
+    vars_out[0] = BPG_VAR_LEFT(i);
+    vars_out[1] = BPG_VAR_RIGHT(i);
+    vars_out[2] = BPG_VAR_OUT(i);
+    return BPG_OK;
+}
+
+int bpg_prover_multiply(bpg_prover* p, const uint32_t* lvars, const uint8_t* lcoef32, size_t ln, const uint32_t* rvars,
+                        const uint8_t* rcoef32, size_t rn, uint32_t vars_out[3]) {
+    if (!p || !vars_out) return BPG_E_ARG;
+    const uint32_t i = (uint32_t)p->aL.size();
+    ConstraintStore& cs = p->cs;
+    const size_t mark_v = cs.term_var.size();
+    int rc;
+    // constraint "left - L_i": terms of left, then (-1) L_i ; same for right
+    if ((rc = cs.add_lc(lvars, lcoef32, ln))) return rc;
+    bool ok = true;
+    const sc lval = eval_lc(p, lvars, cs.term_coef.data() + mark_v, ln, &ok);
+    const sc minus_one = sc_neg(sc_one());
+    cs.term(BPG_VAR_LEFT(i), minus_one);
+    cs.end();
+    const size_t mark_r = cs.term_var.size();
+    if (ok && (rc = cs.add_lc(rvars, rcoef32, rn))) return rc;
+    const sc rval = ok ? eval_lc(p, rvars, cs.term_coef.data() + mark_r, rn, &ok) : sc_zero();
+    if (!ok) {
+        bpg_set_error("multiply: linear combination references an unallocated variable");
+        cs.term_var.resize(mark_v);
+        cs.term_coef.resize(mark_v);
+        cs.row_start.pop_back();
+        return BPG_E_ARG;
+    }
+    cs.term(BPG_VAR_RIGHT(i), minus_one);
+    cs.end();
+    p->aL.push_back(lval);
+    p->aR.push_back(rval);
+    p->aO.push_back(sc_mul(lval, rval));
+    vars_out[0] = BPG_VAR_LEFT(i);
+    vars_out[1] = BPG_VAR_RIGHT(i);
+    vars_out[2] = BPG_VAR_OUT(i);
+    return BPG_OK;
+}
+
+int bpg_prover_constrain(bpg_prover* p, const uint32_t* vars, const uint8_t* coef32, size_t n) {
+    if (!p) return BPG_E_ARG;
+    int rc = p->cs.add_lc(vars, coef32, n);
+    if (rc) return rc;
+    p->cs.end();
+    return BPG_OK;
+}
+uint64_t bpg_prover_num_constraints(const bpg_prover* p) { return p ? p->cs.num_constraints() : 0; }
+uint64_t bpg_prover_num_multipliers(const bpg_prover* p) { return p ? p->aL.size() : 0; }
+
+int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!p || !proof_out || !proof_len) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    std::vector<uint8_t> proof;
+    int rc = prover_prove(p, rng_seed32, &proof);
+    if (rc) return rc;
+    if (proof.size() > proof_cap) {
+        bpg_set_error("proof buffer too small: need %zu", proof.size());
+        *proof_len = proof.size();
+        return BPG_E_ARG;
+    }
+    memcpy(proof_out, proof.data(), proof.size());
+    *proof_len = proof.size();
+    return BPG_OK;
+}
+
+int bpg_verifier_new(bpg_ctx* ctx, bpg_transcript* t, bpg_verifier** out) {
+    if (!ctx || !t || !out) return BPG_E_ARG;
+    bpg_verifier* v = new bpg_verifier();
+    v->ctx = ctx;
+    v->T = &t->t;
+    v->T->append_message("dom-sep", reinterpret_cast<const uint8_t*>("r1cs v1"), 7);
+    *out = v;
+    return BPG_OK;
+}
+void bpg_verifier_free(bpg_verifier* v) { delete v; }
+int bpg_verifier_commit(bpg_verifier* v, const uint8_t V[32], uint32_t* var_out) {
+    if (!v || !V) return BPG_E_ARG;
+    std::array<uint8_t, 32> a;
+    memcpy(a.data(), V, 32);
+    if (var_out) *var_out = BPG_VAR_COMMITTED((uint32_t)v->V.size());
+    v->V.push_back(a);
+    v->T->append_message("V", V, 32);
+    return BPG_OK;
+}
+int bpg_verifier_allocate_multiplier(bpg_verifier* v, uint32_t vars_out[3]) {
+    if (!v || !vars_out) return BPG_E_ARG;
+    const uint32_t i = (uint32_t)v->num_vars++;
+    vars_out[0] = BPG_VAR_LEFT(i);
+    vars_out[1] = BPG_VAR_RIGHT(i);
+    vars_out[2] = BPG_VAR_OUT(i);
+    return BPG_OK;
+}
+int bpg_verifier_multiply(bpg_verifier* v, const uint32_t* lvars, const uint8_t* lcoef32, size_t ln,
+                          const uint32_t* rvars, const uint8_t* rcoef32, size_t rn, uint32_t vars_out[3]) {
+    if (!v || !vars_out) return BPG_E_ARG;
+    const uint32_t i = (uint32_t)v->num_vars;
+    int rc;
+    const sc minus_one = sc_neg(sc_one());
+    if ((rc = v->cs.add_lc(lvars, lcoef32, ln))) return rc;
+    v->cs.term(BPG_VAR_LEFT(i), minus_one);
+    v->cs.end();
+    if ((rc = v->cs.add_lc(rvars, rcoef32, rn))) return rc;
+    v->cs.term(BPG_VAR_RIGHT(i), minus_one);
+    v->cs.end();
+    v->num_vars++;
+    vars_out[0] = BPG_VAR_LEFT(i);
+    vars_out[1] = BPG_VAR_RIGHT(i);
+    vars_out[2] = BPG_VAR_OUT(i);
+    return BPG_OK;
+}
+int bpg_verifier_constrain(bpg_verifier* v, const uint32_t* vars, const uint8_t* coef32, size_t n) {
+    if (!v) return BPG_E_ARG;
+    int rc = v->cs.add_lc(vars, coef32, n);
+    if (rc) return rc;
+    v->cs.end();
+    return BPG_OK;
+}
+uint64_t bpg_verifier_num_vars(const bpg_verifier* v) { return v ? v->num_vars : 0; }
+int bpg_verifier_verify(bpg_verifier* v, const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32) {
+    if (!v || !proof) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(v->ctx->device));
+    return verifier_verify(v, proof, proof_len, rng_seed32);
+}
+
+}  // extern "C"
