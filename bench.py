@@ -1,0 +1,262 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json headline: R1CS prove & verify per second on B200 (config 2:
+`BOUND` 64-bit range statements x1024 in ONE R1CS proof, n = 2^17 multipliers, m = 3072 commitments).
+
+One "step" = one pass of the hot path over one statement: m Pedersen commitments + Prover::prove
++ Verifier::verify (accepting).  Three legs:
+  value  constraint system and witness already resident in HBM (bpg_circuit); CUDA events on the
+         library stream; proofs verified inside the timed region.
+  e2e    the same step through the C ABI with HOST buffers (bpg_prover_load_cs / bpg_verifier_load_cs):
+         every host->device copy of witness / constraints and the device->host proof are inside the timer.
+  cpu_baseline  the CPU restatement of dalek's algorithms (oracle/c, 1 core) on the same statement.
+`--impl reference` times that CPU restatement alone with all host cores (the real reference is pure
+Rust and cannot be built in this image: no cargo/rustc, crates not vendored).
+
+N > 1 (torchrun): every rank proves/verifies its own independent statement ("weak" scaling, no
+data-path collective); value = N statements / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "r1cs_prove_verify_per_sec"
+UNIT = "proof+verify/s"
+WORKLOAD = "bounds_check 64-bit x1024 in one R1CS proof (n=2^17 multipliers, m=3072, q=265216)"
+# measured on this pool's B200 by tools/imad_peak.cu (profiles/r01_imad_peak.jsonl): sustained
+# IMAD.WIDE.U32 issue rate, the instruction the field multiplication is built from
+IMAD_WIDE_PEAK_TOPS = 8.157
+IMAD_PER_MADD = 504  # 7 field muls x (64 + 8) 32x32->64 multiply-adds, SURVEY.md 8(d)
+
+
+def _dist():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    return ws, int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.reasons, self.stop_flag, self.max_mhz = gpu_index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def run_reference(args, ws, rank):
+    """CPU restatement (oracle/c) on all host cores; bounded sample: BOUND x128 per worker per step."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from bulletproof_gadgets_b200 import workloads as W
+    from oracle import coracle
+    coracle.lib()
+    sample_count, scale = 128, 8.0  # 1024 / 128; cost is linear in n (Straus / folds / Pippenger per point)
+    cores = os.cpu_count() or 1
+    st = W.bounds_check_statement(sample_count)
+
+    def worker(q_in, q_out):
+        from oracle import coracle as co
+        while True:
+            job = q_in.get()
+            if job is None:
+                return
+            proof, coms = co.prove_flat(st, b"\x07" * 32, cache_gens=False)  # the reference rebuilds generators per run
+            ok = co.verify_flat(st, coms, proof, b"\x09" * 32, cache_gens=False)
+            q_out.put(ok is True)
+
+    q_in, q_out = mp.Queue(), mp.Queue()
+    procs = [mp.Process(target=worker, args=(q_in, q_out)) for _ in range(cores)]
+    for p in procs:
+        p.start()
+
+    def step():
+        for _ in range(cores):
+            q_in.put(1)
+        assert all(q_out.get() for _ in range(cores))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    for _ in procs:
+        q_in.put(None)
+    for p in procs:
+        p.join()
+    value = cores * args.steps / (dt * scale)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "backend": "CPU restatement of dalek's u64 serial algorithms (oracle/c), "
+                       "not the Rust binary (no cargo/rustc in the image)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "BOUND x128 (n=2^14) prove+verify per core per step, generators rebuilt per proof "
+                                       "as the reference does; scaled x1/8 to the x1024 statement (cost linear in n)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--count", type=int, default=1024, help="BOUND statements per proof (1024 = BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    ws, rank, local_rank = _dist()
+    if args.impl == "reference":
+        return run_reference(args, ws, rank)
+
+    import torch
+    import torch.distributed as dist
+    if ws > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import bulletproof_gadgets_b200 as bpg
+    from bulletproof_gadgets_b200 import build, workloads as W
+    build.build_lib()
+    ctx = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
+    st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank)
+    ctx.gens_ensure(st.n)
+    circuit = bpg.Circuit(ctx, st.n, st.m, st.row_start, st.term_var, st.term_coef, st.q).set_witness(st.aL, st.aR)
+    stream = torch.cuda.ExternalStream(ctx.get("stream"), device=torch.device("cuda", local_rank))
+
+    def step_resident(i):
+        seed = (i + 1).to_bytes(32, "little")
+        T = bpg.Transcript(st.label)
+        p = bpg.Prover(ctx, T)
+        coms = [c for c, _ in p.commit_batch(st.v, st.vbl)]
+        p.attach(circuit)
+        proof = p.prove(seed)
+        T2 = bpg.Transcript(st.label)
+        vf = bpg.Verifier(ctx, T2)
+        vf.commit_batch(coms)
+        vf.attach(circuit)
+        if not vf.verify(proof, seed):
+            raise SystemExit("GPU proof did not verify")
+        return proof
+
+    def step_e2e(i):
+        seed = (i + 1).to_bytes(32, "little")
+        proof, coms = W.prove_statement(bpg, ctx, st, seed)
+        if not W.verify_statement(bpg, ctx, st, proof, coms, seed):
+            raise SystemExit("GPU proof did not verify")
+        return proof
+
+    def barrier():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if ws > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.get("launches")
+    ms_res = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = ctx.get("launches") - launches0 - 0
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3) if args.warmup else 0)
+    sampler.stop_flag = True
+
+    # dominant kernel (MSM bucket accumulation): one instrumented step, CUDA events around every launch
+    ctx.set("time_accum", 1)
+    step_resident(10 ** 6)
+    acc_ns, acc_entries = ctx.get("sum_accum_ns"), ctx.get("sum_entries")
+    ctx.set("time_accum", 0)
+
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    per_step_ms = ms_res / args.steps
+    value = ws * args.steps / (ms_res * 1e-3)
+    e2e_value = ws * args.steps / (ms_e2e * 1e-3)
+    achieved = acc_entries * IMAD_PER_MADD / (acc_ns * 1e-9) / 1e12 if acc_ns else None
+    # bytes crossing PCIe per e2e step (counted from the buffers handed to the C ABI)
+    csc_bytes = 4 * (3 * st.n + st.m + 2) + st.nnz * 36
+    h2d = (2 * 32 * st.n + 4 * (st.q + 1) + 36 * st.nnz) * 2 + 2 * 32 * st.m + 32 * st.m  # load_cs x2, commits, V
+    h2d += 3 * 32 * st.n + 2 * csc_bytes + 128 * st.n  # library-internal uploads: a_L/a_R/a_O, transposed constraints x2, rng draws
+    d2h = 32 * st.m + 1505 + 128 * (3 + 2 * 17 + 2)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
+                   "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
+                   "rng": "transcript rng seeded per step; proofs byte-identical to the CPU oracle",
+                   "window_bits": ctx.get("window_bits"), "task_len": 32},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "k_accumulate (MSM bucket accumulation, mixed Edwards adds)", "bound": "imad",
+                     "achieved": achieved, "peak": IMAD_WIDE_PEAK_TOPS, "unit": "T IMAD.WIDE/s",
+                     "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": None,
+                     "peak_source": "tools/imad_peak.cu on this pool (profiles/r01_imad_peak.jsonl); IMAD.WIDE.U32 issues at "
+                                    "28/clk/SM vs 64 for 32-bit IMAD; not in MEASURED_PEAKS.json",
+                     "work": "%d mixed adds x %d IMAD.WIDE" % (acc_entries, IMAD_PER_MADD),
+                     "kernel_ms_per_step": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / per_step_ms},
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        from oracle import coracle
+        t0 = time.perf_counter()
+        p_c, coms_c = coracle.prove_flat(st, (1).to_bytes(32, "little"), cache_gens=False)
+        ok = coracle.verify_flat(st, coms_c, p_c, (1).to_bytes(32, "little"), cache_gens=False)
+        dt = time.perf_counter() - t0
+        same = p_c == step_resident(0)
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "the full statement once (prove+verify, generators rebuilt per run as the reference "
+                                          "does): %.1f s; CPU proof accepted=%s, byte-identical to the GPU proof=%s" % (dt, ok, same)}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,7 @@ import os
 from . import _capi
 from ._capi import BpgError, lib  # noqa: F401
 from .api import (  # noqa: F401
+    Circuit,
     Context,
     LinearCombination,
     Prover,

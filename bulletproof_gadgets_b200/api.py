@@ -185,8 +185,35 @@ class _CS:
         return Variable(arr[0]), Variable(arr[1]), Variable(arr[2])
 
 
+class Circuit:
+    """Device-resident flattened constraint system (+ optional witness): bpg_circuit."""
+
+    def __init__(self, ctx, n, m, row_start, term_var, term_coef, q):
+        self.ctx, self.n, self.m, self.q = ctx, n, m, q
+        self._h = c_void_p()
+        check(lib().bpg_circuit_create(ctx._h, n, m, row_start.ctypes.data, term_var.ctypes.data, term_coef, q,
+                                       byref(self._h)))
+
+    def set_witness(self, aL, aR):
+        assert len(aL) == len(aR) == 32 * self.n
+        check(lib().bpg_circuit_set_witness(self._h, aL or None, aR or None))
+        return self
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bpg_circuit_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class Prover(_CS):
     """bulletproofs::r1cs::Prover (GPU-backed)."""
+
+    def attach(self, circuit):
+        check(lib().bpg_prover_attach(self._h, circuit._h))
+        self._circuit = circuit
 
     def __init__(self, ctx, transcript):
         self.ctx, self.transcript = ctx, transcript
@@ -233,6 +260,13 @@ class Prover(_CS):
         v, c, n = LinearCombination.of(lc)._pack()
         check(lib().bpg_prover_constrain(self._h, v, c, n))
 
+    def load_cs(self, aL, aR, row_start, term_var, term_coef, q):
+        """Bulk allocate_multiplier + constrain: aL/aR are n*32 bytes, constraints a CSR term list
+        (numpy uint32 row_start[q+1], term_var[nnz]; term_coef nnz*32 bytes)."""
+        assert len(aL) == len(aR) and len(aL) % 32 == 0
+        check(lib().bpg_prover_load_cs(self._h, aL or None, aR or None, len(aL) // 32, row_start.ctypes.data,
+                                       term_var.ctypes.data, term_coef, q))
+
     def num_constraints(self):
         return lib().bpg_prover_num_constraints(self._h)
 
@@ -250,6 +284,10 @@ class Prover(_CS):
 
 class Verifier(_CS):
     """bulletproofs::r1cs::Verifier (GPU-backed)."""
+
+    def attach(self, circuit):
+        check(lib().bpg_verifier_attach(self._h, circuit._h))
+        self._circuit = circuit
 
     def __init__(self, ctx, transcript):
         self.ctx, self.transcript = ctx, transcript
@@ -269,6 +307,11 @@ class Verifier(_CS):
         check(lib().bpg_verifier_commit(self._h, bytes(V), byref(var)))
         return Variable(var.value)
 
+    def commit_batch(self, Vs):
+        first = c_uint32()
+        check(lib().bpg_verifier_commit_batch(self._h, b"".join(Vs), len(Vs), byref(first)))
+        return [Variable(first.value + i) for i in range(len(Vs))]
+
     def allocate_multiplier(self, assignment=None):
         arr = (c_uint32 * 3)()
         check(lib().bpg_verifier_allocate_multiplier(self._h, arr))
@@ -284,6 +327,9 @@ class Verifier(_CS):
     def constrain(self, lc):
         v, c, n = LinearCombination.of(lc)._pack()
         check(lib().bpg_verifier_constrain(self._h, v, c, n))
+
+    def load_cs(self, n, row_start, term_var, term_coef, q):
+        check(lib().bpg_verifier_load_cs(self._h, n, row_start.ctypes.data, term_var.ctypes.data, term_coef, q))
 
     def num_vars(self):
         return lib().bpg_verifier_num_vars(self._h)

@@ -35,7 +35,7 @@ static inline uint32_t var_idx(uint32_t v) { return v & ((1u << 29) - 1); }
 struct ProofWork {
     DevBuf<sc> aL, aR, aO, sL, sR, w, ypow, yinv, zpow, l1, r0, r1, r3, lvec, rvec, sG, sH, mG, mH, partial, small;
     DevBuf<sc> vbl, col_coef, dyn_s, ped_in;
-    DevBuf<uint32_t> col_start, col_row, fail;
+    DevBuf<uint32_t> col_start, col_row, fail, long_t;
     DevBuf<uint8_t> wide, dyn_enc;
     DevBuf<ge_ext> dyn_pts, dyn_blk;
     uint8_t* h_pin = nullptr;  // pinned staging
@@ -60,6 +60,7 @@ void r1cs_release_work(bpg_ctx* ctx) {
     p->col_start.release();
     p->col_row.release();
     p->fail.release();
+    p->long_t.release();
     p->wide.release();
     p->dyn_enc.release();
     p->dyn_pts.release();
@@ -115,7 +116,7 @@ struct ConstraintStore {
 // transposed (by target) form of the constraints for the flatten kernel.
 // targets: [wL(n) | wR(n) | wO(n) | wV(m) | wc]
 struct Csc {
-    std::vector<uint32_t> col_start, col_row;
+    std::vector<uint32_t> col_start, col_row, long_targets;
     std::vector<sc> col_coef;
     uint32_t nt = 0;
 };
@@ -148,6 +149,9 @@ static int build_csc(const ConstraintStore& cs, uint32_t n, uint32_t m, bool wit
     const uint32_t nnz = out->col_start[nt];
     out->col_row.resize(nnz ? nnz : 1);
     out->col_coef.resize(nnz ? nnz : 1);
+    out->long_targets.clear();
+    for (uint32_t t = 0; t < nt; t++)
+        if (out->col_start[t + 1] - out->col_start[t] > FLATTEN_LONG) out->long_targets.push_back(t);
     std::vector<uint32_t> cur(out->col_start.begin(), out->col_start.end() - 1);
     for (size_t j = 0; j < q; j++) {
         for (uint32_t e = cs.row_start[j]; e < cs.row_start[j + 1]; e++) {
@@ -165,9 +169,29 @@ static int build_csc(const ConstraintStore& cs, uint32_t n, uint32_t m, bool wit
 // ------------------------------------------------------------------------------------------
 // prover / verifier objects
 // ------------------------------------------------------------------------------------------
+// device-resident circuit: transposed constraints (always including the `One` column, which the prover
+// simply does not read) and, optionally, the multiplier assignments
+struct bpg_circuit {
+    bpg_ctx* ctx = nullptr;
+    uint32_t n = 0, m = 0, q = 0, nt = 0, nnz = 0;
+    uint32_t *d_col_start = nullptr, *d_col_row = nullptr, *d_long = nullptr;
+    uint32_t n_long = 0;
+    sc *d_col_coef = nullptr, *d_aL = nullptr, *d_aR = nullptr, *d_aO = nullptr;
+    bool has_witness = false;
+};
+__global__ void __launch_bounds__(256) k_mul_vec(const sc* a, const sc* b, sc* out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sc_mul(a[i], b[i]);
+}
+__global__ void __launch_bounds__(256) k_reduce_vec(sc* a, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = sc_reduce(a[i]);
+}
+
 struct bpg_prover {
     bpg_ctx* ctx;
     bpg::Transcript* T;
+    const bpg_circuit* circ = nullptr;
     ConstraintStore cs;
     std::vector<sc> aL, aR, aO, v, vbl;                // canonical
     std::vector<std::array<uint8_t, 32>> vbl_raw;     // as given (rekeys the transcript rng)
@@ -175,10 +199,73 @@ struct bpg_prover {
 struct bpg_verifier {
     bpg_ctx* ctx;
     bpg::Transcript* T;
+    const bpg_circuit* circ = nullptr;
     ConstraintStore cs;
     std::vector<std::array<uint8_t, 32>> V;
     uint64_t num_vars = 0;
 };
+
+// BPG_TRACE=1: per-phase wall times (stream synchronised at every mark) on stderr
+struct Trace {
+    bool on;
+    cudaStream_t st;
+    double t0, last;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    Trace(cudaStream_t s) : on(getenv("BPG_TRACE") != nullptr), st(s) { t0 = last = on ? now() : 0; }
+    void mark(const char* what) {
+        if (!on) return;
+        double a = now();
+        cudaStreamSynchronize(st);
+        double b = now();
+        fprintf(stderr, "[bpg trace] %-28s host %8.3f ms  +gpu-drain %8.3f ms  (t=%.3f)\n", what, a - last, b - a, b - t0);
+        last = b;
+    }
+};
+
+struct CscView {
+    const uint32_t *col_start, *col_row, *long_targets;
+    const sc* col_coef;
+    uint32_t nt, n_long;
+};
+// device view of the transposed constraints: the attached circuit's, or an upload of the host store
+static int csc_view(bpg_ctx* ctx, ProofWork* pw, const bpg_circuit* circ, const ConstraintStore& cs, uint32_t n,
+                    uint32_t m, CscView* out) {
+    if (circ) {
+        out->col_start = circ->d_col_start;
+        out->col_row = circ->d_col_row;
+        out->col_coef = circ->d_col_coef;
+        out->nt = circ->nt;
+        out->long_targets = circ->d_long;
+        out->n_long = circ->n_long;
+        return BPG_OK;
+    }
+    Csc csc;
+    int rc;
+    if ((rc = build_csc(cs, n, m, true, &csc))) return rc;
+    const uint32_t nnz = csc.col_start[csc.nt];
+    if ((rc = pw->col_start.ensure(csc.nt + 1)) || (rc = pw->col_row.ensure(nnz + 1)) ||
+        (rc = pw->col_coef.ensure(nnz + 1)) || (rc = pw->long_t.ensure(csc.long_targets.size() + 1)))
+        return rc;
+    cudaStream_t st = ctx->stream;
+    if (!csc.long_targets.empty())
+        CUDA_TRY(cudaMemcpyAsync(pw->long_t.p, csc.long_targets.data(), 4 * csc.long_targets.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->col_start.p, csc.col_start.data(), 4 * (size_t)(csc.nt + 1), cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CUDA_TRY(cudaMemcpyAsync(pw->col_row.p, csc.col_row.data(), 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pw->col_coef.p, csc.col_coef.data(), 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+    out->col_start = pw->col_start.p;
+    out->col_row = pw->col_row.p;
+    out->col_coef = pw->col_coef.p;
+    out->nt = csc.nt;
+    out->long_targets = pw->long_t.p;
+    out->n_long = (uint32_t)csc.long_targets.size();
+    return BPG_OK;
+}
 
 static void os_random(uint8_t out[32]) {
     std::random_device rd;
@@ -275,12 +362,18 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     cudaStream_t st = ctx->stream;
     ProofWork* pw = work(ctx);
     int rc;
-    const uint32_t n = (uint32_t)P->aL.size(), m = (uint32_t)P->v.size();
+    const bpg_circuit* circ = P->circ;
+    if (circ && (!circ->has_witness || circ->m != P->v.size() || !P->aL.empty() || P->cs.num_constraints())) {
+        bpg_set_error("prove: attached circuit needs a witness, m = #commitments, and no other constraints");
+        return BPG_E_ARG;
+    }
+    const uint32_t n = circ ? circ->n : (uint32_t)P->aL.size(), m = (uint32_t)P->v.size();
     const uint32_t npad = next_pow2(n ? n : 1);
-    const uint32_t q = (uint32_t)P->cs.num_constraints();
+    const uint32_t q = circ ? circ->q : (uint32_t)P->cs.num_constraints();
     uint32_t lg = 0;
     while ((1u << lg) < npad) lg++;
 
+    Trace trace(st);
     T.append_u64("m", m);
     uint8_t seed[32];
     if (seed32) memcpy(seed, seed32, 32); else os_random(seed);
@@ -308,7 +401,12 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     sc* small = pw->small.p;  // [0..2] blindings, [8..13] t1..t6, [16] t2_blinding, [20..21] cw, [24..25] a,b
     ge_ext* slots = ctx->d_points.p;
 
-    if (n) {
+    const sc *d_aL = pw->aL.p, *d_aR = pw->aR.p, *d_aO = pw->aO.p;
+    if (circ) {
+        d_aL = circ->d_aL;
+        d_aR = circ->d_aR;
+        d_aO = circ->d_aO;
+    } else if (n) {
         CUDA_TRY(cudaMemcpyAsync(pw->aL.p, P->aL.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(pw->aR.p, P->aR.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(pw->aO.p, P->aO.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -322,15 +420,16 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
 
     MsmSegments segs;
     memset(&segs, 0, sizeof segs);
-    seg_push(segs, pw->aL.p, 0, n, 0, 0, 1);
-    seg_push(segs, pw->aR.p, cap, n, 0, 0, 1);
+    seg_push(segs, d_aL, 0, n, 0, 0, 1);
+    seg_push(segs, d_aR, cap, n, 0, 0, 1);
     seg_push(segs, small + 0, iBb, 1, 0, 0, 1);
     if ((rc = msm_run(ctx, segs, 1, slots + 0))) return rc;  // A_I1
     memset(&segs, 0, sizeof segs);
-    seg_push(segs, pw->aO.p, 0, n, 0, 0, 1);
+    seg_push(segs, d_aO, 0, n, 0, 0, 1);
     seg_push(segs, small + 1, iBb, 1, 0, 0, 1);
     if ((rc = msm_run(ctx, segs, 1, slots + 1))) return rc;  // A_O1
 
+    trace.mark("upload+A_I1+A_O1 launched");
     // the sequential STROBE stream runs on the host while the two MSMs above execute
     if (n) {
         if ((rc = pw->pin(128 * (size_t)n))) return rc;
@@ -340,6 +439,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p + 64 * (size_t)n, pw->sR.p, n);
         ctx->launches += 2;
     }
+    trace.mark("rng s_L,s_R (host keccak)");
     memset(&segs, 0, sizeof segs);
     seg_push(segs, pw->sL.p, 0, n, 0, 0, 1);
     seg_push(segs, pw->sR.p, cap, n, 0, 0, 1);
@@ -347,18 +447,10 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     if ((rc = msm_run(ctx, segs, 1, slots + 2))) return rc;  // S1
 
     // transposed constraints (host work overlapping the S1 MSM)
-    Csc csc;
-    if ((rc = build_csc(P->cs, n, m, false, &csc))) return rc;
-    const uint32_t nnz = csc.col_start[csc.nt];
-    if ((rc = pw->col_start.ensure(csc.nt + 1)) || (rc = pw->col_row.ensure(nnz + 1)) ||
-        (rc = pw->col_coef.ensure(nnz + 1)))
-        return rc;
-    CUDA_TRY(cudaMemcpyAsync(pw->col_start.p, csc.col_start.data(), 4 * (size_t)(csc.nt + 1), cudaMemcpyHostToDevice, st));
-    if (nnz) {
-        CUDA_TRY(cudaMemcpyAsync(pw->col_row.p, csc.col_row.data(), 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pw->col_coef.p, csc.col_coef.data(), 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
-    }
+    CscView csc;
+    if ((rc = csc_view(ctx, pw, circ, P->cs, n, m, &csc))) return rc;
 
+    trace.mark("S1 msm + csc upload");
     ge_ext hp[8];
     if ((rc = fetch_points(ctx, slots, 3, hp))) return rc;
     uint8_t A_I1[32], A_O1[32], S1[32];
@@ -374,6 +466,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     T.append_message("A_O2", ZERO32, 32);
     T.append_message("S2", ZERO32, 32);
     const Scalar y = challenge_scalar(T, "y"), z = challenge_scalar(T, "z");
+    trace.mark("fetch+compress A,S; y,z");
     const Scalar y_inv = y.invert();
 
     sk_powers(st, pw->ypow.p, pow_table(y), npad, 0);
@@ -383,11 +476,12 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     sc* wR = wL + n;
     sc* wO = wR + n;
     sc* wV = wO + n;
-    sk_flatten(st, pw->col_start.p, pw->col_row.p, pw->col_coef.p, pw->zpow.p, pw->w.p, csc.nt - 1, 3 * n);
-    sk_lr_poly(st, pw->aL.p, pw->aR.p, pw->aO.p, pw->sL.p, pw->sR.p, wL, wR, wO, pw->ypow.p, pw->yinv.p, pw->l1.p,
+    sk_flatten(st, csc.col_start, csc.col_row, csc.col_coef, pw->zpow.p, pw->w.p, csc.nt - 1, 3 * n, csc.long_targets, csc.n_long);
+    sk_lr_poly(st, d_aL, d_aR, d_aO, pw->sL.p, pw->sR.p, wL, wR, wO, pw->ypow.p, pw->yinv.p, pw->l1.p,
                pw->r0.p, pw->r1.p, pw->r3.p, pw->partial.p, small + 8, n);
     sk_dot(st, wV, pw->vbl.p, m, small + 16);
     ctx->launches += 7;
+    trace.mark("powers+flatten+lr_poly");
     sc th[9];
     CUDA_TRY(cudaMemcpyAsync(th, small + 8, 9 * 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -405,6 +499,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     T.append_message("T_4", Tc[2], 32);
     T.append_message("T_5", Tc[3], 32);
     T.append_message("T_6", Tc[4], 32);
+    trace.mark("T commitments");
     const Scalar u = challenge_scalar(T, "u"), x = challenge_scalar(T, "x");
 
     auto poly6 = [&](const Scalar& c1, const Scalar& c2, const Scalar& c3, const Scalar& c4, const Scalar& c5,
@@ -413,13 +508,14 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     const Scalar t_x_blinding = poly6(tb1, tb2, tb3, tb4, tb5, tb6);
     const Scalar e_blinding = x * (i_bl + x * (o_bl + x * s_bl));
 
-    sk_eval_lr(st, pw->l1.p, pw->aO.p, pw->sL.p, pw->r0.p, pw->r1.p, pw->r3.p, pw->ypow.p, x.s, pw->lvec.p,
+    sk_eval_lr(st, pw->l1.p, d_aO, pw->sL.p, pw->r0.p, pw->r1.p, pw->r3.p, pw->ypow.p, x.s, pw->lvec.p,
                pw->rvec.p, n, npad);
     append_scalar(T, "t_x", t_x);
     append_scalar(T, "t_x_blinding", t_x_blinding);
     append_scalar(T, "e_blinding", e_blinding);
     const Scalar w = challenge_scalar(T, "w");
 
+    trace.mark("eval l,r; w");
     // ---- inner-product argument (InnerProductProof::create) ----
     T.append_message("dom-sep", reinterpret_cast<const uint8_t*>("ipp v1"), 6);
     T.append_u64("n", npad);
@@ -448,12 +544,14 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, npad, nk);
         ctx->launches++;
     }
+    trace.mark("ipp rounds");
     sc ab[2];
     CUDA_TRY(cudaMemcpyAsync(&ab[0], pw->lvec.p, 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&ab[1], pw->rvec.p, 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
 
+    trace.mark("final a,b");
     // ---- R1CSProof::to_bytes (1-phase) ----
     std::vector<uint8_t>& o = *proof_out;
     o.clear();
@@ -554,12 +652,18 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
         bpg_set_error("malformed proof bytes");
         return rc;
     }
-    const uint32_t n = (uint32_t)Vf->num_vars, m = (uint32_t)Vf->V.size();
+    const bpg_circuit* circ = Vf->circ;
+    if (circ && (circ->m != Vf->V.size() || Vf->num_vars || Vf->cs.num_constraints())) {
+        bpg_set_error("verify: attached circuit needs m = #commitments and no other constraints");
+        return BPG_E_ARG;
+    }
+    const uint32_t n = circ ? circ->n : (uint32_t)Vf->num_vars, m = (uint32_t)Vf->V.size();
     const uint32_t npad = next_pow2(n ? n : 1);
-    const uint32_t q = (uint32_t)Vf->cs.num_constraints();
+    const uint32_t q = circ ? circ->q : (uint32_t)Vf->cs.num_constraints();
     uint32_t lg = 0;
     while ((1u << lg) < npad) lg++;
 
+    Trace trace(st);
     T.append_u64("m", m);
 #define VALIDATE_APPEND(label, pt)                     \
     do {                                               \
@@ -614,28 +718,22 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     const Scalar r = rng_scalar(rng);
     const Scalar xx = x * x, rxx = r * xx, xxx = x * xx;
 
+    trace.mark("v: transcript+challenges");
     if ((rc = gens_build(ctx, npad))) return rc;
     const uint64_t cap = ctx->table.capacity;
     const uint64_t iB = 2 * cap, iBb = 2 * cap + 1;
 
-    Csc csc;
-    if ((rc = build_csc(Vf->cs, n, m, true, &csc))) return rc;
-    const uint32_t nnz = csc.col_start[csc.nt];
+    CscView csc;
+    if ((rc = csc_view(ctx, pw, circ, Vf->cs, n, m, &csc))) return rc;
     const uint32_t ndyn = 6 + m + 5 + 2 * lg;
     const size_t nn = npad;
     if ((rc = pw->w.ensure(3 * (size_t)n + m + 1)) || (rc = pw->yinv.ensure(nn)) || (rc = pw->zpow.ensure(q + 1)) ||
         (rc = pw->mG.ensure(nn)) || (rc = pw->mH.ensure(nn)) || (rc = pw->partial.ensure(SK_PARTIAL_SCALARS)) ||
-        (rc = pw->small.ensure(64)) || (rc = pw->col_start.ensure(csc.nt + 1)) || (rc = pw->col_row.ensure(nnz + 1)) ||
-        (rc = pw->col_coef.ensure(nnz + 1)) || (rc = pw->dyn_s.ensure(ndyn)) || (rc = pw->dyn_enc.ensure(32 * (size_t)ndyn)) ||
+        (rc = pw->small.ensure(64)) || (rc = pw->dyn_s.ensure(ndyn)) || (rc = pw->dyn_enc.ensure(32 * (size_t)ndyn)) ||
         (rc = pw->dyn_pts.ensure(ndyn)) || (rc = pw->dyn_blk.ensure(ndyn / 64 + 2)) || (rc = pw->fail.ensure(1)) ||
         (rc = ctx->d_points.ensure(64)))
         return rc;
     sc* small = pw->small.p;  // [0] delta, [1] sB, [2] sBb
-    CUDA_TRY(cudaMemcpyAsync(pw->col_start.p, csc.col_start.data(), 4 * (size_t)(csc.nt + 1), cudaMemcpyHostToDevice, st));
-    if (nnz) {
-        CUDA_TRY(cudaMemcpyAsync(pw->col_row.p, csc.col_row.data(), 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pw->col_coef.p, csc.col_coef.data(), 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
-    }
     sk_powers(st, pw->yinv.p, pow_table(y_inv), npad, 0);
     sk_powers(st, pw->zpow.p, pow_table(z), q, 1);
     sc* wL = pw->w.p;
@@ -643,7 +741,8 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     sc* wO = wR + n;
     sc* wV = wO + n;
     sc* wc = wV + m;
-    sk_flatten(st, pw->col_start.p, pw->col_row.p, pw->col_coef.p, pw->zpow.p, pw->w.p, csc.nt, 3 * n);
+    sk_flatten(st, csc.col_start, csc.col_row, csc.col_coef, pw->zpow.p, pw->w.p, csc.nt, 3 * n, csc.long_targets, csc.n_long);
+    trace.mark("v: csc+powers+flatten");
     VerChallenges ch;
     memset(&ch, 0, sizeof ch);
     for (uint32_t k = 0; k < lg; k++) {
@@ -655,6 +754,7 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     ch.b = pr.b.s;
     ch.u_pad = u.s;
     sk_ver_scalars(st, ch, wL, wR, wO, pw->yinv.p, pw->mG.p, pw->mH.p, pw->partial.p, small + 0, n, npad, lg);
+    trace.mark("v: ver_scalars");
     const Scalar w_tab = w * (pr.t_x - pr.a * pr.b);
     const Scalar sBb = -pr.e_blinding - r * pr.t_x_blinding;
     // dynamic scalars, in dalek's point order: A_I1 A_O1 S1 A_I2 A_O2 S2 | V | T_1 T_3 T_4 T_5 T_6 | L.. | R..
@@ -690,9 +790,11 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     CUDA_TRY(cudaMemsetAsync(pw->fail.p, 0, 4, st));
     sk_ver_head(st, wV, wc, small + 0, rxx.s, r.s, xx.s, w_tab.s, pr.t_x.s, pw->dyn_s.p + 6, small + 1, m);
     pk_decompress(st, pw->dyn_enc.p, pw->dyn_pts.p, ndyn, pw->fail.p);
+    trace.mark("v: head+decompress");
     ge_ext* slots = ctx->d_points.p;
     pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, ndyn, pw->dyn_blk.p, slots + 8);
     ctx->launches += 10;
+    trace.mark("v: dyn msm");
     MsmSegments segs;
     memset(&segs, 0, sizeof segs);
     seg_push(segs, pw->mG.p, 0, npad, 0, 0, 1);
@@ -702,6 +804,7 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     if ((rc = msm_run(ctx, segs, 1, slots + 9))) return rc;
     pk_add2(st, slots + 8, slots + 9, slots + 10);
     ctx->launches++;
+    trace.mark("v: fixed msm");
     uint32_t fail = 0;
     ge_ext res;
     CUDA_TRY(cudaMemcpyAsync(&fail, pw->fail.p, 4, cudaMemcpyDeviceToHost, st));
@@ -879,8 +982,41 @@ int bpg_prover_constrain(bpg_prover* p, const uint32_t* vars, const uint8_t* coe
     p->cs.end();
     return BPG_OK;
 }
-uint64_t bpg_prover_num_constraints(const bpg_prover* p) { return p ? p->cs.num_constraints() : 0; }
-uint64_t bpg_prover_num_multipliers(const bpg_prover* p) { return p ? p->aL.size() : 0; }
+static int load_constraints(ConstraintStore& cs, const uint32_t* row_start, const uint32_t* term_var,
+                            const uint8_t* term_coef32, uint64_t q) {
+    if (q == 0) return BPG_OK;
+    if (!row_start || !term_var || !term_coef32 || row_start[0] != 0) return BPG_E_ARG;
+    const uint32_t nnz = row_start[q];
+    cs.term_var.reserve(cs.term_var.size() + nnz);
+    cs.term_coef.reserve(cs.term_coef.size() + nnz);
+    for (uint64_t j = 0; j < q; j++) {
+        if (row_start[j + 1] < row_start[j]) return BPG_E_ARG;
+        int rc = cs.add_lc(term_var + row_start[j], term_coef32 + 32 * (size_t)row_start[j], row_start[j + 1] - row_start[j]);
+        if (rc) return rc;
+        cs.end();
+    }
+    return BPG_OK;
+}
+
+int bpg_prover_load_cs(bpg_prover* p, const uint8_t* aL32n, const uint8_t* aR32n, uint64_t n, const uint32_t* row_start,
+                       const uint32_t* term_var, const uint8_t* term_coef32, uint64_t q) {
+    if (!p || (n && (!aL32n || !aR32n))) return BPG_E_ARG;
+    p->aL.reserve(p->aL.size() + n);
+    p->aR.reserve(p->aR.size() + n);
+    p->aO.reserve(p->aO.size() + n);
+    for (uint64_t i = 0; i < n; i++) {
+        if ((aL32n[32 * i + 31] | aR32n[32 * i + 31]) & 0x80) return BPG_E_ARG;
+        const sc l = Scalar::from_bytes_mod_order(aL32n + 32 * i).s, r = Scalar::from_bytes_mod_order(aR32n + 32 * i).s;
+        p->aL.push_back(l);
+        p->aR.push_back(r);
+        p->aO.push_back(sc_mul(l, r));
+    }
+    return load_constraints(p->cs, row_start, term_var, term_coef32, q);
+}
+uint64_t bpg_prover_num_constraints(const bpg_prover* p) {
+    return !p ? 0 : p->circ ? p->circ->q : p->cs.num_constraints();
+}
+uint64_t bpg_prover_num_multipliers(const bpg_prover* p) { return !p ? 0 : p->circ ? p->circ->n : p->aL.size(); }
 
 int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     if (!p || !proof_out || !proof_len) return BPG_E_ARG;
@@ -895,6 +1031,88 @@ int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_ou
     }
     memcpy(proof_out, proof.data(), proof.size());
     *proof_len = proof.size();
+    return BPG_OK;
+}
+
+int bpg_circuit_create(bpg_ctx* ctx, uint64_t n, uint64_t m, const uint32_t* row_start, const uint32_t* term_var,
+                       const uint8_t* term_coef32, uint64_t q, bpg_circuit** out) {
+    if (!ctx || !out || n >= (1u << 29) || m >= (1u << 29)) return BPG_E_ARG;
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ConstraintStore cs;
+    int rc;
+    if ((rc = load_constraints(cs, row_start, term_var, term_coef32, q))) return rc;
+    Csc csc;
+    if ((rc = build_csc(cs, (uint32_t)n, (uint32_t)m, true, &csc))) return rc;
+    bpg_circuit* c = new bpg_circuit();
+    c->ctx = ctx;
+    c->n = (uint32_t)n;
+    c->m = (uint32_t)m;
+    c->q = (uint32_t)q;
+    c->nt = csc.nt;
+    c->nnz = csc.col_start[csc.nt];
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMalloc((void**)&c->d_col_start, 4 * (size_t)(c->nt + 1)));
+    CUDA_TRY(cudaMalloc((void**)&c->d_col_row, 4 * (size_t)(c->nnz + 1)));
+    CUDA_TRY(cudaMalloc((void**)&c->d_col_coef, 32 * (size_t)(c->nnz + 1)));
+    c->n_long = (uint32_t)csc.long_targets.size();
+    CUDA_TRY(cudaMalloc((void**)&c->d_long, 4 * (size_t)(c->n_long + 1)));
+    if (c->n_long)
+        CUDA_TRY(cudaMemcpyAsync(c->d_long, csc.long_targets.data(), 4 * (size_t)c->n_long, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_col_start, csc.col_start.data(), 4 * (size_t)(c->nt + 1), cudaMemcpyHostToDevice, st));
+    if (c->nnz) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_col_row, csc.col_row.data(), 4 * (size_t)c->nnz, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->d_col_coef, csc.col_coef.data(), 32 * (size_t)c->nnz, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out = c;
+    return BPG_OK;
+}
+int bpg_circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR32n) {
+    if (!c || (c->n && (!aL32n || !aR32n))) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    const size_t n = c->n;
+    for (size_t i = 0; i < n; i++)
+        if ((aL32n[32 * i + 31] | aR32n[32 * i + 31]) & 0x80) return BPG_E_ARG;
+    cudaStream_t st = c->ctx->stream;
+    if (!c->d_aL) {
+        CUDA_TRY(cudaMalloc((void**)&c->d_aL, 32 * (n + 1)));
+        CUDA_TRY(cudaMalloc((void**)&c->d_aR, 32 * (n + 1)));
+        CUDA_TRY(cudaMalloc((void**)&c->d_aO, 32 * (n + 1)));
+    }
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_aL, aL32n, 32 * n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->d_aR, aR32n, 32 * n, cudaMemcpyHostToDevice, st));
+        const uint32_t blocks = (uint32_t)((n + 255) / 256);
+        k_reduce_vec<<<blocks, 256, 0, st>>>(c->d_aL, (uint32_t)n);  // Scalar::from_bits values may be >= l
+        k_reduce_vec<<<blocks, 256, 0, st>>>(c->d_aR, (uint32_t)n);
+        k_mul_vec<<<blocks, 256, 0, st>>>(c->d_aL, c->d_aR, c->d_aO, (uint32_t)n);
+        c->ctx->launches += 3;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->has_witness = true;
+    return BPG_OK;
+}
+void bpg_circuit_free(bpg_circuit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaFree(c->d_col_start);
+    cudaFree(c->d_col_row);
+    cudaFree(c->d_col_coef);
+    cudaFree(c->d_long);
+    cudaFree(c->d_aL);
+    cudaFree(c->d_aR);
+    cudaFree(c->d_aO);
+    delete c;
+}
+int bpg_prover_attach(bpg_prover* p, const bpg_circuit* c) {
+    if (!p || !c || c->ctx != p->ctx) return BPG_E_ARG;
+    p->circ = c;
+    return BPG_OK;
+}
+int bpg_verifier_attach(bpg_verifier* v, const bpg_circuit* c) {
+    if (!v || !c || c->ctx != v->ctx) return BPG_E_ARG;
+    v->circ = c;
     return BPG_OK;
 }
 
@@ -915,6 +1133,15 @@ int bpg_verifier_commit(bpg_verifier* v, const uint8_t V[32], uint32_t* var_out)
     if (var_out) *var_out = BPG_VAR_COMMITTED((uint32_t)v->V.size());
     v->V.push_back(a);
     v->T->append_message("V", V, 32);
+    return BPG_OK;
+}
+int bpg_verifier_commit_batch(bpg_verifier* v, const uint8_t* V32k, uint64_t k, uint32_t* first_var_out) {
+    if (!v || (k && !V32k)) return BPG_E_ARG;
+    if (first_var_out) *first_var_out = BPG_VAR_COMMITTED((uint32_t)v->V.size());
+    for (uint64_t i = 0; i < k; i++) {
+        int rc = bpg_verifier_commit(v, V32k + 32 * i, nullptr);
+        if (rc) return rc;
+    }
     return BPG_OK;
 }
 int bpg_verifier_allocate_multiplier(bpg_verifier* v, uint32_t vars_out[3]) {
@@ -950,7 +1177,13 @@ int bpg_verifier_constrain(bpg_verifier* v, const uint32_t* vars, const uint8_t*
     v->cs.end();
     return BPG_OK;
 }
-uint64_t bpg_verifier_num_vars(const bpg_verifier* v) { return v ? v->num_vars : 0; }
+int bpg_verifier_load_cs(bpg_verifier* v, uint64_t n, const uint32_t* row_start, const uint32_t* term_var,
+                         const uint8_t* term_coef32, uint64_t q) {
+    if (!v) return BPG_E_ARG;
+    v->num_vars += n;
+    return load_constraints(v->cs, row_start, term_var, term_coef32, q);
+}
+uint64_t bpg_verifier_num_vars(const bpg_verifier* v) { return !v ? 0 : v->circ ? v->circ->n : v->num_vars; }
 int bpg_verifier_verify(bpg_verifier* v, const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32) {
     if (!v || !proof) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(v->ctx->device));

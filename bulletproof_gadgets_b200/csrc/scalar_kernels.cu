@@ -62,9 +62,31 @@ __global__ void __launch_bounds__(SK_THREADS) k_flatten(const uint32_t* __restri
     if (t >= nt) return;
     sc acc = sc_zero();
     const uint32_t e0 = col_start[t], e1 = col_start[t + 1];
+    if (e1 - e0 > FLATTEN_LONG) return;  // handled by k_flatten_long (one CTA per long column)
     for (uint32_t e = e0; e < e1; e++) acc = sc_add(acc, sc_mul(ld_sc(col_coef + e), ld_sc(zpow + col_row[e])));
     if (t >= neg_from) acc = sc_neg(acc);
     st_sc(out + t, acc);
+}
+
+// columns with more than FLATTEN_LONG terms (e.g. the `One` column of a range-proof circuit: one term per bit)
+__global__ void __launch_bounds__(1024) k_flatten_long(const uint32_t* __restrict__ col_start,
+                                                       const uint32_t* __restrict__ col_row,
+                                                       const sc* __restrict__ col_coef, const sc* __restrict__ zpow,
+                                                       sc* __restrict__ out, const uint32_t* __restrict__ long_targets,
+                                                       uint32_t nt, uint32_t neg_from) {
+    __shared__ sc sh[1024];
+    const uint32_t t = long_targets[blockIdx.x];
+    if (t >= nt) return;  // (uniform per block)
+    const uint32_t e0 = col_start[t], e1 = col_start[t + 1], tid = threadIdx.x;
+    sc acc = sc_zero();
+    for (uint32_t e = e0 + tid; e < e1; e += 1024) acc = sc_add(acc, sc_mul(ld_sc(col_coef + e), ld_sc(zpow + col_row[e])));
+    sh[tid] = acc;
+    __syncthreads();
+    for (uint32_t s = 512; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] = sc_add(sh[tid], sh[tid + s]);
+        __syncthreads();
+    }
+    if (tid == 0) st_sc(out + t, t >= neg_from ? sc_neg(sh[0]) : sh[0]);
 }
 
 // l1 = aL + yinv^i wR ; r0 = wO - y^i ; r1 = y^i aR + wL ; r3 = y^i sR   (l2 = aO, l3 = sL)
@@ -246,8 +268,11 @@ void sk_powers(cudaStream_t st, sc* out, const PowTable& tbl, uint32_t n, uint32
     if (n) k_powers<<<nblk(n), SK_THREADS, 0, st>>>(out, tbl, n, start);
 }
 void sk_flatten(cudaStream_t st, const uint32_t* col_start, const uint32_t* col_row, const sc* col_coef,
-                const sc* zpow, sc* out, uint32_t nt, uint32_t neg_from) {
+                const sc* zpow, sc* out, uint32_t nt, uint32_t neg_from, const uint32_t* long_targets,
+                uint32_t n_long) {
     if (nt) k_flatten<<<nblk(nt), SK_THREADS, 0, st>>>(col_start, col_row, col_coef, zpow, out, nt, neg_from);
+    if (nt && n_long)
+        k_flatten_long<<<n_long, 1024, 0, st>>>(col_start, col_row, col_coef, zpow, out, long_targets, nt, neg_from);
 }
 void sk_lr_poly(cudaStream_t st, const sc* aL, const sc* aR, const sc* aO, const sc* sL, const sc* sR, const sc* wL,
                 const sc* wR, const sc* wO, const sc* ypow, const sc* yinv, sc* l1, sc* r0, sc* r1, sc* r3,

@@ -1,0 +1,103 @@
+"""Synthetic statements of the BASELINE.json configs, flattened to the arrays the C ABI bulk loaders
+take (bpg_prover_load_cs / bpg_verifier_load_cs).  Pure host-side data preparation (numpy); the
+circuits are what the reference's gadgets emit:
+
+  bounds_check  BOUND v in [min, max], two n-bit range proofs per statement
+                /root/reference/src/bounds_check/bounds_check_gadget.rs:13-48, /root/reference/src/utils.rs:5-35
+"""
+import numpy as np
+
+L_ORDER = 2**252 + 27742317777372353535851937790883648493
+COMMITTED, MUL_LEFT, MUL_RIGHT, MUL_OUT, ONE = 0, 1, 2, 3, 4
+
+
+def _tag(kind, idx):
+    return (kind << 29) | idx
+
+
+class FlatStatement:
+    """committed values + blindings + multiplier assignments + CSR constraints."""
+
+    def __init__(self, label, v, vbl, aL, aR, row_start, term_var, term_coef, n, q):
+        self.label = label
+        self.v, self.vbl = v, vbl                      # lists of ints
+        self.aL, self.aR = aL, aR                      # bytes, n*32
+        self.row_start, self.term_var = row_start, term_var
+        self.term_coef = term_coef                     # bytes, nnz*32
+        self.n, self.q = n, q
+        self.m = len(v)
+
+    @property
+    def nnz(self):
+        return int(self.row_start[-1])
+
+
+def _scalar_bytes(x):
+    return int(x % L_ORDER).to_bytes(32, "little")
+
+
+def bounds_check_statement(count=1024, max_bytes=8, seed=20261018, label=b"bench-bound"):
+    """`count` x  BOUND W_i I_min I_max  with I_min = 0, I_max = 2^(8*max_bytes)-1.
+    Committed variables per statement: [v, a = v - min, b = max - v]  (witness + 2 derived)."""
+    n_bits = 8 * max_bytes
+    vmin, vmax = 0, (1 << n_bits) - 1
+    rng = np.random.default_rng(seed)
+    vals = [int.from_bytes(rng.integers(0, 256, size=max_bytes, dtype=np.uint8).tobytes(), "big") for _ in range(count)]
+    v, vbl = [], []
+    brng = np.random.default_rng(seed + 1)
+    n = count * 2 * n_bits
+    aL = np.zeros((n, 32), dtype=np.uint8)
+    aR = np.zeros((n, 32), dtype=np.uint8)
+    row_start = [0]
+    tvar, tcoef = [], []
+    one_b, minus_one_b = _scalar_bytes(1), _scalar_bytes(-1)
+    pow2_neg = [_scalar_bytes(-(1 << i)) for i in range(n_bits)]
+    mult = 0
+    for s, val in enumerate(vals):
+        a, b = val - vmin, vmax - val
+        for x in (val, a, b):
+            v.append(x % L_ORDER)
+            vbl.append(int.from_bytes(brng.integers(0, 256, size=32, dtype=np.uint8).tobytes(), "little") % L_ORDER)
+        va, vb = _tag(COMMITTED, 3 * s + 1), _tag(COMMITTED, 3 * s + 2)
+        # (a + b) - (max - min) = 0
+        tvar += [va, vb, _tag(ONE, 0)]
+        tcoef += [one_b, one_b, _scalar_bytes(-(vmax - vmin))]
+        row_start.append(len(tvar))
+        for var, x in ((va, a), (vb, b)):
+            acc_vars, acc_coef = [var], [one_b]
+            for i in range(n_bits):
+                bit = (x >> i) & 1
+                aL[mult, 0] = 1 - bit
+                aR[mult, 0] = bit
+                tvar.append(_tag(MUL_OUT, mult))          # o = 0
+                tcoef.append(one_b)
+                row_start.append(len(tvar))
+                tvar += [_tag(MUL_LEFT, mult), _tag(MUL_RIGHT, mult), _tag(ONE, 0)]   # a + (b - 1) = 0
+                tcoef += [one_b, one_b, minus_one_b]
+                row_start.append(len(tvar))
+                acc_vars.append(_tag(MUL_RIGHT, mult))
+                acc_coef.append(pow2_neg[i])
+                mult += 1
+            tvar += acc_vars                               # x - sum b_i 2^i = 0
+            tcoef += acc_coef
+            row_start.append(len(tvar))
+    assert mult == n
+    return FlatStatement(label, v, vbl, aL.tobytes(), aR.tobytes(), np.asarray(row_start, dtype=np.uint32),
+                         np.asarray(tvar, dtype=np.uint32), b"".join(tcoef), n, len(row_start) - 1)
+
+
+def prove_statement(bpg, ctx, st, seed=b"\x07" * 32):
+    """Drives one statement through the C ABI prover: returns (proof bytes, commitments)."""
+    T = bpg.Transcript(st.label)
+    p = bpg.Prover(ctx, T)
+    coms = [c for c, _ in p.commit_batch(st.v, st.vbl)]
+    p.load_cs(st.aL, st.aR, st.row_start, st.term_var, st.term_coef, st.q)
+    return p.prove(seed), coms
+
+
+def verify_statement(bpg, ctx, st, proof, coms, seed=b"\x09" * 32):
+    T = bpg.Transcript(st.label)
+    vf = bpg.Verifier(ctx, T)
+    vf.commit_batch(coms)
+    vf.load_cs(st.n, st.row_start, st.term_var, st.term_coef, st.q)
+    return vf.verify(proof, seed)

@@ -104,6 +104,12 @@ int bpg_prover_multiply(bpg_prover* p, const uint32_t* lvars, const uint8_t* lco
                         const uint32_t* rvars, const uint8_t* rcoef32, size_t rn, uint32_t vars_out[3]);
 /* ConstraintSystem::constrain(lc) -- /root/reference/src/cs_buffer.rs:112-115 */
 int bpg_prover_constrain(bpg_prover* p, const uint32_t* vars, const uint8_t* coef32, size_t n);
+/* Bulk form of the three calls above: appends n multipliers (allocate_multiplier semantics: no implicit
+ * constraints; a_O is recomputed as a_L*a_R) and q constraints given as a CSR term list
+ * (row_start[q+1], term_var[nnz], term_coef32[nnz]).  Variables inside the terms are absolute tags.
+ * Replaces the op-by-op replay of /root/reference/src/prove.rs:84-99 (assign_buffer). */
+int bpg_prover_load_cs(bpg_prover* p, const uint8_t* aL32n, const uint8_t* aR32n, uint64_t n,
+                       const uint32_t* row_start, const uint32_t* term_var, const uint8_t* term_coef32, uint64_t q);
 /* Prover::num_constraints / get_num_multiplications (FairAds fork) -- /root/reference/src/prove.rs:75,78 */
 uint64_t bpg_prover_num_constraints(const bpg_prover* p);
 uint64_t bpg_prover_num_multipliers(const bpg_prover* p);
@@ -112,17 +118,37 @@ uint64_t bpg_prover_num_multipliers(const bpg_prover* p);
  * thread_rng(); NULL = draw from the OS.  Generators for round_pow2(n) are ensured. */
 int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
+/* ---- device-resident circuits ------------------------------------------------------------ */
+/* A flattened constraint system (and optionally its witness) kept in HBM so that many proofs /
+ * verifications of the same circuit pay the host->device upload once.  What the circuit holds is
+ * exactly what assign_buffer replays (/root/reference/src/prove.rs:84-99, src/verify.rs:75-90):
+ * n multipliers, q constraints over m committed variables.  a_O is computed on the device. */
+typedef struct bpg_circuit bpg_circuit;
+int bpg_circuit_create(bpg_ctx* ctx, uint64_t n, uint64_t m, const uint32_t* row_start, const uint32_t* term_var,
+                       const uint8_t* term_coef32, uint64_t q, bpg_circuit** out);
+int bpg_circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR32n);
+void bpg_circuit_free(bpg_circuit* c);
+/* Use the resident circuit instead of multiply/allocate_multiplier/constrain calls (exclusive). */
+int bpg_prover_attach(bpg_prover* p, const bpg_circuit* c);
+int bpg_verifier_attach(bpg_verifier* v, const bpg_circuit* c);
+
 /* ---- R1CS constraint system: verifier ------------------------------------------------- */
 /* Verifier::new(&mut transcript) -- /root/reference/src/verify.rs:46 */
 int bpg_verifier_new(bpg_ctx* ctx, bpg_transcript* t, bpg_verifier** out);
 void bpg_verifier_free(bpg_verifier* v);
 /* Verifier::commit(V) -> Variable -- /root/reference/src/lalrpop/assignment_parser.rs:138 */
 int bpg_verifier_commit(bpg_verifier* v, const uint8_t V[32], uint32_t* var_out);
+/* k commitments in file order (the .coms replay of /root/reference/src/lalrpop/assignment_parser.rs:133-141) */
+int bpg_verifier_commit_batch(bpg_verifier* v, const uint8_t* V32k, uint64_t k, uint32_t* first_var_out);
 /* allocate_multiplier(None) / multiply / constrain -- /root/reference/src/cs_buffer.rs:173-199 */
 int bpg_verifier_allocate_multiplier(bpg_verifier* v, uint32_t vars_out[3]);
 int bpg_verifier_multiply(bpg_verifier* v, const uint32_t* lvars, const uint8_t* lcoef32, size_t ln,
                           const uint32_t* rvars, const uint8_t* rcoef32, size_t rn, uint32_t vars_out[3]);
 int bpg_verifier_constrain(bpg_verifier* v, const uint32_t* vars, const uint8_t* coef32, size_t n);
+/* Bulk form: n multipliers without assignments and q constraints (CSR) -- the replay of
+ * /root/reference/src/verify.rs:75-90 (assign_buffer). */
+int bpg_verifier_load_cs(bpg_verifier* v, uint64_t n, const uint32_t* row_start, const uint32_t* term_var,
+                         const uint8_t* term_coef32, uint64_t q);
 uint64_t bpg_verifier_num_vars(const bpg_verifier* v); /* Verifier::get_num_vars -- /root/reference/src/verify.rs:70 */
 /* R1CSProof::from_bytes + Verifier::verify(&proof, &pc_gens, &bp_gens) -- /root/reference/src/verify.rs:53,71.
  * BPG_OK = accepted, BPG_E_VERIFY = rejected, BPG_E_FORMAT = malformed proof bytes. */
