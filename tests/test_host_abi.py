@@ -1,0 +1,151 @@
+"""CPU-side checks of the product's host code (no GPU, no compute through the device):
+
+  * libbpg.so loads and exports every symbol include/bpg.h declares; the ctypes prototype table covers them
+  * without a CUDA device the library fails loudly (BPG_E_CUDA) -- there is no CPU fallback
+  * the host Merlin transcript behind bpg_transcript_* equals the oracle's (merlin 2.0.1 KAT + random op mixes)
+  * the portable (host) branch of the device math headers fe25519/ge25519 agrees with big-int arithmetic
+"""
+import ctypes
+import hashlib
+import os
+import random
+import re
+import subprocess
+
+import pytest
+
+import bulletproof_gadgets_b200 as bpg
+from bulletproof_gadgets_b200 import _capi, build
+from oracle.pyref import ed
+from oracle.pyref.merlin import Transcript as OTranscript
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 2**255 - 19
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_lib()
+    return bpg.lib()
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "bpg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(bpg_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), "libbpg.so does not export %s" % s
+    missing = [s for s in syms if s not in _capi.PROTOTYPES]
+    assert not missing, "ctypes prototypes missing for %s" % missing
+    extra = [s for s in _capi.PROTOTYPES if s not in syms]
+    assert not extra, "prototypes without a declaration in include/bpg.h: %s" % extra
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = lib.bpg_ctx_create(0, ctypes.byref(h))
+    assert rc == _capi.E_CUDA and not h
+    assert b"no CPU fallback" in lib.bpg_last_error()
+    with pytest.raises(bpg.BpgError):
+        bpg.Context(0)
+
+
+def test_product_does_not_import_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "bulletproof_gadgets_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libbp_oracle" not in src and "coracle" not in src, f
+
+
+def test_host_transcript_known_answer(lib):
+    T = bpg.Transcript(b"test protocol")
+    T.append_message(b"some label", b"some data")
+    assert T.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_host_transcript_matches_oracle_on_random_ops(lib):
+    rnd = random.Random(2001)
+    for trial in range(20):
+        label = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 40)))
+        a, b = bpg.Transcript(label), OTranscript(label)
+        for _ in range(rnd.randrange(1, 30)):
+            lab = bytes(rnd.randrange(1, 256) for _ in range(rnd.randrange(1, 12)))
+            if rnd.random() < 0.6:
+                msg = bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 1, 8, 32, 165, 166, 167, 400])))
+                a.append_message(lab, msg)
+                b.append_message(lab, msg)
+            else:
+                n = rnd.choice([1, 32, 64, 166, 200, 333])
+                assert a.challenge_bytes(lab, n) == b.challenge_bytes(lab, n)
+        c = a.clone()  # a clone continues the same stream independently
+        want = b.challenge_bytes(b"x", 64)
+        assert c.challenge_bytes(b"x", 64) == want and a.challenge_bytes(b"x", 64) == want
+
+
+# ---------------------------------------------------------------------------- device math headers on the host
+@pytest.fixture(scope="module")
+def hm():
+    out = os.path.join(ROOT, "build", "libhost_math.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "host_math", "host_math.cpp")
+    inc = os.path.join(ROOT, "bulletproof_gadgets_b200", "csrc")
+    deps = [src] + [os.path.join(inc, f) for f in ("fe25519.cuh", "ge25519.cuh", "sc25519.cuh", "consts.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", inc, src, "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+def _fe(x):
+    return (ctypes.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def _int(arr):
+    return sum(int(arr[i]) << (32 * i) for i in range(8))
+
+
+def test_field_arithmetic_portable_branch(hm):
+    rnd = random.Random(25519)
+    edge = [0, 1, 2, 19, P - 1, P - 2, P, P + 1, (1 << 255) - 1, (1 << 256) - 1, (1 << 256) - 38, (1 << 255) + 5]
+    vals = edge + [rnd.randrange(1 << 256) for _ in range(200)]
+    out, canon = (ctypes.c_uint32 * 8)(), (ctypes.c_uint32 * 8)()
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        for fn, op in ((hm.hm_fe_mul, lambda x, y: x * y), (hm.hm_fe_add, lambda x, y: x + y),
+                       (hm.hm_fe_sub, lambda x, y: x - y)):
+            fn(_fe(a), _fe(b), out)
+            hm.hm_fe_canon(out, canon)
+            assert _int(canon) == op(a, b) % P, (fn, hex(a), hex(b))
+        hm.hm_fe_canon(_fe(a), canon)
+        assert _int(canon) == a % P
+        if a % P:
+            hm.hm_fe_invert(_fe(a), out)
+            assert _int(out) * a % P == 1
+
+
+def test_group_and_codec_portable_branch(hm):
+    from tests.test_oracle_anchors import RFC9496_BAD, RFC9496_MULTIPLES
+    o1, o2, o3 = (ctypes.create_string_buffer(32) for _ in range(3))
+    for k, enc in enumerate(RFC9496_MULTIPLES):
+        assert hm.hm_decompress_ops(bytes.fromhex(enc), o1, o2, o3) == 1
+        assert o1.raw.hex() == enc
+        assert o2.raw == (ed.BASEPOINT * (2 * k)).compress() == o3.raw
+    for enc in RFC9496_BAD:
+        assert hm.hm_decompress_ops(bytes.fromhex(enc), o1, o2, o3) == 0
+    for i in range(32):
+        u = hashlib.shake_256(b"hm-%d" % i).digest(64)
+        hm.hm_from_uniform(u, o1)
+        assert o1.raw == ed.from_uniform_bytes(u).compress()
+    a, b = bytes.fromhex(RFC9496_MULTIPLES[5]), bytes.fromhex(RFC9496_MULTIPLES[9])
+    assert hm.hm_add(a, b, o1) == 1 and o1.raw.hex() == RFC9496_MULTIPLES[14]

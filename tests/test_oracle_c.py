@@ -1,0 +1,172 @@
+"""The C restatement (oracle/c, the CPU baseline) against the big-int python oracle and the committed goldens.
+
+Both are test infrastructure.  The C port follows dalek's CPU algorithms (constant-time radix-16 Straus,
+vartime Straus below 190 points, vartime Pippenger above -- curve25519-dalek 3.2.0
+backend/serial/scalar_mul/{straus,pippenger}.rs), so this also checks that every MSM algorithm produces
+the same 32 ristretto bytes."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+from oracle import coracle
+from oracle.pyref import ed, r1cs as O
+from oracle.pyref.merlin import L, Transcript
+from tests import circuits as C
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "r1cs_small.json")))
+
+
+def _buf(n=32):
+    return ctypes.create_string_buffer(n)
+
+
+def test_c_merlin_kat():
+    out = _buf(32)
+    coracle.lib().bpo_merlin_kat(b"test protocol", 13, b"some label", b"some data", 9, b"challenge", out, 32)
+    assert out.raw.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_c_scalar_ops_match_bigint():
+    lib = coracle.lib()
+    rnd = random.Random(1)
+    for _ in range(200):
+        a, b = rnd.randrange(L), rnd.randrange(1, L)
+        out = _buf()
+        lib.bpo_scalar_mul(a.to_bytes(32, "little"), b.to_bytes(32, "little"), out)
+        assert int.from_bytes(out.raw, "little") == a * b % L
+        lib.bpo_scalar_invert(b.to_bytes(32, "little"), out)
+        assert int.from_bytes(out.raw, "little") == pow(b, L - 2, L)
+        w = rnd.randrange(1 << 512)
+        lib.bpo_scalar_from_wide(w.to_bytes(64, "little"), out)
+        assert int.from_bytes(out.raw, "little") == w % L
+    for w in (0, L, L - 1, (1 << 512) - 1, L << 250):
+        out = _buf()
+        lib.bpo_scalar_from_wide(w.to_bytes(64, "little"), out)
+        assert int.from_bytes(out.raw, "little") == w % L
+
+
+def test_c_ristretto_codec_and_elligator():
+    lib = coracle.lib()
+    for i in range(64):
+        u = hashlib.shake_256(b"uniform-%d" % i).digest(64)
+        out = _buf()
+        lib.bpo_from_uniform(u, out)
+        want = ed.from_uniform_bytes(u).compress()
+        assert out.raw == want
+        back = _buf()
+        assert lib.bpo_decompress_compress(want, back) == 0 and back.raw == want
+    from tests.test_oracle_anchors import RFC9496_BAD, RFC9496_MULTIPLES
+    for enc in RFC9496_BAD:
+        assert lib.bpo_decompress_compress(bytes.fromhex(enc), _buf()) == -1
+    for enc in RFC9496_MULTIPLES:
+        back = _buf()
+        assert lib.bpo_decompress_compress(bytes.fromhex(enc), back) == 0 and back.raw.hex() == enc
+
+
+def test_c_generators_match_golden_and_python():
+    g = GOLDEN["generators"]
+    assert [x.hex() for x in coracle.gens("G", 0, 16)] == g["G"]
+    assert [x.hex() for x in coracle.gens("H", 0, 16)] == g["H"]
+    assert coracle.gens("B", 0, 1)[0].hex() == g["B"]
+    assert coracle.gens("B_blinding", 0, 1)[0].hex() == g["B_blinding"]
+    # later chain entries (the chain is one SHAKE256 stream: 64 bytes per point)
+    gens = O.BulletproofGens(40)
+    assert coracle.gens("G", 37, 3) == [p.compress() for p in gens.G[37:40]]
+    assert coracle.gens("H", 37, 3) == [p.compress() for p in gens.H[37:40]]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 33])
+def test_c_msm_small_matches_bigint(n):
+    rnd = random.Random(n)
+    pts = [ed.from_uniform_bytes(hashlib.shake_256(b"msm-pt-%d" % i).digest(64)) for i in range(n)]
+    enc = [p.compress() for p in pts]
+    sc = [rnd.randrange(L) for _ in range(n)]
+    want = ed.msm(sc, pts).compress()
+    assert coracle.msm(sc, enc, constant_time=False) == want
+    assert coracle.msm(sc, enc, constant_time=True) == want
+
+
+@pytest.mark.parametrize("n", [189, 190, 191, 499, 500, 799, 800, 1100])
+def test_c_msm_algorithm_thresholds_agree(n):
+    """vartime Straus (<190) / Pippenger w=6 (<500) / w=7 (<800) / w=8 vs constant-time Straus: same bytes."""
+    rnd = random.Random(n)
+    sG = b"".join(rnd.randrange(L).to_bytes(32, "little") for _ in range(n // 2))
+    sH = b"".join(rnd.randrange(L).to_bytes(32, "little") for _ in range(n - n // 2 - 2))
+    sB, sBb = rnd.randrange(L).to_bytes(32, "little"), rnd.randrange(L).to_bytes(32, "little")
+    a = coracle.msm_gens(sG, sH, sB, sBb, constant_time=False)
+    b = coracle.msm_gens(sG, sH, sB, sBb, constant_time=True)
+    assert a == b and a != bytes(32)
+
+
+def test_c_msm_edge_scalars():
+    """0, 1, l-1, and Scalar::from_bits values >= l (2^255-1) -- reduced by arithmetic like dalek."""
+    enc = coracle.gens("G", 0, 4)
+    pts = [ed.decompress(e) for e in enc]
+    sc = [0, 1, L - 1, (1 << 255) - 1]
+    want = ed.msm([s % L for s in sc], pts).compress()
+    assert coracle.msm(sc, enc) == want
+    assert coracle.msm(sc, enc, constant_time=True) == want
+    assert coracle.msm([0, 0], enc[:2]) == bytes(32)
+    assert coracle.msm([5], [bytes.fromhex("00" + "ff" * 31)]) is None  # undecodable point
+
+
+class _Recorder:
+    """Runs a tests/circuits.py builder against the python oracle prover and keeps the flat statement."""
+
+    def __init__(self, circ):
+        ob = C.OracleBackend()
+        T = ob.transcript(circ.label)
+        p = ob.prover(T)
+        self.blind = [C.det_scalar(circ.blind_tag, i) for i in range(len(circ.values))]
+        vars_ = [p.commit(v, b)[1] for v, b in zip(circ.values, self.blind)]
+        circ.builder(ob, p, vars_, circ.values)
+        self.p, self.label, self.values = p, circ.label, circ.values
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN["cases"]))
+def test_c_prover_verifier_match_golden(name):
+    case = GOLDEN["cases"][name]
+    circ = eval("C." + case["make"])
+    rec = _Recorder(circ)
+    p = rec.p
+    proof, coms = coracle.prove(rec.label, rec.values, rec.blind, p.a_L, p.a_R, p.a_O, p.constraints,
+                                bytes.fromhex(GOLDEN["seed_prove"]))
+    assert [c.hex() for c in coms] == case["commitments"]
+    assert proof.hex() == case["proof"]
+    n = len(p.a_L)
+    assert coracle.verify(rec.label, coms, n, p.constraints, proof, b"\x09" * 32) is True
+    assert coracle.verify(b"other label", coms, n, p.constraints, proof, b"\x09" * 32) is False
+    bad = bytearray(proof)
+    bad[1 + 8 * 32] ^= 1  # t_x
+    assert coracle.verify(rec.label, coms, n, p.constraints, bytes(bad), b"\x09" * 32) is False
+    assert coracle.verify(rec.label, coms, n, p.constraints, proof[:-1], b"\x09" * 32) == "format"
+    # the python oracle accepts the C oracle's proof and reproduces the golden bytes itself
+    ob = C.OracleBackend()
+    assert circ.verify(ob, proof, coms) is True
+
+
+def test_python_oracle_reproduces_golden():
+    ob = C.OracleBackend()
+    for name in ("empty", "mul3", "range-8-1"):
+        case = GOLDEN["cases"][name]
+        proof, coms = eval("C." + case["make"]).prove(ob, bytes.fromhex(GOLDEN["seed_prove"]))
+        assert proof.hex() == case["proof"] and [c.hex() for c in coms] == case["commitments"]
+
+
+def test_proof_length_formula_and_codec():
+    """R1CSProof bytes = 1 + 11*32 + (2 lg n' + 2)*32 in the 1-phase case."""
+    for name, case in GOLDEN["cases"].items():
+        proof = bytes.fromhex(case["proof"])
+        assert proof[0] == 0 and (len(proof) - 1) % 32 == 0
+        pr = O.R1CSProof.from_bytes(proof)
+        assert pr.to_bytes() == proof
+        lg = (len(proof) - 1 - 13 * 32) // 64
+        assert len(proof) == 1 + 11 * 32 + (2 * lg + 2) * 32
+    with pytest.raises(O.FormatError):
+        O.R1CSProof.from_bytes(b"\x02" + bytes(13 * 32))
+    with pytest.raises(O.FormatError):
+        O.R1CSProof.from_bytes(b"")
