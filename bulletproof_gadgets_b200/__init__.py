@@ -19,6 +19,8 @@ from .api import (  # noqa: F401
     Transcript,
     Variable,
     Verifier,
+    pinned_copy,
+    pinned_empty,
     prove,
     verify,
 )

@@ -31,7 +31,10 @@ _u32p = POINTER(c_uint32)
 PROTOTYPES = {
     "bpg_last_error": (c_char_p, []),
     "bpg_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "bpg_ctx_create_shared": (c_int, [c_void_p, POINTER(c_void_p)]),
     "bpg_ctx_destroy": (None, [c_void_p]),
+    "bpg_host_alloc": (c_void_p, [c_size_t]),
+    "bpg_host_free": (None, [c_void_p]),
     "bpg_ctx_set": (c_int, [c_void_p, c_char_p, c_int64]),
     "bpg_ctx_get": (c_int64, [c_void_p, c_char_p]),
     "bpg_gens_ensure": (c_int, [c_void_p, c_uint64]),
@@ -48,28 +51,28 @@ PROTOTYPES = {
     "bpg_prover_new": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "bpg_prover_free": (None, [c_void_p]),
     "bpg_prover_commit": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, _u32p]),
-    "bpg_prover_commit_batch": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_char_p, _u32p]),
+    "bpg_prover_commit_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_char_p, _u32p]),
     "bpg_prover_allocate_multiplier": (c_int, [c_void_p, c_char_p, c_char_p, _u32p]),
     "bpg_prover_multiply": (c_int, [c_void_p, _u32p, c_char_p, c_size_t, _u32p, c_char_p, c_size_t, _u32p]),
     "bpg_prover_constrain": (c_int, [c_void_p, _u32p, c_char_p, c_size_t]),
-    "bpg_prover_load_cs": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_void_p, c_void_p, c_char_p, c_uint64]),
+    "bpg_prover_load_cs": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64]),
     "bpg_prover_num_constraints": (c_uint64, [c_void_p]),
     "bpg_prover_num_multipliers": (c_uint64, [c_void_p]),
     "bpg_prover_prove": (c_int, [c_void_p, c_char_p, c_char_p, c_size_t, POINTER(c_size_t)]),
-    "bpg_circuit_create": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_char_p, c_uint64,
+    "bpg_circuit_create": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64,
                                    POINTER(c_void_p)]),
-    "bpg_circuit_set_witness": (c_int, [c_void_p, c_char_p, c_char_p]),
+    "bpg_circuit_set_witness": (c_int, [c_void_p, c_void_p, c_void_p]),
     "bpg_circuit_free": (None, [c_void_p]),
     "bpg_prover_attach": (c_int, [c_void_p, c_void_p]),
     "bpg_verifier_attach": (c_int, [c_void_p, c_void_p]),
     "bpg_verifier_new": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "bpg_verifier_free": (None, [c_void_p]),
     "bpg_verifier_commit": (c_int, [c_void_p, c_char_p, _u32p]),
-    "bpg_verifier_commit_batch": (c_int, [c_void_p, c_char_p, c_uint64, _u32p]),
+    "bpg_verifier_commit_batch": (c_int, [c_void_p, c_void_p, c_uint64, _u32p]),
     "bpg_verifier_allocate_multiplier": (c_int, [c_void_p, _u32p]),
     "bpg_verifier_multiply": (c_int, [c_void_p, _u32p, c_char_p, c_size_t, _u32p, c_char_p, c_size_t, _u32p]),
     "bpg_verifier_constrain": (c_int, [c_void_p, _u32p, c_char_p, c_size_t]),
-    "bpg_verifier_load_cs": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_char_p, c_uint64]),
+    "bpg_verifier_load_cs": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64]),
     "bpg_verifier_num_vars": (c_uint64, [c_void_p]),
     "bpg_verifier_verify": (c_int, [c_void_p, c_char_p, c_size_t, c_char_p]),
     "bpg_prove": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, c_char_p, c_char_p, c_char_p,

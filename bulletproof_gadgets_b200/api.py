@@ -25,12 +25,63 @@ def _sb(x):
     return x.to_bytes(32, "little")
 
 
+def _buf(x):
+    """bytes / bytearray / numpy array -> something ctypes passes as a pointer (None for empty)."""
+    if x is None:
+        return None
+    if isinstance(x, (bytes, bytearray)):
+        return bytes(x) or None
+    return x.ctypes.data if x.size else None          # numpy (e.g. pinned_empty)
+
+
+def _nbytes(x):
+    return len(x) if isinstance(x, (bytes, bytearray)) else x.nbytes
+
+
+def _scalars(xs):
+    """list of ints / 32-byte strings, or an already packed buffer -> (pointer-able, count)."""
+    if isinstance(xs, (list, tuple)):
+        b = b"".join(_sb(x) for x in xs)
+        return b or None, len(xs)
+    return _buf(xs), _nbytes(xs) // 32
+
+
+def pinned_empty(nbytes):
+    """numpy uint8 array over page-locked host memory (bpg_host_alloc): buffers handed to the bulk
+    loaders from here are uploaded by asynchronous DMA."""
+    import numpy as np
+    import weakref
+    nbytes = int(nbytes)
+    p = lib().bpg_host_alloc(nbytes)
+    if not p:
+        raise BpgError(_capi.E_CUDA, (lib().bpg_last_error() or b"").decode())
+    arr = np.ctypeslib.as_array((ctypes.c_uint8 * max(nbytes, 1)).from_address(p))[:nbytes]
+    weakref.finalize(arr, lib().bpg_host_free, p)
+    return arr
+
+
+def pinned_copy(data, dtype=None):
+    """Copies bytes / a numpy array into pinned memory; returns a numpy view of the same dtype."""
+    import numpy as np
+    src = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data)
+    out = pinned_empty(src.nbytes)
+    out[:] = src.view(np.uint8).reshape(-1)
+    return out.view(dtype or src.dtype)
+
+
 class Context:
     """One per GPU: device streams, cached generator tables, work buffers (bpg_ctx)."""
 
-    def __init__(self, device=0):
-        self._h = c_void_p()
-        check(lib().bpg_ctx_create(device, byref(self._h)))
+    def __init__(self, device=0, _h=None):
+        self._h = c_void_p() if _h is None else _h
+        if _h is None:
+            check(lib().bpg_ctx_create(device, byref(self._h)))
+
+    def shared(self):
+        """Another context on the same GPU (own stream + work buffers, generator tables shared)."""
+        h = c_void_p()
+        check(lib().bpg_ctx_create_shared(self._h, byref(h)))
+        return Context(_h=h)
 
     def close(self):
         if self._h:
@@ -191,12 +242,12 @@ class Circuit:
     def __init__(self, ctx, n, m, row_start, term_var, term_coef, q):
         self.ctx, self.n, self.m, self.q = ctx, n, m, q
         self._h = c_void_p()
-        check(lib().bpg_circuit_create(ctx._h, n, m, row_start.ctypes.data, term_var.ctypes.data, term_coef, q,
+        check(lib().bpg_circuit_create(ctx._h, n, m, row_start.ctypes.data, term_var.ctypes.data, _buf(term_coef), q,
                                        byref(self._h)))
 
     def set_witness(self, aL, aR):
-        assert len(aL) == len(aR) == 32 * self.n
-        check(lib().bpg_circuit_set_witness(self._h, aL or None, aR or None))
+        assert _nbytes(aL) == _nbytes(aR) == 32 * self.n
+        check(lib().bpg_circuit_set_witness(self._h, _buf(aL), _buf(aR)))
         return self
 
     def __del__(self):
@@ -235,12 +286,23 @@ class Prover(_CS):
         return out.raw, Variable(var.value)
 
     def commit_batch(self, vs, blindings):
-        k = len(vs)
+        """k commitments in one launch.  vs / blindings: lists of scalars or packed k*32-byte buffers."""
+        bv, k = _scalars(vs)
+        bb, kb = _scalars(blindings)
+        assert k == kb
         out = ctypes.create_string_buffer(32 * max(k, 1))
         first = c_uint32()
-        check(lib().bpg_prover_commit_batch(self._h, b"".join(_sb(v) for v in vs),
-                                            b"".join(_sb(b) for b in blindings), k, out, byref(first)))
-        return [(out.raw[32 * i: 32 * i + 32], Variable(first.value + i)) for i in range(k)]
+        check(lib().bpg_prover_commit_batch(self._h, bv, bb, k, out, byref(first)))
+        raw = out.raw
+        return [(raw[32 * i: 32 * i + 32], Variable(first.value + i)) for i in range(k)]
+
+    def commit_batch_packed(self, vs, blindings):
+        """Same, returning the k commitments as one k*32-byte string."""
+        bv, k = _scalars(vs)
+        bb, _ = _scalars(blindings)
+        out = ctypes.create_string_buffer(32 * max(k, 1))
+        check(lib().bpg_prover_commit_batch(self._h, bv, bb, k, out, None))
+        return out.raw[: 32 * k]
 
     def allocate_multiplier(self, assignment):
         if assignment is None:
@@ -263,9 +325,9 @@ class Prover(_CS):
     def load_cs(self, aL, aR, row_start, term_var, term_coef, q):
         """Bulk allocate_multiplier + constrain: aL/aR are n*32 bytes, constraints a CSR term list
         (numpy uint32 row_start[q+1], term_var[nnz]; term_coef nnz*32 bytes)."""
-        assert len(aL) == len(aR) and len(aL) % 32 == 0
-        check(lib().bpg_prover_load_cs(self._h, aL or None, aR or None, len(aL) // 32, row_start.ctypes.data,
-                                       term_var.ctypes.data, term_coef, q))
+        assert _nbytes(aL) == _nbytes(aR) and _nbytes(aL) % 32 == 0
+        check(lib().bpg_prover_load_cs(self._h, _buf(aL), _buf(aR), _nbytes(aL) // 32, row_start.ctypes.data,
+                                       term_var.ctypes.data, _buf(term_coef), q))
 
     def num_constraints(self):
         return lib().bpg_prover_num_constraints(self._h)
@@ -308,9 +370,13 @@ class Verifier(_CS):
         return Variable(var.value)
 
     def commit_batch(self, Vs):
+        """Vs: list of 32-byte commitments or one packed k*32-byte string."""
+        if isinstance(Vs, (list, tuple)):
+            Vs = b"".join(Vs)
+        k = len(Vs) // 32
         first = c_uint32()
-        check(lib().bpg_verifier_commit_batch(self._h, b"".join(Vs), len(Vs), byref(first)))
-        return [Variable(first.value + i) for i in range(len(Vs))]
+        check(lib().bpg_verifier_commit_batch(self._h, Vs or None, k, byref(first)))
+        return [Variable(first.value + i) for i in range(k)]
 
     def allocate_multiplier(self, assignment=None):
         arr = (c_uint32 * 3)()
@@ -329,7 +395,7 @@ class Verifier(_CS):
         check(lib().bpg_verifier_constrain(self._h, v, c, n))
 
     def load_cs(self, n, row_start, term_var, term_coef, q):
-        check(lib().bpg_verifier_load_cs(self._h, n, row_start.ctypes.data, term_var.ctypes.data, term_coef, q))
+        check(lib().bpg_verifier_load_cs(self._h, n, row_start.ctypes.data, term_var.ctypes.data, _buf(term_coef), q))
 
     def num_vars(self):
         return lib().bpg_verifier_num_vars(self._h)

@@ -27,6 +27,18 @@ extern "C" {
 
 const char* bpg_last_error(void) { return g_err; }
 
+static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
+    bpg_ctx* ctx = new bpg_ctx();
+    ctx->device = device;
+    ctx->store = store;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_a));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_b));
+    CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
+    *out = ctx;
+    return BPG_OK;
+}
+
 int bpg_ctx_create(int device, bpg_ctx** out) {
     if (!out) return BPG_E_ARG;
     *out = nullptr;
@@ -48,22 +60,31 @@ int bpg_ctx_create(int device, bpg_ctx** out) {
         bpg_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return BPG_E_CUDA;
     }
-    bpg_ctx* ctx = new bpg_ctx();
-    ctx->device = device;
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&ctx->ev_a));
-    CUDA_TRY(cudaEventCreate(&ctx->ev_b));
-    CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
-    *out = ctx;
-    return BPG_OK;
+    // per-proof device buffers come from the stream-ordered pool: keep freed memory cached
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return ctx_new(device, new GensStore(), out);
+}
+
+int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
+    if (!parent || !out) return BPG_E_ARG;
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(parent->device));
+    {
+        std::lock_guard<std::mutex> lock(parent->store->mu);
+        parent->store->refs++;
+    }
+    int rc = ctx_new(parent->device, parent->store, out);
+    if (rc == BPG_OK) (*out)->task_len = parent->task_len;
+    return rc;
 }
 
 void bpg_ctx_destroy(bpg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->table.rows) cudaFree(ctx->table.rows);
-    if (ctx->gens_ext) cudaFree(ctx->gens_ext);
     MsmWork& w = ctx->work;
     w.hist.release();
     w.bucket_off.release();
@@ -75,14 +96,26 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     w.meta.release();
     ctx->d_scalars.release();
     ctx->d_points.release();
-    if (ctx->ped) cudaFree(ctx->ped);
     r1cs_release_work(ctx);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
     cudaStreamDestroy(ctx->stream);
+    gens_store_release(ctx->store);
     delete ctx;
+}
+
+void* bpg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        bpg_set_error("bpg_host_alloc(%zu): pinned allocation failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void bpg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
@@ -93,11 +126,14 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
         ctx->task_len = (int)value;
     } else if (k == "window_bits") {
         if (value != 0 && (value < 4 || value > 16)) return BPG_E_ARG;
-        if (ctx->table.rows && value != ctx->window_bits) {  // force a rebuild on next ensure
-            cudaFree(ctx->table.rows);
+        GensStore* g = ctx->store;
+        std::lock_guard<std::mutex> lock(g->mu);
+        if (g->table.rows && value != g->window_bits) {  // force a rebuild on next ensure
+            g->garbage.push_back(g->table.rows);
+            g->table = FixedTable();
             ctx->table = FixedTable();
         }
-        ctx->window_bits = (int)value;
+        g->window_bits = (int)value;
     } else if (k == "time_accum") {
         ctx->time_accum = value != 0;
         ctx->sum_accum_ms = 0;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -72,6 +73,20 @@ struct FixedTable {
     uint64_t capacity = 0;  // generator capacity: points are [G_0..G_cap-1, H_0..H_cap-1, B, B_blinding]
 };
 
+// Generator tables of one GPU, shared by every context created on it with bpg_ctx_create_shared
+// (contexts = independent streams + work buffers; the 400 MB fixed-base table exists once).
+// Superseded tables are kept until the store dies, so a context may keep using its snapshot while
+// another one grows the capacity.
+struct GensStore {
+    std::mutex mu;
+    FixedTable table;
+    ge_ext* gens_ext = nullptr;
+    ge_niels* ped = nullptr;
+    int window_bits = 0;  // 0 = auto
+    std::vector<void*> garbage;
+    int refs = 1;
+};
+
 struct MsmWork {
     DevBuf<uint32_t> hist;       // [nsets*nb] counts, then reused as scatter cursors
     DevBuf<uint32_t> bucket_off; // [nsets*nb]
@@ -86,6 +101,8 @@ struct MsmWork {
 struct bpg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    GensStore* store = nullptr;  // shared per GPU
+    // snapshots of the store taken by gens_build() at the start of every operation
     FixedTable table;
     ge_ext* gens_ext = nullptr;  // untabulated generators (extended), same order as the table
     MsmWork work;
@@ -94,11 +111,9 @@ struct bpg_ctx {
     size_t h_stage_cap = 0;
     DevBuf<uint32_t> d_scalars;  // staging for host-provided scalars
     DevBuf<ge_ext> d_points;     // result slots of asynchronous MSMs
-    ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu)
-    uint64_t ped_capacity = 0;
+    ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu); snapshot
     struct ProofWork* pw = nullptr;  // reusable device vectors of the R1CS driver (r1cs.cu)
     int task_len = 32;
-    int window_bits = 0;  // 0 = auto
     // counters for bench.py ("gpu_launches")
     uint64_t launches = 0;
     // timing of the dominant kernel (accumulate), CUDA events on ctx stream
@@ -118,7 +133,8 @@ int fetch_points(bpg_ctx* ctx, const ge_ext* d_pts, uint32_t n, ge_ext* h_out);
 // r1cs.cu
 void r1cs_release_work(bpg_ctx* ctx);
 // gens.cu
-int gens_build(bpg_ctx* ctx, uint64_t capacity);
+int gens_build(bpg_ctx* ctx, uint64_t capacity);  // ensures capacity in the shared store and refreshes ctx snapshots
+void gens_store_release(GensStore* g);
 int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out);
 // host_fe.cpp
 void host_ristretto_compress(uint8_t out[32], const ge_ext& p);

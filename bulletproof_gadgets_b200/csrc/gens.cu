@@ -7,6 +7,7 @@
 // the window multiples 2^(c*w)*P and the affine-Niels normalisation run on the GPU.  The reference
 // rebuilds the generators on every run; here they are cached per context.
 #include "ctx.hpp"
+#include "kernels.hpp"
 #include "merlin.hpp"
 
 __global__ void __launch_bounds__(128) k_uniform_to_ext(const uint8_t* __restrict__ uniform, ge_ext* __restrict__ out,
@@ -72,13 +73,25 @@ static const uint8_t BASEPOINT_COMPRESSED[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0
                                                  0x61, 0xc5, 0x00, 0x51, 0x5f, 0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82,
                                                  0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
 
+static void snapshot(bpg_ctx* ctx) {
+    GensStore* g = ctx->store;
+    ctx->table = g->table;
+    ctx->gens_ext = g->gens_ext;
+    ctx->ped = g->ped;
+}
+
 int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     if (capacity == 0) capacity = 1;
-    if (ctx->table.rows && ctx->table.capacity >= capacity) return BPG_OK;
+    GensStore* g = ctx->store;
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (g->table.rows && g->table.capacity >= capacity) {
+        snapshot(ctx);
+        return BPG_OK;
+    }
     // grow geometrically so repeated small requests do not rebuild
-    uint64_t cap = ctx->table.capacity ? ctx->table.capacity : 1;
+    uint64_t cap = g->table.capacity ? g->table.capacity : 1;
     while (cap < capacity) cap *= 2;
-    const int c = ctx->window_bits ? ctx->window_bits : 16;
+    const int c = g->window_bits ? g->window_bits : 16;
     const int K = (256 + c - 1) / c;
     const uint64_t n = 2 * cap + 2;
     if ((uint64_t)K * n >= (1ull << 31)) {
@@ -104,12 +117,14 @@ int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     ge_ext* d_ext = nullptr;
     ge_ext* d_tmp = nullptr;
     ge_niels* d_rows = nullptr;
+    ge_niels* d_ped = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_uni, uni.size()));
     CUDA_TRY(cudaMalloc((void**)&d_bp, 32));
     CUDA_TRY(cudaMalloc((void**)&d_fail, 4));
     CUDA_TRY(cudaMalloc((void**)&d_ext, n * sizeof(ge_ext)));
     CUDA_TRY(cudaMalloc((void**)&d_tmp, (size_t)K * n * sizeof(ge_ext)));
     CUDA_TRY(cudaMalloc((void**)&d_rows, (size_t)K * n * sizeof(ge_niels)));
+    CUDA_TRY(cudaMalloc((void**)&d_ped, 1024 * sizeof(ge_niels)));
     CUDA_TRY(cudaMemcpyAsync(d_uni, uni.data(), uni.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_bp, BASEPOINT_COMPRESSED, 32, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_fail, 0, 4, st));
@@ -119,22 +134,41 @@ int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     k_window_multiples<<<(n32 + 127) / 128, 128, 0, st>>>(d_ext, d_tmp, n32, c, K);
     const uint64_t total = (uint64_t)K * n;
     k_to_niels<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(d_tmp, d_rows, total);
-    ctx->launches += 4;
+    pk_pedersen_table(st, d_ext, (uint32_t)(2 * cap), d_ped);
+    ctx->launches += 5;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(d_uni);
     cudaFree(d_bp);
     cudaFree(d_fail);
     cudaFree(d_tmp);
-    if (ctx->table.rows) cudaFree(ctx->table.rows);
-    if (ctx->gens_ext) cudaFree(ctx->gens_ext);
-    ctx->gens_ext = d_ext;
-    ctx->table.rows = d_rows;
-    ctx->table.n_points = n32;
-    ctx->table.c = c;
-    ctx->table.K = K;
-    ctx->table.capacity = cap;
+    // other contexts of this GPU may still be reading the superseded tables: keep them until the store dies
+    if (g->table.rows) g->garbage.push_back(g->table.rows);
+    if (g->gens_ext) g->garbage.push_back(g->gens_ext);
+    if (g->ped) g->garbage.push_back(g->ped);
+    g->gens_ext = d_ext;
+    g->ped = d_ped;
+    g->table.rows = d_rows;
+    g->table.n_points = n32;
+    g->table.c = c;
+    g->table.K = K;
+    g->table.capacity = cap;
+    snapshot(ctx);
     return BPG_OK;
+}
+
+void gens_store_release(GensStore* g) {
+    bool last;
+    {
+        std::lock_guard<std::mutex> lock(g->mu);
+        last = --g->refs == 0;
+    }
+    if (!last) return;
+    if (g->table.rows) cudaFree(g->table.rows);
+    if (g->gens_ext) cudaFree(g->gens_ext);
+    if (g->ped) cudaFree(g->ped);
+    for (void* p : g->garbage) cudaFree(p);
+    delete g;
 }
 
 int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out) {

@@ -18,6 +18,7 @@
 #include <array>
 #include <random>
 
+#include "circuit.hpp"
 #include "ctx.hpp"
 #include "host_sc.hpp"
 #include "kernels.hpp"
@@ -113,85 +114,18 @@ struct ConstraintStore {
     }
 };
 
-// transposed (by target) form of the constraints for the flatten kernel.
-// targets: [wL(n) | wR(n) | wO(n) | wV(m) | wc]
-struct Csc {
-    std::vector<uint32_t> col_start, col_row, long_targets;
-    std::vector<sc> col_coef;
-    uint32_t nt = 0;
-};
-static int build_csc(const ConstraintStore& cs, uint32_t n, uint32_t m, bool with_one, Csc* out) {
-    const uint32_t nt = 3 * n + m + 1;
-    out->nt = nt;
-    out->col_start.assign(nt + 1, 0);
-    const size_t q = cs.num_constraints();
-    auto target = [&](uint32_t v, uint32_t* t) -> bool {
-        uint32_t k = var_kind(v), i = var_idx(v);
-        switch (k) {
-            case V_LEFT: if (i >= n) return false; *t = i; return true;
-            case V_RIGHT: if (i >= n) return false; *t = n + i; return true;
-            case V_OUT: if (i >= n) return false; *t = 2 * n + i; return true;
-            case V_COMMITTED: if (i >= m) return false; *t = 3 * n + i; return true;
-            case V_ONE: *t = 3 * n + m; return true;
-            default: return false;
-        }
-    };
-    for (size_t e = 0; e < cs.term_var.size(); e++) {
-        uint32_t t;
-        if (!target(cs.term_var[e], &t)) {
-            bpg_set_error("constraint term %zu references an unknown variable 0x%08x", e, cs.term_var[e]);
-            return BPG_E_ARG;
-        }
-        if (t == 3 * n + m && !with_one) continue;
-        out->col_start[t + 1]++;
-    }
-    for (uint32_t t = 0; t < nt; t++) out->col_start[t + 1] += out->col_start[t];
-    const uint32_t nnz = out->col_start[nt];
-    out->col_row.resize(nnz ? nnz : 1);
-    out->col_coef.resize(nnz ? nnz : 1);
-    out->long_targets.clear();
-    for (uint32_t t = 0; t < nt; t++)
-        if (out->col_start[t + 1] - out->col_start[t] > FLATTEN_LONG) out->long_targets.push_back(t);
-    std::vector<uint32_t> cur(out->col_start.begin(), out->col_start.end() - 1);
-    for (size_t j = 0; j < q; j++) {
-        for (uint32_t e = cs.row_start[j]; e < cs.row_start[j + 1]; e++) {
-            uint32_t t;
-            target(cs.term_var[e], &t);
-            if (t == 3 * n + m && !with_one) continue;
-            uint32_t pos = cur[t]++;
-            out->col_row[pos] = (uint32_t)j;
-            out->col_coef[pos] = cs.term_coef[e];
-        }
-    }
-    return BPG_OK;
-}
-
 // ------------------------------------------------------------------------------------------
 // prover / verifier objects
 // ------------------------------------------------------------------------------------------
-// device-resident circuit: transposed constraints (always including the `One` column, which the prover
-// simply does not read) and, optionally, the multiplier assignments
-struct bpg_circuit {
-    bpg_ctx* ctx = nullptr;
-    uint32_t n = 0, m = 0, q = 0, nt = 0, nnz = 0;
-    uint32_t *d_col_start = nullptr, *d_col_row = nullptr, *d_long = nullptr;
-    uint32_t n_long = 0;
-    sc *d_col_coef = nullptr, *d_aL = nullptr, *d_aR = nullptr, *d_aO = nullptr;
-    bool has_witness = false;
-};
-__global__ void __launch_bounds__(256) k_mul_vec(const sc* a, const sc* b, sc* out, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = sc_mul(a[i], b[i]);
-}
-__global__ void __launch_bounds__(256) k_reduce_vec(sc* a, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = sc_reduce(a[i]);
-}
-
+// `circ` is either a caller-owned resident circuit (bpg_prover_attach) or `owned`: the device copy that
+// bpg_prover_load_cs builds directly from the caller's arrays (no host-side constraint store at all).
+// Op-by-op calls (multiply / allocate_multiplier / constrain) fill the host store `cs` instead, which
+// prove() uploads and transposes on the device.
 struct bpg_prover {
     bpg_ctx* ctx;
     bpg::Transcript* T;
     const bpg_circuit* circ = nullptr;
+    bpg_circuit* owned = nullptr;
     ConstraintStore cs;
     std::vector<sc> aL, aR, aO, v, vbl;                // canonical
     std::vector<std::array<uint8_t, 32>> vbl_raw;     // as given (rekeys the transcript rng)
@@ -200,6 +134,7 @@ struct bpg_verifier {
     bpg_ctx* ctx;
     bpg::Transcript* T;
     const bpg_circuit* circ = nullptr;
+    bpg_circuit* owned = nullptr;
     ConstraintStore cs;
     std::vector<std::array<uint8_t, 32>> V;
     uint64_t num_vars = 0;
@@ -231,41 +166,25 @@ struct CscView {
     const sc* col_coef;
     uint32_t nt, n_long;
 };
-// device view of the transposed constraints: the attached circuit's, or an upload of the host store
-static int csc_view(bpg_ctx* ctx, ProofWork* pw, const bpg_circuit* circ, const ConstraintStore& cs, uint32_t n,
-                    uint32_t m, CscView* out) {
-    if (circ) {
-        out->col_start = circ->d_col_start;
-        out->col_row = circ->d_col_row;
-        out->col_coef = circ->d_col_coef;
-        out->nt = circ->nt;
-        out->long_targets = circ->d_long;
-        out->n_long = circ->n_long;
-        return BPG_OK;
-    }
-    Csc csc;
-    int rc;
-    if ((rc = build_csc(cs, n, m, true, &csc))) return rc;
-    const uint32_t nnz = csc.col_start[csc.nt];
-    if ((rc = pw->col_start.ensure(csc.nt + 1)) || (rc = pw->col_row.ensure(nnz + 1)) ||
-        (rc = pw->col_coef.ensure(nnz + 1)) || (rc = pw->long_t.ensure(csc.long_targets.size() + 1)))
-        return rc;
-    cudaStream_t st = ctx->stream;
-    if (!csc.long_targets.empty())
-        CUDA_TRY(cudaMemcpyAsync(pw->long_t.p, csc.long_targets.data(), 4 * csc.long_targets.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pw->col_start.p, csc.col_start.data(), 4 * (size_t)(csc.nt + 1), cudaMemcpyHostToDevice, st));
-    if (nnz) {
-        CUDA_TRY(cudaMemcpyAsync(pw->col_row.p, csc.col_row.data(), 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pw->col_coef.p, csc.col_coef.data(), 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
-    }
-    out->col_start = pw->col_start.p;
-    out->col_row = pw->col_row.p;
-    out->col_coef = pw->col_coef.p;
-    out->nt = csc.nt;
-    out->long_targets = pw->long_t.p;
-    out->n_long = (uint32_t)csc.long_targets.size();
-    return BPG_OK;
+static CscView csc_view(const bpg_circuit* circ) {
+    CscView v;
+    v.col_start = circ->d_col_start;
+    v.col_row = circ->d_col_row;
+    v.col_coef = circ->d_col_coef;
+    v.nt = circ->nt;
+    v.long_targets = circ->d_long;
+    v.n_long = circ->n_long;
+    return v;
 }
+// per-proof circuit of the op-by-op path: uploads the host store and transposes it on the device
+static int circuit_from_store(bpg_ctx* ctx, const ConstraintStore& cs, uint64_t n, uint64_t m, bpg_circuit** out) {
+    return circuit_build(ctx, n, m, cs.num_constraints(), cs.row_start.data(), cs.term_var.data(),
+                         reinterpret_cast<const uint8_t*>(cs.term_coef.data()), true, out);
+}
+struct CircuitGuard {  // frees a per-proof circuit on every exit path
+    bpg_circuit* c = nullptr;
+    ~CircuitGuard() { circuit_free(c); }
+};
 
 static void os_random(uint8_t out[32]) {
     std::random_device rd;
@@ -303,22 +222,11 @@ static uint32_t next_pow2(uint64_t n) {
     while (p < n) p <<= 1;
     return p;
 }
-static int ensure_pedersen_table(bpg_ctx* ctx) {
-    int rc = gens_build(ctx, 1);
-    if (rc) return rc;
-    if (ctx->ped && ctx->ped_capacity == ctx->table.capacity) return BPG_OK;
-    if (!ctx->ped) CUDA_TRY(cudaMalloc((void**)&ctx->ped, 1024 * sizeof(ge_niels)));
-    pk_pedersen_table(ctx->stream, ctx->gens_ext, (uint32_t)(2 * ctx->table.capacity), ctx->ped);
-    ctx->launches++;
-    ctx->ped_capacity = ctx->table.capacity;
-    return BPG_OK;
-}
-
 // k Pedersen commitments v_i*B + r_i*B_blinding -> compressed (host pointers, canonical scalars)
 static int pedersen_batch(bpg_ctx* ctx, const sc* v, const sc* r, uint64_t k, uint8_t* out32k) {
     if (k == 0) return BPG_OK;
     int rc;
-    if ((rc = ensure_pedersen_table(ctx))) return rc;
+    if ((rc = gens_build(ctx, 1))) return rc;
     ProofWork* pw = work(ctx);
     cudaStream_t st = ctx->stream;
     if ((rc = pw->ped_in.ensure(2 * k)) || (rc = pw->dyn_pts.ensure(k)) || (rc = pw->dyn_enc.ensure(32 * k)))
@@ -367,9 +275,17 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         bpg_set_error("prove: attached circuit needs a witness, m = #commitments, and no other constraints");
         return BPG_E_ARG;
     }
-    const uint32_t n = circ ? circ->n : (uint32_t)P->aL.size(), m = (uint32_t)P->v.size();
+    CircuitGuard per_proof;
+    if (!circ) {  // op-by-op path: upload + transpose the host store now
+        if ((rc = circuit_from_store(ctx, P->cs, P->aL.size(), P->v.size(), &per_proof.c))) return rc;
+        if ((rc = circuit_set_witness(per_proof.c, reinterpret_cast<const uint8_t*>(P->aL.data()),
+                                      reinterpret_cast<const uint8_t*>(P->aR.data()))))
+            return rc;
+        circ = per_proof.c;
+    }
+    const uint32_t n = circ->n, m = (uint32_t)P->v.size();
     const uint32_t npad = next_pow2(n ? n : 1);
-    const uint32_t q = circ ? circ->q : (uint32_t)P->cs.num_constraints();
+    const uint32_t q = circ->q;
     uint32_t lg = 0;
     while ((1u << lg) < npad) lg++;
 
@@ -382,14 +298,13 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     for (auto& b : P->vbl_raw) wit.push_back(b.data());
     bpg::TranscriptRng rng = T.build_rng(wit, seed);
 
-    if ((rc = gens_build(ctx, npad)) || (rc = ensure_pedersen_table(ctx))) return rc;
+    if ((rc = gens_build(ctx, npad))) return rc;
     const uint64_t cap = ctx->table.capacity;
     const uint64_t iB = 2 * cap, iBb = 2 * cap + 1;
 
     // device vectors
     const size_t nn = npad;
-    if ((rc = pw->aL.ensure(nn)) || (rc = pw->aR.ensure(nn)) || (rc = pw->aO.ensure(nn)) || (rc = pw->sL.ensure(nn)) ||
-        (rc = pw->sR.ensure(nn)) || (rc = pw->w.ensure(3 * (size_t)n + m + 1)) || (rc = pw->ypow.ensure(nn)) ||
+    if ((rc = pw->sL.ensure(nn)) || (rc = pw->sR.ensure(nn)) || (rc = pw->w.ensure(3 * (size_t)n + m + 1)) || (rc = pw->ypow.ensure(nn)) ||
         (rc = pw->yinv.ensure(nn)) || (rc = pw->zpow.ensure(q + 1)) || (rc = pw->l1.ensure(nn)) ||
         (rc = pw->r0.ensure(nn)) || (rc = pw->r1.ensure(nn)) || (rc = pw->r3.ensure(nn)) ||
         (rc = pw->lvec.ensure(nn)) || (rc = pw->rvec.ensure(nn)) || (rc = pw->sG.ensure(nn)) ||
@@ -401,16 +316,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     sc* small = pw->small.p;  // [0..2] blindings, [8..13] t1..t6, [16] t2_blinding, [20..21] cw, [24..25] a,b
     ge_ext* slots = ctx->d_points.p;
 
-    const sc *d_aL = pw->aL.p, *d_aR = pw->aR.p, *d_aO = pw->aO.p;
-    if (circ) {
-        d_aL = circ->d_aL;
-        d_aR = circ->d_aR;
-        d_aO = circ->d_aO;
-    } else if (n) {
-        CUDA_TRY(cudaMemcpyAsync(pw->aL.p, P->aL.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pw->aR.p, P->aR.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pw->aO.p, P->aO.data(), 32 * (size_t)n, cudaMemcpyHostToDevice, st));
-    }
+    const sc *d_aL = circ->d_aL, *d_aR = circ->d_aR, *d_aO = circ->d_aO;
     if (m) CUDA_TRY(cudaMemcpyAsync(pw->vbl.p, P->vbl.data(), 32 * (size_t)m, cudaMemcpyHostToDevice, st));
 
     // rng order: i, o, s blindings, then s_L[0..n), s_R[0..n)
@@ -446,11 +352,9 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     seg_push(segs, small + 2, iBb, 1, 0, 0, 1);
     if ((rc = msm_run(ctx, segs, 1, slots + 2))) return rc;  // S1
 
-    // transposed constraints (host work overlapping the S1 MSM)
-    CscView csc;
-    if ((rc = csc_view(ctx, pw, circ, P->cs, n, m, &csc))) return rc;
+    const CscView csc = csc_view(circ);
 
-    trace.mark("S1 msm + csc upload");
+    trace.mark("S1 msm");
     ge_ext hp[8];
     if ((rc = fetch_points(ctx, slots, 3, hp))) return rc;
     uint8_t A_I1[32], A_O1[32], S1[32];
@@ -657,9 +561,14 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
         bpg_set_error("verify: attached circuit needs m = #commitments and no other constraints");
         return BPG_E_ARG;
     }
-    const uint32_t n = circ ? circ->n : (uint32_t)Vf->num_vars, m = (uint32_t)Vf->V.size();
+    CircuitGuard per_proof;
+    if (!circ) {
+        if ((rc = circuit_from_store(ctx, Vf->cs, Vf->num_vars, Vf->V.size(), &per_proof.c))) return rc;
+        circ = per_proof.c;
+    }
+    const uint32_t n = circ->n, m = (uint32_t)Vf->V.size();
     const uint32_t npad = next_pow2(n ? n : 1);
-    const uint32_t q = circ ? circ->q : (uint32_t)Vf->cs.num_constraints();
+    const uint32_t q = circ->q;
     uint32_t lg = 0;
     while ((1u << lg) < npad) lg++;
 
@@ -723,8 +632,7 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     const uint64_t cap = ctx->table.capacity;
     const uint64_t iB = 2 * cap, iBb = 2 * cap + 1;
 
-    CscView csc;
-    if ((rc = csc_view(ctx, pw, circ, Vf->cs, n, m, &csc))) return rc;
+    const CscView csc = csc_view(circ);
     const uint32_t ndyn = 6 + m + 5 + 2 * lg;
     const size_t nn = npad;
     if ((rc = pw->w.ensure(3 * (size_t)n + m + 1)) || (rc = pw->yinv.ensure(nn)) || (rc = pw->zpow.ensure(q + 1)) ||
@@ -892,7 +800,11 @@ int bpg_prover_new(bpg_ctx* ctx, bpg_transcript* t, bpg_prover** out) {
     *out = p;
     return BPG_OK;
 }
-void bpg_prover_free(bpg_prover* p) { delete p; }
+void bpg_prover_free(bpg_prover* p) {
+    if (!p) return;
+    circuit_free(p->owned);
+    delete p;
+}
 
 int bpg_prover_commit_batch(bpg_prover* p, const uint8_t* v32k, const uint8_t* vb32k, uint64_t k, uint8_t* V_out32k,
                             uint32_t* first_var_out) {
@@ -982,36 +894,25 @@ int bpg_prover_constrain(bpg_prover* p, const uint32_t* vars, const uint8_t* coe
     p->cs.end();
     return BPG_OK;
 }
-static int load_constraints(ConstraintStore& cs, const uint32_t* row_start, const uint32_t* term_var,
-                            const uint8_t* term_coef32, uint64_t q) {
-    if (q == 0) return BPG_OK;
-    if (!row_start || !term_var || !term_coef32 || row_start[0] != 0) return BPG_E_ARG;
-    const uint32_t nnz = row_start[q];
-    cs.term_var.reserve(cs.term_var.size() + nnz);
-    cs.term_coef.reserve(cs.term_coef.size() + nnz);
-    for (uint64_t j = 0; j < q; j++) {
-        if (row_start[j + 1] < row_start[j]) return BPG_E_ARG;
-        int rc = cs.add_lc(term_var + row_start[j], term_coef32 + 32 * (size_t)row_start[j], row_start[j + 1] - row_start[j]);
-        if (rc) return rc;
-        cs.end();
-    }
-    return BPG_OK;
-}
-
 int bpg_prover_load_cs(bpg_prover* p, const uint8_t* aL32n, const uint8_t* aR32n, uint64_t n, const uint32_t* row_start,
                        const uint32_t* term_var, const uint8_t* term_coef32, uint64_t q) {
     if (!p || (n && (!aL32n || !aR32n))) return BPG_E_ARG;
-    p->aL.reserve(p->aL.size() + n);
-    p->aR.reserve(p->aR.size() + n);
-    p->aO.reserve(p->aO.size() + n);
-    for (uint64_t i = 0; i < n; i++) {
-        if ((aL32n[32 * i + 31] | aR32n[32 * i + 31]) & 0x80) return BPG_E_ARG;
-        const sc l = Scalar::from_bytes_mod_order(aL32n + 32 * i).s, r = Scalar::from_bytes_mod_order(aR32n + 32 * i).s;
-        p->aL.push_back(l);
-        p->aR.push_back(r);
-        p->aO.push_back(sc_mul(l, r));
+    if (p->circ || !p->aL.empty() || p->cs.num_constraints()) {
+        bpg_set_error("load_cs: the bulk loader must be the only constraint-system call on a prover");
+        return BPG_E_ARG;
     }
-    return load_constraints(p->cs, row_start, term_var, term_coef32, q);
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    // straight from the caller's arrays to HBM: upload, reduce mod l, a_O = a_L*a_R and the transposition all
+    // run on the device (no host-side constraint store)
+    int rc = circuit_build(p->ctx, n, p->v.size(), q, row_start, term_var, term_coef32, true, &p->owned);
+    if (rc) return rc;
+    if ((rc = circuit_set_witness(p->owned, aL32n, aR32n))) {
+        circuit_free(p->owned);
+        p->owned = nullptr;
+        return rc;
+    }
+    p->circ = p->owned;
+    return BPG_OK;
 }
 uint64_t bpg_prover_num_constraints(const bpg_prover* p) {
     return !p ? 0 : p->circ ? p->circ->q : p->cs.num_constraints();
@@ -1034,84 +935,13 @@ int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_ou
     return BPG_OK;
 }
 
-int bpg_circuit_create(bpg_ctx* ctx, uint64_t n, uint64_t m, const uint32_t* row_start, const uint32_t* term_var,
-                       const uint8_t* term_coef32, uint64_t q, bpg_circuit** out) {
-    if (!ctx || !out || n >= (1u << 29) || m >= (1u << 29)) return BPG_E_ARG;
-    *out = nullptr;
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    ConstraintStore cs;
-    int rc;
-    if ((rc = load_constraints(cs, row_start, term_var, term_coef32, q))) return rc;
-    Csc csc;
-    if ((rc = build_csc(cs, (uint32_t)n, (uint32_t)m, true, &csc))) return rc;
-    bpg_circuit* c = new bpg_circuit();
-    c->ctx = ctx;
-    c->n = (uint32_t)n;
-    c->m = (uint32_t)m;
-    c->q = (uint32_t)q;
-    c->nt = csc.nt;
-    c->nnz = csc.col_start[csc.nt];
-    cudaStream_t st = ctx->stream;
-    CUDA_TRY(cudaMalloc((void**)&c->d_col_start, 4 * (size_t)(c->nt + 1)));
-    CUDA_TRY(cudaMalloc((void**)&c->d_col_row, 4 * (size_t)(c->nnz + 1)));
-    CUDA_TRY(cudaMalloc((void**)&c->d_col_coef, 32 * (size_t)(c->nnz + 1)));
-    c->n_long = (uint32_t)csc.long_targets.size();
-    CUDA_TRY(cudaMalloc((void**)&c->d_long, 4 * (size_t)(c->n_long + 1)));
-    if (c->n_long)
-        CUDA_TRY(cudaMemcpyAsync(c->d_long, csc.long_targets.data(), 4 * (size_t)c->n_long, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_col_start, csc.col_start.data(), 4 * (size_t)(c->nt + 1), cudaMemcpyHostToDevice, st));
-    if (c->nnz) {
-        CUDA_TRY(cudaMemcpyAsync(c->d_col_row, csc.col_row.data(), 4 * (size_t)c->nnz, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->d_col_coef, csc.col_coef.data(), 32 * (size_t)c->nnz, cudaMemcpyHostToDevice, st));
-    }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    *out = c;
-    return BPG_OK;
-}
-int bpg_circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR32n) {
-    if (!c || (c->n && (!aL32n || !aR32n))) return BPG_E_ARG;
-    CUDA_TRY(cudaSetDevice(c->ctx->device));
-    const size_t n = c->n;
-    for (size_t i = 0; i < n; i++)
-        if ((aL32n[32 * i + 31] | aR32n[32 * i + 31]) & 0x80) return BPG_E_ARG;
-    cudaStream_t st = c->ctx->stream;
-    if (!c->d_aL) {
-        CUDA_TRY(cudaMalloc((void**)&c->d_aL, 32 * (n + 1)));
-        CUDA_TRY(cudaMalloc((void**)&c->d_aR, 32 * (n + 1)));
-        CUDA_TRY(cudaMalloc((void**)&c->d_aO, 32 * (n + 1)));
-    }
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(c->d_aL, aL32n, 32 * n, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->d_aR, aR32n, 32 * n, cudaMemcpyHostToDevice, st));
-        const uint32_t blocks = (uint32_t)((n + 255) / 256);
-        k_reduce_vec<<<blocks, 256, 0, st>>>(c->d_aL, (uint32_t)n);  // Scalar::from_bits values may be >= l
-        k_reduce_vec<<<blocks, 256, 0, st>>>(c->d_aR, (uint32_t)n);
-        k_mul_vec<<<blocks, 256, 0, st>>>(c->d_aL, c->d_aR, c->d_aO, (uint32_t)n);
-        c->ctx->launches += 3;
-    }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    c->has_witness = true;
-    return BPG_OK;
-}
-void bpg_circuit_free(bpg_circuit* c) {
-    if (!c) return;
-    cudaSetDevice(c->ctx->device);
-    cudaFree(c->d_col_start);
-    cudaFree(c->d_col_row);
-    cudaFree(c->d_col_coef);
-    cudaFree(c->d_long);
-    cudaFree(c->d_aL);
-    cudaFree(c->d_aR);
-    cudaFree(c->d_aO);
-    delete c;
-}
 int bpg_prover_attach(bpg_prover* p, const bpg_circuit* c) {
-    if (!p || !c || c->ctx != p->ctx) return BPG_E_ARG;
+    if (!p || !c || c->ctx->store != p->ctx->store || p->circ) return BPG_E_ARG;  // same GPU, nothing attached yet
     p->circ = c;
     return BPG_OK;
 }
 int bpg_verifier_attach(bpg_verifier* v, const bpg_circuit* c) {
-    if (!v || !c || c->ctx != v->ctx) return BPG_E_ARG;
+    if (!v || !c || c->ctx->store != v->ctx->store || v->circ) return BPG_E_ARG;
     v->circ = c;
     return BPG_OK;
 }
@@ -1125,7 +955,11 @@ int bpg_verifier_new(bpg_ctx* ctx, bpg_transcript* t, bpg_verifier** out) {
     *out = v;
     return BPG_OK;
 }
-void bpg_verifier_free(bpg_verifier* v) { delete v; }
+void bpg_verifier_free(bpg_verifier* v) {
+    if (!v) return;
+    circuit_free(v->owned);
+    delete v;
+}
 int bpg_verifier_commit(bpg_verifier* v, const uint8_t V[32], uint32_t* var_out) {
     if (!v || !V) return BPG_E_ARG;
     std::array<uint8_t, 32> a;
@@ -1180,8 +1014,15 @@ int bpg_verifier_constrain(bpg_verifier* v, const uint32_t* vars, const uint8_t*
 int bpg_verifier_load_cs(bpg_verifier* v, uint64_t n, const uint32_t* row_start, const uint32_t* term_var,
                          const uint8_t* term_coef32, uint64_t q) {
     if (!v) return BPG_E_ARG;
-    v->num_vars += n;
-    return load_constraints(v->cs, row_start, term_var, term_coef32, q);
+    if (v->circ || v->num_vars || v->cs.num_constraints()) {
+        bpg_set_error("load_cs: the bulk loader must be the only constraint-system call on a verifier");
+        return BPG_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(v->ctx->device));
+    int rc = circuit_build(v->ctx, n, v->V.size(), q, row_start, term_var, term_coef32, true, &v->owned);
+    if (rc) return rc;
+    v->circ = v->owned;
+    return BPG_OK;
 }
 uint64_t bpg_verifier_num_vars(const bpg_verifier* v) { return !v ? 0 : v->circ ? v->circ->n : v->num_vars; }
 int bpg_verifier_verify(bpg_verifier* v, const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32) {

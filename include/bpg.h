@@ -39,7 +39,14 @@ const char* bpg_last_error(void);
 /* ---- context and generators ------------------------------------------------------------ */
 /* One context per GPU.  Replaces nothing in the reference (it has no device state). */
 int bpg_ctx_create(int device, bpg_ctx** out);
+/* A second (third, ...) context on the same GPU as `parent`: its own stream and work buffers, the
+ * generator tables shared.  One host thread per context lets several proofs be in flight on one GPU:
+ * the sequential Merlin rng stream of one proof overlaps the MSMs of another. */
+int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out);
 void bpg_ctx_destroy(bpg_ctx* ctx);
+/* Page-locked host memory for buffers handed to the bulk loaders (uploads then run as async DMA). */
+void* bpg_host_alloc(size_t bytes);
+void bpg_host_free(void* p);
 /* tuning knobs: "task_len" (entries per accumulate task), "window_bits" (0 = auto) */
 int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value);
 /* counters: "launches" (kernels launched so far), "accum_us" / "accum_entries" (last timed MSM) */
