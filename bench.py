@@ -3,17 +3,21 @@
 `BOUND` 64-bit range statements x1024 in ONE R1CS proof, n = 2^17 multipliers, m = 3072 commitments).
 
 One "step" = one pass of the hot path over one statement: m Pedersen commitments + Prover::prove
-+ Verifier::verify (accepting).  Three legs:
-  value  constraint system and witness already resident in HBM (bpg_circuit); CUDA events on the
-         library stream; proofs verified inside the timed region.
-  e2e    the same step through the C ABI with HOST buffers (bpg_prover_load_cs / bpg_verifier_load_cs):
-         every host->device copy of witness / constraints and the device->host proof are inside the timer.
++ Verifier::verify (accepting).  Legs:
+  value  constraint system and witness already resident in HBM (bpg_circuit); proofs verified inside
+         the timed region.  `inflight` host threads (one bpg context = one stream each, generator
+         tables shared) keep several independent steps in flight on the GPU, because the prover's
+         Merlin TranscriptRng stream (2n dependent Keccak-f permutations) is a sequential host job.
+  e2e    the same steps through the C ABI with HOST buffers in pinned memory (bpg_prover_load_cs /
+         bpg_verifier_load_cs): every host->device copy of witness / constraints and the
+         device->host proof are inside the timer.
+  latency  one step at a time on one context (no overlap), resident circuit.
   cpu_baseline  the CPU restatement of dalek's algorithms (oracle/c, 1 core) on the same statement.
 `--impl reference` times that CPU restatement alone with all host cores (the real reference is pure
 Rust and cannot be built in this image: no cargo/rustc, crates not vendored).
 
-N > 1 (torchrun): every rank proves/verifies its own independent statement ("weak" scaling, no
-data-path collective); value = N statements / max-over-ranks time.
+N > 1 (torchrun): every rank proves/verifies its own independent statements ("weak" scaling, no
+data-path collective); value = all ranks' statements / max-over-ranks time.
 """
 import argparse
 import json
@@ -126,10 +130,11 @@ def run_reference(args, ws, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--count", type=int, default=1024, help="BOUND statements per proof (1024 = BASELINE config 2)")
+    ap.add_argument("--inflight", type=int, default=0, help="steps in flight per GPU (host threads); 0 = auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     ws, rank, local_rank = _dist()
@@ -144,28 +149,30 @@ def main():
     import bulletproof_gadgets_b200 as bpg
     from bulletproof_gadgets_b200 import build, workloads as W
     build.build_lib()
-    ctx = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
-    st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank)
-    ctx.gens_ensure(st.n)
-    circuit = bpg.Circuit(ctx, st.n, st.m, st.row_start, st.term_var, st.term_coef, st.q).set_witness(st.aL, st.aR)
-    stream = torch.cuda.ExternalStream(ctx.get("stream"), device=torch.device("cuda", local_rank))
+    warmup = max(args.warmup, 3)
+    inflight = args.inflight or max(1, min(6, (os.cpu_count() or 1) // ws))
+    ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
+    ctxs = [ctx0] + [ctx0.shared() for _ in range(inflight - 1)]
+    st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank).pin(bpg)
+    ctx0.gens_ensure(st.n)
+    circuit = bpg.Circuit(ctx0, st.n, st.m, st.row_start, st.term_var, st.term_coef, st.q).set_witness(st.aL, st.aR)
+    dev = torch.device("cuda", local_rank)
+    streams = [torch.cuda.ExternalStream(c.get("stream"), device=dev) for c in ctxs]
 
-    def step_resident(i):
+    def step_resident(ctx, i):
         seed = (i + 1).to_bytes(32, "little")
-        T = bpg.Transcript(st.label)
-        p = bpg.Prover(ctx, T)
-        coms = [c for c, _ in p.commit_batch(st.v, st.vbl)]
+        p = bpg.Prover(ctx, bpg.Transcript(st.label))
+        coms = p.commit_batch_packed(st.v_bytes, st.vbl_bytes)
         p.attach(circuit)
         proof = p.prove(seed)
-        T2 = bpg.Transcript(st.label)
-        vf = bpg.Verifier(ctx, T2)
+        vf = bpg.Verifier(ctx, bpg.Transcript(st.label))
         vf.commit_batch(coms)
         vf.attach(circuit)
         if not vf.verify(proof, seed):
             raise SystemExit("GPU proof did not verify")
         return proof
 
-    def step_e2e(i):
+    def step_e2e(ctx, i):
         seed = (i + 1).to_bytes(32, "little")
         proof, coms = W.prove_statement(bpg, ctx, st, seed)
         if not W.verify_statement(bpg, ctx, st, proof, coms, seed):
@@ -173,20 +180,49 @@ def main():
         return proof
 
     def barrier():
-        stream.synchronize()
+        for s in streams:
+            s.synchronize()
         torch.cuda.synchronize()
         if ws > 1:
             dist.barrier()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
+    def run_steps(fn, first, count, use_ctxs):
+        """`count` steps spread over the contexts: each host thread pulls the next step index."""
+        if len(use_ctxs) == 1:
+            for i in range(first, first + count):
+                fn(use_ctxs[0], i)
+            return
+        lock, nxt, errs = threading.Lock(), [first], []
+
+        def work(c):
+            try:
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= first + count:
+                        return
+                    fn(c, i)
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(c,)) for c in use_ctxs]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def timed(fn, steps, warm, use_ctxs):
+        run_steps(fn, 0, max(warm, len(use_ctxs)), use_ctxs)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record(stream)
+        e0.record(streams[0])
+        run_steps(fn, 1000, steps, use_ctxs)
+        for s in streams:
+            s.synchronize()
+        e1.record(streams[0])
         e1.synchronize()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -199,17 +235,19 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.get("launches")
-    ms_res = timed(step_resident, args.steps, max(args.warmup, 3))
-    launches = ctx.get("launches") - launches0 - 0
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3) if args.warmup else 0)
+    launches0 = sum(c.get("launches") for c in ctxs)
+    ms_res = timed(step_resident, args.steps, warmup, ctxs)
+    launches = sum(c.get("launches") for c in ctxs) - launches0
+    ms_e2e = timed(step_e2e, args.steps, warmup, ctxs)
+    lat_steps = max(3, min(10, args.steps))
+    ms_lat = timed(step_resident, lat_steps, warmup, ctxs[:1])
     sampler.stop_flag = True
 
     # dominant kernel (MSM bucket accumulation): one instrumented step, CUDA events around every launch
-    ctx.set("time_accum", 1)
-    step_resident(10 ** 6)
-    acc_ns, acc_entries = ctx.get("sum_accum_ns"), ctx.get("sum_entries")
-    ctx.set("time_accum", 0)
+    ctx0.set("time_accum", 1)
+    step_resident(ctx0, 10 ** 6)
+    acc_ns, acc_entries = ctx0.get("sum_accum_ns"), ctx0.get("sum_entries")
+    ctx0.set("time_accum", 0)
 
     if ws > 1:
         dist.barrier()
@@ -220,38 +258,50 @@ def main():
     value = ws * args.steps / (ms_res * 1e-3)
     e2e_value = ws * args.steps / (ms_e2e * 1e-3)
     achieved = acc_entries * IMAD_PER_MADD / (acc_ns * 1e-9) / 1e12 if acc_ns else None
-    # bytes crossing PCIe per e2e step (counted from the buffers handed to the C ABI)
-    csc_bytes = 4 * (3 * st.n + st.m + 2) + st.nnz * 36
-    h2d = (2 * 32 * st.n + 4 * (st.q + 1) + 36 * st.nnz) * 2 + 2 * 32 * st.m + 32 * st.m  # load_cs x2, commits, V
-    h2d += 3 * 32 * st.n + 2 * csc_bytes + 128 * st.n  # library-internal uploads: a_L/a_R/a_O, transposed constraints x2, rng draws
-    d2h = 32 * st.m + 1505 + 128 * (3 + 2 * 17 + 2)
+    lg = max(st.n - 1, 0).bit_length()
+    # bytes crossing PCIe per e2e step, counted from the buffers handed to the C ABI plus the library's own uploads
+    csr = 4 * (st.q + 1) + 36 * st.nnz
+    h2d = 2 * 32 * st.n + csr            # bpg_prover_load_cs: a_L, a_R, CSR constraints
+    h2d += csr                           # bpg_verifier_load_cs
+    h2d += 64 * st.m + 32 * st.m         # commit_batch (v, blinding) ; v_blinding vector of the prover
+    h2d += 128 * st.n                    # 64-byte TranscriptRng draws for s_L, s_R (reduced mod l on the device)
+    h2d += 32 * (6 + st.m + 5 + 2 * lg) * 2  # verifier: compressed points + head scalars
+    d2h = 32 * st.m + 128 * (3 + 2 * lg) + 9 * 32 + 64 + 128 + 16  # commitments, A/S/L/R points, t scalars, a/b, check point, flags
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
+                   "inflight": inflight,
                    "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
                    "rng": "transcript rng seeded per step; proofs byte-identical to the CPU oracle",
-                   "window_bits": ctx.get("window_bits"), "task_len": 32},
+                   "window_bits": ctx0.get("window_bits"), "task_len": 32},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
+        "latency": {"ms_per_step": ms_lat / lat_steps, "steps": lat_steps,
+                    "note": "one step at a time on one context; the prover waits on the host for the sequential "
+                            "Merlin TranscriptRng stream (2n Keccak-f permutations)"},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_accumulate (MSM bucket accumulation, mixed Edwards adds)", "bound": "imad",
                      "achieved": achieved, "peak": IMAD_WIDE_PEAK_TOPS, "unit": "T IMAD.WIDE/s",
-                     "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": None,
+                     "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": 659e6,
+                     "traffic_note": "dram bytes read+write per launch from profiles/r01_accumulate_ncu_details.csv "
+                                     "(IPP-round MSM, 4.19 M entries x 96 B = 403 MB algorithmic gather)",
                      "peak_source": "tools/imad_peak.cu on this pool (profiles/r01_imad_peak.jsonl); IMAD.WIDE.U32 issues at "
                                     "28/clk/SM vs 64 for 32-bit IMAD; not in MEASURED_PEAKS.json",
                      "work": "%d mixed adds x %d IMAD.WIDE" % (acc_entries, IMAD_PER_MADD),
-                     "kernel_ms_per_step": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / per_step_ms},
+                     "kernel_ms_per_step": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / (ms_lat / lat_steps),
+                     "share_note": "share of the un-overlapped (latency) step"},
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
         from oracle import coracle
+        cst = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank)
         t0 = time.perf_counter()
-        p_c, coms_c = coracle.prove_flat(st, (1).to_bytes(32, "little"), cache_gens=False)
-        ok = coracle.verify_flat(st, coms_c, p_c, (1).to_bytes(32, "little"), cache_gens=False)
+        p_c, coms_c = coracle.prove_flat(cst, (1).to_bytes(32, "little"), cache_gens=False)
+        ok = coracle.verify_flat(cst, coms_c, p_c, (1).to_bytes(32, "little"), cache_gens=False)
         dt = time.perf_counter() - t0
-        same = p_c == step_resident(0)
+        same = p_c == step_resident(ctx0, 0)
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "the full statement once (prove+verify, generators rebuilt per run as the reference "
                                           "does): %.1f s; CPU proof accepted=%s, byte-identical to the GPU proof=%s" % (dt, ok, same)}

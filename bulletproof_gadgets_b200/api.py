@@ -55,8 +55,9 @@ def pinned_empty(nbytes):
     p = lib().bpg_host_alloc(nbytes)
     if not p:
         raise BpgError(_capi.E_CUDA, (lib().bpg_last_error() or b"").decode())
-    arr = np.ctypeslib.as_array((ctypes.c_uint8 * max(nbytes, 1)).from_address(p))[:nbytes]
-    weakref.finalize(arr, lib().bpg_host_free, p)
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p)
+    weakref.finalize(buf, lib().bpg_host_free, p)   # `buf` is the base of every numpy view taken below
+    arr = np.frombuffer(buf, dtype=np.uint8)[:nbytes]
     return arr
 
 

@@ -26,6 +26,20 @@ class FlatStatement:
         self.term_coef = term_coef                     # bytes, nnz*32
         self.n, self.q = n, q
         self.m = len(v)
+        # packed forms for the batch entry points (k*32 bytes, little-endian)
+        self.v_bytes = b"".join(int(x).to_bytes(32, "little") for x in v)
+        self.vbl_bytes = b"".join(int(x).to_bytes(32, "little") for x in vbl)
+
+    def pin(self, bpg):
+        """Moves the bulk arrays into page-locked host memory (bpg_host_alloc) so that the C ABI's uploads are
+        asynchronous DMA; returns self."""
+        import numpy as np
+        self.aL = bpg.pinned_copy(self.aL, np.uint8)
+        self.aR = bpg.pinned_copy(self.aR, np.uint8)
+        self.row_start = bpg.pinned_copy(self.row_start)
+        self.term_var = bpg.pinned_copy(self.term_var)
+        self.term_coef = bpg.pinned_copy(self.term_coef, np.uint8)
+        return self
 
     @property
     def nnz(self):
@@ -90,7 +104,8 @@ def prove_statement(bpg, ctx, st, seed=b"\x07" * 32):
     """Drives one statement through the C ABI prover: returns (proof bytes, commitments)."""
     T = bpg.Transcript(st.label)
     p = bpg.Prover(ctx, T)
-    coms = [c for c, _ in p.commit_batch(st.v, st.vbl)]
+    packed = p.commit_batch_packed(st.v_bytes, st.vbl_bytes)
+    coms = [packed[32 * i: 32 * i + 32] for i in range(st.m)]
     p.load_cs(st.aL, st.aR, st.row_start, st.term_var, st.term_coef, st.q)
     return p.prove(seed), coms
 
