@@ -94,6 +94,7 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     w.partials.release();
     w.blockres.release();
     w.meta.release();
+    w.tile_sum.release();
     ctx->d_scalars.release();
     ctx->d_points.release();
     r1cs_release_work(ctx);

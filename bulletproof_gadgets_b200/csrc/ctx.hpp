@@ -95,6 +95,7 @@ struct MsmWork {
     DevBuf<uint2> tasks;         // {start, bucket<<8 | count}
     DevBuf<ge_ext> partials;     // one per task
     DevBuf<ge_ext> blockres;     // [nsets][REDUCE_BLOCKS]
+    DevBuf<uint64_t> tile_sum;   // scan scratch (entries | tasks << 32 per 2048-bucket tile)
     DevBuf<uint32_t> meta;       // [0]=ntasks total, [1+s]=task start of set s, ... see msm.cu
 };
 

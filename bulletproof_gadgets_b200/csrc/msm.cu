@@ -79,67 +79,99 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 2: exclusive scans (entries, tasks) over all buckets of all sets; single CTA
+// stage 2: exclusive scans (entries, tasks) over all buckets of all sets.  The two sums ride one
+// 64-bit word (entries low, tasks high; both < 2^32), tiles of 2048 buckets, three small launches.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ bucket_off,
-                                               uint32_t* __restrict__ task_off, uint32_t* __restrict__ meta,
-                                               uint32_t G, uint32_t nb, uint32_t nsets, uint32_t task_len) {
-    __shared__ uint32_t sh_e[32], sh_t[32];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (G + 1023u) / 1024u;
-    const uint32_t b0 = tid * per, b1 = min(b0 + per, G);
-    uint32_t se = 0, st = 0;
-    for (uint32_t b = b0; b < b1; b++) {
-        uint32_t cnt = hist[b];
-        se += cnt;
-        st += (cnt + task_len - 1) / task_len;
-    }
-    // block exclusive scan of (se, st)
-    uint32_t ie = se, it = st;
-    const uint32_t lane = tid & 31, wid = tid >> 5;
+#define BS_THREADS 256
+#define BS_ITEMS 8
+#define BS_TILE (BS_THREADS * BS_ITEMS)
+__device__ __forceinline__ uint64_t bs_block_exclusive(uint64_t v, uint64_t* total, uint64_t* sh /*[32]*/) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint64_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t ve = __shfl_up_sync(0xffffffffu, ie, o), vt = __shfl_up_sync(0xffffffffu, it, o);
-        if (lane >= (uint32_t)o) {
-            ie += ve;
-            it += vt;
-        }
+        uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
     }
-    if (lane == 31) {
-        sh_e[wid] = ie;
-        sh_t[wid] = it;
-    }
+    if (lane == 31) sh[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t ve = sh_e[lane], vt = sh_t[lane];
+        uint64_t w = lane < nw ? sh[lane] : 0ull;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t ue = __shfl_up_sync(0xffffffffu, ve, o), ut = __shfl_up_sync(0xffffffffu, vt, o);
-            if (lane >= (uint32_t)o) {
-                ve += ue;
-                vt += ut;
-            }
+            uint64_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += t;
         }
-        sh_e[lane] = ve;
-        sh_t[lane] = vt;
+        sh[lane] = w;
     }
     __syncthreads();
-    uint32_t pe = ie - se + (wid ? sh_e[wid - 1] : 0u);
-    uint32_t pt = it - st + (wid ? sh_t[wid - 1] : 0u);
-    for (uint32_t b = b0; b < b1; b++) {
-        uint32_t cnt = hist[b];
-        bucket_off[b] = pe;
-        task_off[b] = pt;
-        if (b % nb == 0) meta[1 + b / nb] = pt;
-        hist[b] = 0;  // becomes the scatter cursor
-        pe += cnt;
-        pt += (cnt + task_len - 1) / task_len;
+    const uint64_t base = wid ? sh[wid - 1] : 0ull;
+    *total = sh[nw - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+__global__ void __launch_bounds__(BS_THREADS) k_bscan_tiles(const uint32_t* __restrict__ hist, uint32_t* __restrict__ bucket_off,
+                                                            uint32_t* __restrict__ task_off, uint64_t* __restrict__ tile_sum,
+                                                            uint32_t G, uint32_t task_len) {
+    __shared__ uint64_t sh[32];
+    const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_ITEMS;
+    uint64_t v[BS_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < BS_ITEMS; k++) {
+        const uint32_t cnt = base + k < G ? hist[base + k] : 0u;
+        v[k] = (uint64_t)cnt | ((uint64_t)((cnt + task_len - 1) / task_len) << 32);
+        s += v[k];
     }
-    if (tid == 1023) {
-        bucket_off[G] = sh_e[31];
-        task_off[G] = sh_t[31];
-        meta[0] = sh_t[31];
-        meta[1 + nsets] = sh_t[31];
+    uint64_t total;
+    uint64_t pre = bs_block_exclusive(s, &total, sh);
+#pragma unroll
+    for (int k = 0; k < BS_ITEMS; k++) {
+        if (base + k < G) {
+            bucket_off[base + k] = (uint32_t)pre;
+            task_off[base + k] = (uint32_t)(pre >> 32);
+        }
+        pre += v[k];
+    }
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_bscan_top(uint64_t* __restrict__ tile_sum, uint32_t ntiles) {
+    __shared__ uint64_t sh[32];
+    uint64_t carry = 0;
+    for (uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint64_t v = i < ntiles ? tile_sum[i] : 0ull;
+        uint64_t total;
+        const uint64_t pre = bs_block_exclusive(v, &total, sh);
+        if (i < ntiles) tile_sum[i] = carry + pre;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sum[ntiles] = carry;
+}
+// adds the tile offsets, clears the histogram (it becomes the scatter cursor) and writes
+// meta[0] = #tasks, meta[1+s] = first task of set s, meta[1+nsets] = #tasks
+__global__ void __launch_bounds__(BS_THREADS) k_bscan_finish(uint32_t* __restrict__ hist, uint32_t* __restrict__ bucket_off,
+                                                             uint32_t* __restrict__ task_off, const uint64_t* __restrict__ tile_sum,
+                                                             uint32_t* __restrict__ meta, uint32_t G, uint32_t nb, uint32_t nsets,
+                                                             uint32_t ntiles) {
+    const uint64_t add = tile_sum[blockIdx.x];
+    const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_ITEMS;
+#pragma unroll
+    for (int k = 0; k < BS_ITEMS; k++) {
+        const uint32_t b = base + k;
+        if (b < G) {
+            const uint32_t to = task_off[b] + (uint32_t)(add >> 32);
+            bucket_off[b] += (uint32_t)add;
+            task_off[b] = to;
+            hist[b] = 0;
+            if (b % nb == 0) meta[1 + b / nb] = to;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint64_t tot = tile_sum[ntiles];
+        bucket_off[G] = (uint32_t)tot;
+        task_off[G] = (uint32_t)(tot >> 32);
+        meta[0] = (uint32_t)(tot >> 32);
+        meta[1 + nsets] = (uint32_t)(tot >> 32);
     }
 }
 
@@ -316,7 +348,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
     if ((rc = w.hist.ensure(G)) || (rc = w.bucket_off.ensure(G + 1)) || (rc = w.task_off.ensure(G + 1)) ||
         (rc = w.entries.ensure(max_entries + 1)) || (rc = w.tasks.ensure(max_tasks)) ||
         (rc = w.partials.ensure(max_tasks)) || (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS)) ||
-        (rc = w.meta.ensure(nsets + 3)))
+        (rc = w.meta.ensure(nsets + 3)) || (rc = w.tile_sum.ensure(G / BS_TILE + 3)))
         return rc;
 
     CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));
@@ -325,8 +357,14 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
         k_digits<false><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, nullptr, nullptr);
         ctx->launches++;
     }
-    k_scan<<<1, 1024, 0, st>>>(w.hist.p, w.bucket_off.p, w.task_off.p, w.meta.p, G, nb, nsets, T);
-    ctx->launches++;
+    {
+        const uint32_t ntiles = (G + BS_TILE - 1) / BS_TILE;
+        k_bscan_tiles<<<ntiles, BS_THREADS, 0, st>>>(w.hist.p, w.bucket_off.p, w.task_off.p, w.tile_sum.p, G, T);
+        k_bscan_top<<<1, 1024, 0, st>>>(w.tile_sum.p, ntiles);
+        k_bscan_finish<<<ntiles, BS_THREADS, 0, st>>>(w.hist.p, w.bucket_off.p, w.task_off.p, w.tile_sum.p, w.meta.p, G, nb,
+                                                      nsets, ntiles);
+        ctx->launches += 3;
+    }
     if (total > 0) {
         const uint32_t blocks = (uint32_t)((total + 255) / 256);
         k_digits<true><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, w.bucket_off.p,
