@@ -40,6 +40,9 @@ PROTOTYPES = {
     "bpg_gens_ensure": (c_int, [c_void_p, c_uint64]),
     "bpg_gens_compressed": (c_int, [c_void_p, c_int, c_uint64, c_uint64, c_char_p]),
     "bpg_msm_gens": (c_int, [c_void_p, c_char_p, c_uint64, c_char_p, c_uint64, c_char_p, c_char_p, c_char_p]),
+    "bpg_msm_gens_range": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_uint64, c_uint64, c_char_p, c_char_p,
+                                   c_char_p]),
+    "bpg_point_sum": (c_int, [c_char_p, c_uint64, c_char_p]),
     "bpg_msm_gens_dev": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_void_p, c_char_p]),
     "bpg_msm": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_char_p]),
     "bpg_pedersen_commit_batch": (c_int, [c_void_p, c_char_p, c_char_p, c_uint64, c_char_p]),

@@ -174,9 +174,10 @@ int bpg_gens_compressed(bpg_ctx* ctx, int which, uint64_t start, uint64_t count,
 }
 
 static int msm_gens_common(bpg_ctx* ctx, const uint32_t* d_sG, uint64_t nG, const uint32_t* d_sH, uint64_t nH,
-                           const uint32_t* d_sB, const uint32_t* d_sBb, uint8_t out32[32]) {
+                           const uint32_t* d_sB, const uint32_t* d_sBb, uint8_t out32[32], uint64_t g_start = 0,
+                           uint64_t h_start = 0) {
     const uint64_t cap = ctx->table.capacity;
-    if (nG > cap || nH > cap) {
+    if (g_start + nG > cap || h_start + nH > cap) {
         bpg_set_error("msm: %llu/%llu scalars exceed generator capacity %llu", (unsigned long long)nG,
                       (unsigned long long)nH, (unsigned long long)cap);
         return BPG_E_GENS_LEN;
@@ -194,8 +195,8 @@ static int msm_gens_common(bpg_ctx* ctx, const uint32_t* d_sG, uint64_t nG, cons
         s.period = 1;
         segs.total += (uint32_t)n;
     };
-    push(d_sG, 0, nG);
-    push(d_sH, cap, nH);
+    push(d_sG, g_start, nG);
+    push(d_sH, cap + h_start, nH);
     push(d_sB, 2 * cap, 1);
     push(d_sBb, 2 * cap + 1, 1);
     int rc;
@@ -215,8 +216,8 @@ static int check_scalars(const uint8_t* s, uint64_t n) {
     return BPG_OK;
 }
 
-int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH, uint64_t nH, const uint8_t* sB,
-                 const uint8_t* sBb, uint8_t out32[32]) {
+int bpg_msm_gens_range(bpg_ctx* ctx, const uint8_t* sG, uint64_t g_start, uint64_t nG, const uint8_t* sH, uint64_t h_start,
+                       uint64_t nH, const uint8_t* sB, const uint8_t* sBb, uint8_t out32[32]) {
     if (!ctx || !out32) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!sG) nG = 0;
@@ -225,7 +226,7 @@ int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH
     if ((rc = check_scalars(sG, nG)) || (rc = check_scalars(sH, nH)) || (sB && (rc = check_scalars(sB, 1))) ||
         (sBb && (rc = check_scalars(sBb, 1))))
         return rc;
-    uint64_t need = nG > nH ? nG : nH;
+    uint64_t need = g_start + nG > h_start + nH ? g_start + nG : h_start + nH;
     if ((rc = gens_build(ctx, need ? need : 1))) return rc;
     const uint64_t total = nG + nH + 2;
     if ((rc = ctx->d_scalars.ensure(total * 8))) return rc;
@@ -236,7 +237,28 @@ int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH
     if (sB) CUDA_TRY(cudaMemcpyAsync(d + 8 * (nG + nH), sB, 32, cudaMemcpyHostToDevice, st));
     if (sBb) CUDA_TRY(cudaMemcpyAsync(d + 8 * (nG + nH + 1), sBb, 32, cudaMemcpyHostToDevice, st));
     return msm_gens_common(ctx, nG ? d : nullptr, nG, nH ? d + 8 * nG : nullptr, nH, sB ? d + 8 * (nG + nH) : nullptr,
-                           sBb ? d + 8 * (nG + nH + 1) : nullptr, out32);
+                           sBb ? d + 8 * (nG + nH + 1) : nullptr, out32, g_start, h_start);
+}
+
+int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH, uint64_t nH, const uint8_t* sB,
+                 const uint8_t* sBb, uint8_t out32[32]) {
+    return bpg_msm_gens_range(ctx, sG, 0, nG, sH, 0, nH, sB, sBb, out32);
+}
+
+// host-only: sum of n compressed ristretto points (partial results of a point-range sharded MSM)
+int bpg_point_sum(const uint8_t* points32n, uint64_t n, uint8_t out32[32]) {
+    if (!out32 || (n && !points32n)) return BPG_E_ARG;
+    ge_ext acc = ge_identity();
+    for (uint64_t i = 0; i < n; i++) {
+        ge_ext p;
+        if (!ge_ristretto_decompress(&p, points32n + 32 * i)) {
+            bpg_set_error("point_sum: point %llu does not decode", (unsigned long long)i);
+            return BPG_E_VERIFY;
+        }
+        acc = ge_add(acc, p);
+    }
+    ge_ristretto_compress(out32, acc);
+    return BPG_OK;
 }
 
 int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH, const void* d_sB,

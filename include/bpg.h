@@ -67,6 +67,15 @@ int bpg_gens_compressed(bpg_ctx* ctx, int which, uint64_t start, uint64_t count,
  * /root/reference/src/prove.rs:79.  Host pointers; any of sG/sH/sB/sBb may be NULL. */
 int bpg_msm_gens(bpg_ctx* ctx, const uint8_t* sG, uint64_t nG, const uint8_t* sH, uint64_t nH,
                  const uint8_t* sB, const uint8_t* sBb, uint8_t out32[32]);
+/* Point-range form: sG multiplies G_{g_start}.., sH multiplies H_{h_start}..  One large MSM (dalek
+ * vartime_multiscalar_mul over generator slices, e.g. the verifier's mega-MSM reached from
+ * /root/reference/src/verify.rs:71) is split across GPUs by contiguous point ranges; every GPU returns one
+ * compressed partial point and the host adds them with bpg_point_sum. */
+int bpg_msm_gens_range(bpg_ctx* ctx, const uint8_t* sG, uint64_t g_start, uint64_t nG, const uint8_t* sH, uint64_t h_start,
+                       uint64_t nH, const uint8_t* sB, const uint8_t* sBb, uint8_t out32[32]);
+/* Host-only sum of n compressed ristretto points (<= 8 partial results of a sharded MSM).  BPG_E_VERIFY if a
+ * point does not decode.  Needs no GPU. */
+int bpg_point_sum(const uint8_t* points32n, uint64_t n, uint8_t out32[32]);
 /* Same with DEVICE pointers (scalars already resident in HBM, canonical). */
 int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH,
                      const void* d_sB, const void* d_sBb, uint8_t out32[32]);

@@ -73,3 +73,51 @@ def test_false_statements_rejected_by_gpu_and_oracle(engine, case):
     vs = F.compile_verifier("neg", inst, st.coms_text(coms), gad)
     assert W.verify_statement(bpg, ctx, vs, proof, vs.V, G.SEED_VERIFY) is False
     assert coracle.verify_flat(vs, vs.V, proof, G.SEED_VERIFY) is False
+
+
+def test_batch_of_independent_proofs_in_flight(engine):
+    """BASELINE config 4 shape (LESS_THAN / SET_MEMBER proofs) with several proofs in flight on one GPU:
+    one host thread + one shared-table context each; every proof byte-identical to the oracle's."""
+    import random
+    import threading
+    bpg, W, ctx = engine
+    rnd = random.Random(4096)
+    jobs = []
+    for i in range(16):
+        if i % 2 == 0:
+            a = rnd.randrange(1 << 100)
+            b = a + 1 + rnd.randrange(1 << 100)
+            jobs.append(("LESS_THAN W0 W1", "", "W0 = 0x%030x\nW1 = 0x%030x" % (a, b)))
+        else:
+            elems = [rnd.randrange(1 << 120) for _ in range(16)]
+            member = elems[rnd.randrange(16)]
+            inst = "\n".join("I%d = 0x%032x" % (k, e) for k, e in enumerate(elems))
+            jobs.append(("SET_MEMBER W0 " + " ".join("I%d" % k for k in range(16)), inst, "W0 = 0x%032x" % member))
+    sts = [F.compile_prover("batch-%d" % i, inst, wtns, gad, G.blinding(b"b%d" % i)) for i, (gad, inst, wtns) in enumerate(jobs)]
+    ctxs = [ctx] + [ctx.shared() for _ in range(3)]
+    results, errs = {}, []
+
+    def work(w):
+        try:
+            for i in range(w, len(jobs), len(ctxs)):
+                proof, coms = W.prove_statement(bpg, ctxs[w], sts[i], bytes([i + 1]) * 32)
+                gad, inst, _ = jobs[i]
+                vs = F.compile_verifier("batch-%d" % i, inst, sts[i].coms_text(coms), gad)
+                results[i] = (proof, coms, W.verify_statement(bpg, ctxs[w], vs, proof, vs.V, G.SEED_VERIFY))
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(w,)) for w in range(len(ctxs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(len(jobs)):
+        proof, coms, ok = results[i]
+        assert ok is True
+        assert (proof, coms) == coracle.prove_flat(sts[i], bytes([i + 1]) * 32), i
+    sizes = {sts[0].n, sts[1].n}
+    assert sizes == {379, 32}                       # LESS_THAN: 3*126+1 multipliers; SET_MEMBER k=16: 2k
+    for c in ctxs[1:]:
+        c.close()

@@ -122,3 +122,19 @@ def test_shared_contexts_agree(ctx):
     c2.gens_ensure(8192)                       # growth through the child is visible to the parent
     assert ctx.msm_gens(s, s, None, None) == c2.msm_gens(s, s, None, None)
     c2.close()
+
+
+def test_point_range_sharded_msm(ctx):
+    """One MSM split by contiguous point ranges over several contexts; partial points added on the host."""
+    from bulletproof_gadgets_b200 import sharding
+    rnd = random.Random(8)
+    sG = b"".join(rnd.randrange(L).to_bytes(32, "little") for _ in range(5000))
+    sH = b"".join(rnd.randrange(L).to_bytes(32, "little") for _ in range(3001))
+    sB, sBb = rnd.randrange(L).to_bytes(32, "little"), rnd.randrange(L).to_bytes(32, "little")
+    whole = ctx.msm_gens_bytes(sG, sH, sB, sBb)
+    assert whole == coracle.msm_gens(sG, sH, sB, sBb)
+    for parts in (1, 2, 3, 8):
+        ctxs = [ctx] + [ctx.shared() for _ in range(parts - 1)]
+        assert sharding.msm_gens_sharded(ctxs, sG, sH, sB, sBb) == whole
+        for c in ctxs[1:]:
+            c.close()
