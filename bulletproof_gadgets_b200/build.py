@@ -34,14 +34,16 @@ def sources():
 
 
 def _stamp():
+    """Content hash of the sources and flags, independent of where the tree lives (the GPU box runs a copy)."""
     h = hashlib.sha256()
-    for dirpath, _, files in os.walk(CSRC):
+    for dirpath, dirs, files in os.walk(CSRC):
+        dirs.sort()
         for f in sorted(files):
             p = os.path.join(dirpath, f)
-            h.update(p.encode())
+            h.update(os.path.relpath(p, ROOT).encode())
             h.update(open(p, "rb").read())
     h.update(open(os.path.join(ROOT, "include", "bpg.h"), "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(x.replace(ROOT, ".") for x in NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -57,9 +59,22 @@ def _compile(src):
 def build_lib(force=False, verbose=False):
     stamp_file = OUT + ".stamp"
     stamp = _stamp()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+
+    def fresh():
+        return os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp
+
+    if not force and fresh():
         return OUT
     os.makedirs(OBJDIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(OBJDIR, ".lock"), "w") as lock:      # several ranks may import at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return OUT
+        return _build_locked(stamp_file, stamp, verbose)
+
+
+def _build_locked(stamp_file, stamp, verbose):
     srcs = sources()
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(_compile, srcs))
@@ -68,10 +83,12 @@ def build_lib(force=False, verbose=False):
         for _, err in results:
             if err.strip():
                 print(err, file=sys.stderr)
-    cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = OUT + ".tmp"
+    cmd = ["nvcc", "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, OUT)
     open(stamp_file, "w").write(stamp)
     return OUT
 
