@@ -23,6 +23,13 @@ class ProofArtifacts(ctypes.Structure):
                 ("num_constraints", c_uint64)]
 
 
+class FlatStatementC(ctypes.Structure):
+    _fields_ = [("n", c_uint64), ("m", c_uint64), ("q", c_uint64), ("nnz", c_uint64), ("v32m", POINTER(c_uint8)),
+                ("vbl32m", POINTER(c_uint8)), ("V32m", POINTER(c_uint8)), ("aL32n", POINTER(c_uint8)),
+                ("aR32n", POINTER(c_uint8)), ("row_start", POINTER(c_uint32)), ("term_var", POINTER(c_uint32)),
+                ("term_coef32", POINTER(c_uint8)), ("com_names", c_char_p)]
+
+
 _lib = None
 
 _u8p = POINTER(c_uint8)
@@ -83,6 +90,10 @@ PROTOTYPES = {
     "bpg_verify": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, c_char_p, c_char_p, c_size_t, c_char_p,
                            POINTER(c_int)]),
     "bpg_free_proof": (None, [POINTER(ProofArtifacts)]),
+    "bpg_frontend_flatten_prover": (c_int, [c_char_p, c_char_p, c_char_p, c_char_p, c_char_p,
+                                            POINTER(POINTER(FlatStatementC))]),
+    "bpg_frontend_flatten_verifier": (c_int, [c_char_p, c_char_p, c_char_p, c_char_p, POINTER(POINTER(FlatStatementC))]),
+    "bpg_flat_statement_free": (None, [POINTER(FlatStatementC)]),
 }
 
 

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbpg.so")
 OBJDIR = os.path.join(ROOT, "build", "obj")
+BINDIR = os.path.join(HERE, "bin")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -43,6 +44,8 @@ def _stamp():
             h.update(os.path.relpath(p, ROOT).encode())
             h.update(open(p, "rb").read())
     h.update(open(os.path.join(ROOT, "include", "bpg.h"), "rb").read())
+    for name in ("prover.cpp", "verifier.cpp"):
+        h.update(open(os.path.join(HERE, "cli", name), "rb").read())
     h.update(" ".join(x.replace(ROOT, ".") for x in NVCC_FLAGS).encode())
     return h.hexdigest()
 
@@ -89,6 +92,14 @@ def _build_locked(stamp_file, stamp, verbose):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     os.replace(tmp, OUT)
+    # process-level drop-ins (`prover <stem>`, `verifier <stem>`), linked against the library with an $ORIGIN rpath
+    os.makedirs(BINDIR, exist_ok=True)
+    for name in ("prover", "verifier"):
+        cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "cli", name + ".cpp"),
+               "-o", os.path.join(BINDIR, name), "-L", HERE, "-l:libbpg.so", "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("cli build failed:\n%s\n%s" % (r.stdout, r.stderr))
     open(stamp_file, "w").write(stamp)
     return OUT
 

@@ -1,23 +1,1236 @@
 // Statement-level front end: prove()/verify() over the .gadgets/.inst/.wtns/.coms text formats.
-// (placeholder until the C++ parsers + gadgets land)
+//
+// Host-side mirror (C++; the image has no Rust toolchain) of what sits between the reference's file formats and
+// dalek's constraint system, so that the prover / verifier CLIs and the c_prove / c_verify
+// style ABI work without the Rust crate:
+//   conversions            /root/reference/src/conversions.rs:6-76
+//   commitments / .coms    /root/reference/src/commitments.rs:9-48, /root/reference/src/lalrpop/assignment_parser.rs:15-217
+//   grammars               /root/reference/src/lalrpop/gadget_grammar.lalrpop:6-85, var_grammar.lalrpop:3-29, ast.rs:3-86
+//   cs buffers             /root/reference/src/cs_buffer.rs:6-199
+//   prove() / verify()     /root/reference/src/prove.rs:37-514, /root/reference/src/verify.rs:36-415
+//   Gadget::setup          /root/reference/src/gadget.rs:19-39           range_proof  /root/reference/src/utils.rs:5-35
+//   gadgets                bounds_check_gadget.rs:13-64, equality_gadget.rs:10-40, inequality_gadget.rs:11-114,
+//                          less_than_gadget.rs:15-83, set_membership_gadget.rs:12-132, mimc_hash_gadget.rs:7-151,
+//                          mimc.rs:7-97, merkle_tree_gadget.rs:39-114, or/or_conjunction.rs:4-67
+// Everything here is string / scalar bookkeeping on the CPU (north_star keeps it there).  The result is the FLAT
+// statement the real Prover / Verifier hold after assign_buffer (/root/reference/src/prove.rs:84-99): committed
+// values in commit order, multiplier assignments, constraints in order with the two implicit constraints of every
+// `multiply`.  bpg_prove / bpg_verify hand it to the GPU through the same bulk loaders bench.py measures.
+//
+// Scalars keep dalek's RAW bytes: Scalar::from_bits values may be >= l until arithmetic touches them; == compares
+// raw bytes; + - * invert return canonical values.
+#include <stdlib.h>
+
+#include <functional>
+#include <map>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
 #include "ctx.hpp"
+#include "host_sc.hpp"
+#include "merlin.hpp"
+
+namespace {
+
+struct Panic : std::runtime_error {  // where the reference panics (expect / unwrap / assert)
+    explicit Panic(const std::string& m) : std::runtime_error(m) {}
+};
+
+// ---------------------------------------------------------------------------------------- scalars
+typedef sc S;
+const S MIMC_C[486] = {
+#include "mimc_consts.inc"
+};
+inline S s_zero() { return sc_zero(); }
+inline S s_one() { return sc_one(); }
+inline S s_u64(uint64_t x) {
+    S r = sc_zero();
+    r.v[0] = (uint32_t)x;
+    r.v[1] = (uint32_t)(x >> 32);
+    return r;
+}
+inline bool s_eq(const S& a, const S& b) { return memcmp(a.v, b.v, 32) == 0; }  // raw bytes, like dalek's PartialEq
+inline bool s_is_zero(const S& a) { return sc_is_zero(a); }
+inline S s_red(const S& a) { return sc_reduce(a); }
+inline S s_add(const S& a, const S& b) { return sc_add(s_red(a), s_red(b)); }
+inline S s_mul(const S& a, const S& b) { return sc_mul(a, b); }
+inline S s_neg(const S& a) { return sc_neg(s_red(a)); }
+// dalek 3.2 `&Scalar - &Scalar`: Scalar52::sub adds l ONCE on underflow and then reduces; for unreduced operands whose
+// difference is below -l the 260-bit wrap shows through (+2^260 mod l).
+S s_sub(const S& a, const S& b) {
+    S d;
+    if (sc_sub_raw(&d, a, b) == 0) return s_red(d);  // a >= b
+    S e;
+    sc_sub_raw(&e, b, a);  // e = b - a > 0
+    S t;
+    const bool below_minus_l = sc_sub_raw(&t, sc_L(), e) != 0;  // l - e < 0
+    S r = sc_neg(s_red(e));
+    if (below_minus_l) {
+        const uint32_t C260[8] = {0x6721e6edu, 0x45af48bdu, 0xab5ac67eu, 0x35e51b3bu, 0xffffffebu, 0xffffffffu, 0xffffffffu, 0x0fffffffu};
+        r = sc_add(r, sc_const(C260));
+    }
+    return r;
+}
+S s_invert(const S& a) { return bpg::Scalar::from_sc(s_red(a)).invert().s; }
+inline void s_bytes(const S& a, uint8_t out[32]) { memcpy(out, a.v, 32); }
+inline S s_from_bits(const uint8_t b[32]) {
+    S r;
+    memcpy(r.v, b, 32);
+    r.v[7] &= 0x7fffffffu;
+    return r;
+}
+
+typedef std::vector<uint8_t> Bytes;
+
+std::vector<S> le_to_scalars(Bytes b) {
+    if (b.size() % 32) b.resize(b.size() + 32 - b.size() % 32, 0);
+    std::vector<S> out;
+    for (size_t i = 0; i < b.size(); i += 32) out.push_back(s_from_bits(&b[i]));
+    return out;
+}
+std::vector<S> be_to_scalars(const Bytes& b) { return le_to_scalars(Bytes(b.rbegin(), b.rend())); }
+S le_to_scalar(Bytes b) {
+    if (b.size() > 32) throw Panic("the given vector is longer than 32 bytes");
+    if (b.size() % 32) b.resize(32, 0);
+    if (b.size() < 32) throw Panic("empty byte string");
+    return s_from_bits(b.data());
+}
+S be_to_scalar(const Bytes& b) { return le_to_scalar(Bytes(b.rbegin(), b.rend())); }
+
+// ---------------------------------------------------------------------------------------- MiMC (mimc.rs)
+const int ROUNDS = 486;
+S mimc_encrypt(S state, const S& k) {
+    for (int i = 0; i < ROUNDS; i++) {
+        S tmp = s_add(state, s_add(k, MIMC_C[i]));
+        state = s_mul(s_mul(tmp, tmp), tmp);
+    }
+    return s_add(state, k);
+}
+S mimc_sponge(const std::vector<S>& pre) {
+    S state = s_zero();
+    for (const S& x : pre) state = mimc_encrypt(s_add(state, x), s_zero());
+    return state;
+}
+// (padded block, replaced-the-last-block): mimc.rs:77-97 / mimc_hash_gadget.rs:15-37
+std::pair<S, bool> pkcs7_block(const S& last) {
+    uint8_t le[32];
+    s_bytes(last, le);
+    size_t len = 32;
+    while (len > 0 && le[len - 1] == 0) len--;
+    if (len < 32) {
+        const uint8_t pad = (uint8_t)(32 - len);
+        Bytes p(le, le + len);
+        p.resize(32, pad);
+        return {le_to_scalar(p), true};
+    }
+    return {le_to_scalar(Bytes(32, 32)), false};
+}
+S mimc_hash(const Bytes& preimage) {
+    std::vector<S> pre = be_to_scalars(preimage);
+    if (pre.empty()) throw Panic("mimc_hash of an empty preimage");
+    auto pb = pkcs7_block(pre.back());
+    if (pb.second) pre.pop_back();
+    pre.push_back(pb.first);
+    return mimc_sponge(pre);
+}
+
+// ---------------------------------------------------------------------------------------- linear combinations
+enum { K_COMMITTED = 0, K_LEFT = 1, K_RIGHT = 2, K_OUT = 3, K_ONE = 4 };
+typedef uint32_t Var;
+inline Var mkvar(uint32_t kind, uint32_t idx) { return (kind << 29) | idx; }
+const Var ONE_VAR = 4u << 29;
+
+struct LC {
+    std::vector<std::pair<Var, S>> t;
+    static LC var(Var v) {
+        LC r;
+        r.t.push_back({v, s_one()});
+        return r;
+    }
+    static LC cst(const S& s) {  // Scalar -> LC keeps the raw scalar
+        LC r;
+        r.t.push_back({ONE_VAR, s});
+        return r;
+    }
+    LC operator+(const LC& o) const {
+        LC r = *this;
+        r.t.insert(r.t.end(), o.t.begin(), o.t.end());
+        return r;
+    }
+    LC operator-(const LC& o) const {
+        LC r = *this;
+        for (auto& e : o.t) r.t.push_back({e.first, s_neg(e.second)});
+        return r;
+    }
+    LC scale(const S& s) const {
+        LC r;
+        for (auto& e : t) r.t.push_back({e.first, s_mul(e.second, s)});
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------- cs_buffer.rs
+struct Op {
+    enum Kind { MUL, ALLOC, CON, COMMIT } kind;
+    LC a, b;          // MUL: left, right ; CON: a
+    bool has = false; // ALLOC: assignment present
+    S l = sc_zero(), r = sc_zero();
+};
+struct Vars3 {
+    Var l, r, o;
+};
+// ProverBuffer / VerifierBuffer: records operations; its throw-away inner prover only matters through the multiplier
+// counter that numbers the variables handed back to the gadgets.
+struct Buffer {
+    bool proving;
+    std::vector<Op> ops;
+    std::vector<std::vector<Op>> cache;
+    uint32_t n_mult = 0;
+    explicit Buffer(bool p) : proving(p) {}
+    Vars3 alloc() {
+        const uint32_t i = n_mult++;
+        return {mkvar(K_LEFT, i), mkvar(K_RIGHT, i), mkvar(K_OUT, i)};
+    }
+    Vars3 multiply(const LC& l, const LC& r) {
+        Op o;
+        o.kind = Op::MUL;
+        o.a = l;
+        o.b = r;
+        ops.push_back(std::move(o));
+        return alloc();
+    }
+    Vars3 allocate_multiplier(bool has, const S& l, const S& r) {
+        if (proving && !has) throw Panic("MissingAssignment");
+        Op o;
+        o.kind = Op::ALLOC;
+        o.has = proving;
+        o.l = l;
+        o.r = r;
+        ops.push_back(std::move(o));
+        return alloc();
+    }
+    void constrain(const LC& lc) {
+        Op o;
+        o.kind = Op::CON;
+        o.a = lc;
+        ops.push_back(std::move(o));
+    }
+    void commit_drvd() {
+        Op o;
+        o.kind = Op::COMMIT;
+        ops.push_back(std::move(o));
+    }
+    void initialize_from(const std::vector<const std::vector<Op>*>& init) {
+        for (auto* v : init)
+            for (auto& o : *v)
+                if (o.kind == Op::MUL || o.kind == Op::ALLOC) n_mult++;
+    }
+    void rewind() {
+        cache.push_back(std::move(ops));
+        ops.clear();
+    }
+};
+
+// derived witness: (assignment or none, variable)
+struct Derived {
+    bool has;
+    S val;
+    Var var;
+};
+
+// ---------------------------------------------------------------------------------------- gadgets
+void range_proof(Buffer& cs, LC x, unsigned n, bool has, const S& x_assignment) {  // utils.rs:5-35
+    S exp2 = s_one();
+    uint8_t xb[32] = {0};
+    if (has) s_bytes(x_assignment, xb);
+    for (unsigned i = 0; i < n; i++) {
+        const uint32_t bit = has ? (xb[i / 8] >> (i % 8)) & 1u : 0u;
+        Vars3 v = cs.allocate_multiplier(has, s_u64(1 - bit), s_u64(bit));
+        cs.constrain(LC::var(v.o));
+        cs.constrain(LC::var(v.l) + (LC::var(v.r) - LC::cst(s_one())));
+        x = x - LC::var(v.r).scale(exp2);
+        exp2 = s_add(exp2, exp2);
+    }
+    cs.constrain(x);
+}
+
+struct BoundsCheck {
+    S mn, mx;
+    unsigned n;
+    BoundsCheck(const Bytes& lo, const Bytes& hi) : mn(be_to_scalar(lo)), mx(be_to_scalar(hi)), n((hi.size() * 8) & 0xff) {}
+    std::vector<S> preprocess(const std::vector<S>& w) const { return {s_sub(w[0], mn), s_sub(mx, w[0])}; }
+    void assemble(Buffer& cs, const std::vector<Derived>& d) const {
+        LC a = LC::var(d[0].var), b = LC::var(d[1].var);
+        cs.constrain((a + b) - LC::cst(s_sub(mx, mn)));
+        range_proof(cs, a, n, d[0].has, d[0].val);
+        range_proof(cs, b, n, d[1].has, d[1].val);
+    }
+};
+
+struct MimcHash256 {
+    LC image;
+    MimcHash256() : image(LC::cst(s_zero())) {}
+    explicit MimcHash256(const LC& img) : image(img) {}
+    std::vector<S> preprocess(const std::vector<S>& w) const {
+        const S last = w.back();
+        auto pb = pkcs7_block(last);
+        if (pb.second) return {pb.first, s_sub(pb.first, last)};
+        return {pb.first};
+    }
+    static LC encrypt(Buffer& cs, LC p, const LC& k) {
+        for (int i = 0; i < ROUNDS; i++) {
+            LC t = (p + k) + LC::cst(MIMC_C[i]);
+            Vars3 a = cs.multiply(t, t);
+            Vars3 b = cs.multiply(LC::var(a.o), LC::var(a.l));
+            p = LC::var(b.o);
+        }
+        return p + k;
+    }
+    static LC sponge(Buffer& cs, const std::vector<LC>& pre) {
+        const LC key_zero = LC::cst(s_zero());
+        LC state = LC::cst(s_zero());
+        for (auto& v : pre) state = encrypt(cs, state + v, key_zero);
+        return state;
+    }
+    void assemble(Buffer& cs, std::vector<Var> coms, const std::vector<Derived>& d) const {
+        const Var padded = d[0].var;
+        if (d.size() == 2) {
+            if (coms.empty()) throw Panic("pop from empty commitment list");
+            LC last = LC::var(coms.back());
+            coms.pop_back();
+            cs.constrain((last + LC::var(d[1].var)) - LC::var(padded));
+        }
+        coms.push_back(padded);
+        std::vector<LC> pre;
+        for (Var v : coms) pre.push_back(LC::var(v));
+        cs.constrain(sponge(cs, pre) - image);
+    }
+};
+
+// Merkle pattern: 'W', 'I' or a node with two children
+struct Pattern {
+    char leaf = 0;
+    std::vector<Pattern> kids;
+};
+struct MerkleTree256 {
+    LC root;
+    std::vector<LC> i_vals, w_vals;
+    Pattern pat;
+    static LC next(std::vector<LC>& v, size_t& pos) {
+        if (pos >= v.size()) throw Panic("too few variables provided to satisfy the given pattern");
+        return v[pos++];
+    }
+    LC parse(Buffer& cs, size_t& wp, size_t& ip, const Pattern& p) {
+        std::vector<LC> pre;
+        if (p.leaf == 'W') pre.push_back(next(w_vals, wp));
+        else if (p.leaf == 'I') pre.push_back(next(i_vals, ip));
+        else
+            for (const Pattern& side : p.kids) {
+                if (side.leaf == 'W') pre.push_back(next(w_vals, wp));
+                else if (side.leaf == 'I') pre.push_back(next(i_vals, ip));
+                else pre.push_back(parse(cs, wp, ip, side));
+            }
+        return MimcHash256::sponge(cs, pre);
+    }
+    void assemble(Buffer& cs) {
+        size_t wp = 0, ip = 0;
+        LC h = parse(cs, wp, ip, pat);
+        cs.constrain(h - root);
+    }
+};
+
+void equality_assemble(Buffer& cs, const std::vector<LC>& right, const std::vector<Var>& left) {
+    if (right.size() != left.size()) return cs.constrain(LC::cst(s_one()));
+    for (size_t i = 0; i < left.size(); i++) cs.constrain(right[i] - LC::var(left[i]));
+}
+
+bool ineq_compare(const S& l, const S& r) {  // raw little-endian bytes from the top
+    uint8_t lb[32], rb[32];
+    s_bytes(l, lb);
+    s_bytes(r, rb);
+    for (int i = 31; i >= 0; i--) {
+        if (lb[i] > rb[i]) return true;
+        if (lb[i] < rb[i]) return false;
+    }
+    return true;
+}
+std::vector<S> inequality_preprocess(const std::vector<S>& left, const std::vector<S>& right) {
+    std::vector<S> out;
+    S total = s_zero();
+    for (size_t i = 0; i < left.size(); i++) {
+        const S r = i < right.size() ? right[i] : s_zero();
+        const S delta = ineq_compare(left[i], r) ? s_sub(left[i], r) : s_sub(r, left[i]);
+        out.push_back(delta);
+        if (s_is_zero(delta)) out.push_back(s_zero());
+        else {
+            const S inv = s_invert(delta);
+            out.push_back(inv);
+            total = s_add(total, s_mul(delta, inv));
+        }
+    }
+    out.push_back(s_invert(total));
+    return out;
+}
+void inequality_assemble(Buffer& cs, const std::vector<LC>& right, const std::vector<Var>& left, const std::vector<Derived>& d) {
+    if (right.size() != left.size()) return cs.constrain(LC::cst(s_zero()));
+    LC total = LC::cst(s_zero());
+    for (size_t i = 0; i < left.size(); i++) {
+        const LC left_lc = LC::var(left[i]), delta = LC::var(d[2 * i].var), delta_inv = LC::var(d[2 * i + 1].var);
+        LC l = (left_lc - right[i]) - delta, r = (right[i] - left_lc) - delta;
+        Vars3 z = cs.multiply(l, r);
+        cs.constrain(LC::var(z.o));
+        Vars3 zo = cs.multiply(delta, delta_inv);
+        total = total + LC::var(zo.o);
+    }
+    Vars3 one = cs.multiply(total, LC::var(d.back().var));
+    cs.constrain(LC::cst(s_one()) - LC::var(one.o));
+}
+
+void less_than_assemble(Buffer& cs, const LC& left, bool has, const S& lv, const LC& right, const S& rv, const std::vector<Derived>& d) {
+    const LC delta = LC::var(d[0].var), delta_inv = LC::var(d[1].var);
+    range_proof(cs, left, 126, has, lv);
+    range_proof(cs, right, 126, has, rv);
+    range_proof(cs, delta, 126, d[0].has, d[0].val);
+    Vars3 one = cs.multiply(delta, delta_inv);
+    cs.constrain(LC::cst(s_one()) - LC::var(one.o));
+    cs.constrain((right - left) - delta);
+}
+
+void set_membership_assemble(Buffer& cs, const LC& value, const std::vector<LC>& instance_lcs, const std::vector<Var>& witnesses,
+                             const std::vector<Derived>& d) {
+    std::vector<LC> one_hot;
+    for (auto& e : d) {
+        LC bit = LC::var(e.var);
+        Vars3 z = cs.multiply(LC::cst(s_one()) - bit, bit);
+        cs.constrain(LC::var(z.o));
+        one_hot.push_back(bit);
+    }
+    LC total = LC::cst(s_zero());
+    for (auto& b : one_hot) total = total + b;
+    cs.constrain(LC::cst(s_one()) - total);
+    std::vector<LC> elems;
+    for (Var w : witnesses) elems.push_back(LC::var(w));
+    elems.insert(elems.end(), instance_lcs.begin(), instance_lcs.end());
+    if (one_hot.size() != elems.size()) return cs.constrain(LC::cst(s_one()));
+    LC prod = LC::cst(s_zero());
+    for (size_t i = 0; i < elems.size(); i++) {
+        Vars3 p = cs.multiply(one_hot[i], elems[i]);
+        prod = prod + LC::var(p.o);
+    }
+    cs.constrain(value - prod);
+}
+
+void or_combine(Buffer& main, const Buffer& inner) {  // or_conjunction.rs:4-38
+    std::vector<std::vector<LC>> per_clause;
+    for (auto& ops : inner.cache) {
+        std::vector<LC> cons;
+        for (auto& o : ops) {
+            if (o.kind == Op::MUL) main.multiply(o.a, o.b);
+            else if (o.kind == Op::ALLOC) main.allocate_multiplier(o.has, o.l, o.r);
+            else if (o.kind == Op::CON) cons.push_back(o.a);
+        }
+        per_clause.push_back(std::move(cons));
+    }
+    if (per_clause.empty()) return;
+    std::vector<std::vector<const LC*>> combos;
+    for (auto& c : per_clause[0]) combos.push_back({&c});
+    for (size_t k = 1; k < per_clause.size(); k++) {
+        std::vector<std::vector<const LC*>> nxt;
+        for (auto& xs : combos)
+            for (auto& y : per_clause[k]) {
+                auto v = xs;
+                v.push_back(&y);
+                nxt.push_back(std::move(v));
+            }
+        combos.swap(nxt);
+    }
+    for (auto& combo : combos) {
+        LC prod = *combo[0];
+        for (size_t i = 1; i < combo.size(); i++) {
+            Vars3 p = main.multiply(prod, *combo[i]);
+            prod = LC::var(p.o);
+        }
+        main.constrain(prod);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- grammars
+std::vector<std::string> split_ws(const std::string& s) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        while (i < s.size() && isspace((unsigned char)s[i])) i++;
+        size_t j = i;
+        while (j < s.size() && !isspace((unsigned char)s[j])) j++;
+        if (j > i) out.push_back(s.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+std::vector<std::string> split_lines(const std::string& s) {  // str::lines(): '\n' separated, trailing '\r' stripped
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        size_t j = s.find('\n', i);
+        if (j == std::string::npos) j = s.size();
+        std::string line = s.substr(i, j - i);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        out.push_back(line);
+        i = j + 1;
+    }
+    return out;
+}
+bool is_var(const std::string& t, char kind) {
+    if (t.size() < 2 || t[0] != kind) return false;
+    for (size_t i = 1; i < t.size(); i++)
+        if (!isdigit((unsigned char)t[i])) return false;
+    return true;
+}
+std::string gadget_op(const std::string& line) {
+    auto t = split_ws(line);
+    const std::string op = t.empty() ? "" : t[0];
+    static const char* OPS[] = {"OR", "HASH", "]", "BOUND", "[", "MERKLE", "}", "EQUALS", "{", "UNEQUAL", "LESS_THAN", "SET_MEMBER"};
+    for (const char* o : OPS)
+        if (op == o) return op;
+    throw Panic("unknown gadget: " + op);
+}
+// `<name> = 0x<hex>`; kind 'I', 'W' or 'C' (C|D<d>-<d>(-<d>)?)
+std::pair<std::string, Bytes> parse_var_line(char kind, const std::string& line) {
+    auto bad = [&]() -> Panic { return Panic(std::string("unparsable ") + kind + " line: " + line); };
+    size_t i = 0;
+    auto skip = [&]() {
+        while (i < line.size() && isspace((unsigned char)line[i])) i++;
+    };
+    skip();
+    size_t s0 = i;
+    auto digits = [&]() {
+        size_t d0 = i;
+        while (i < line.size() && isdigit((unsigned char)line[i])) i++;
+        return i > d0;
+    };
+    if (kind == 'C') {
+        if (i >= line.size() || !(line[i] == 'C' || line[i] == 'D' || line[i] == '|')) throw bad();
+        i++;
+        if (!digits()) throw bad();
+        if (i >= line.size() || line[i] != '-') throw bad();
+        i++;
+        if (!digits()) throw bad();
+        if (i < line.size() && line[i] == '-') {
+            i++;
+            if (!digits()) throw bad();
+        }
+    } else {
+        if (i >= line.size() || line[i] != kind) throw bad();
+        i++;
+        if (!digits()) throw bad();
+    }
+    const std::string name = line.substr(s0, i - s0);
+    skip();
+    if (i >= line.size() || line[i] != '=') throw bad();
+    i++;
+    skip();
+    if (i + 1 >= line.size() || line[i] != '0' || (line[i + 1] != 'x' && line[i + 1] != 'X')) throw bad();
+    i += 2;
+    size_t h0 = i;
+    while (i < line.size() && isxdigit((unsigned char)line[i])) i++;
+    const std::string hex = line.substr(h0, i - h0);
+    skip();
+    if (hex.empty() || i != line.size()) throw bad();
+    if (hex.size() % 2) throw Panic("odd number of hex digits: " + line);
+    Bytes b;
+    for (size_t k = 0; k < hex.size(); k += 2) b.push_back((uint8_t)strtoul(hex.substr(k, 2).c_str(), nullptr, 16));
+    return {name, b};
+}
+void parse_two(const std::string& line, const char* op, const char* allowed, std::string* a, std::string* b) {
+    auto t = split_ws(line);
+    if (t.size() == 3 && t[0] == op)
+        for (const char* p = allowed; *p; p += 2)
+            if (is_var(t[1], p[0]) && is_var(t[2], p[1])) {
+                *a = t[1];
+                *b = t[2];
+                return;
+            }
+    throw Panic("cannot parse " + line);
+}
+struct MerkleLine {
+    std::string root;
+    std::vector<std::string> inst, wtns;
+    Pattern pat;
+};
+MerkleLine parse_tree(const std::string& line) {
+    std::vector<std::string> t;
+    for (size_t i = 0; i < line.size();) {
+        const char c = line[i];
+        if (isspace((unsigned char)c)) i++;
+        else if (c == '(' || c == ')') t.push_back(std::string(1, c)), i++;
+        else {
+            size_t j = i;
+            while (j < line.size() && !isspace((unsigned char)line[j]) && line[j] != '(' && line[j] != ')') j++;
+            t.push_back(line.substr(i, j - i));
+            i = j;
+        }
+    }
+    MerkleLine m;
+    if (t.size() < 3 || t[0] != "MERKLE" || !(is_var(t[1], 'I') || is_var(t[1], 'W'))) throw Panic("cannot parse " + line);
+    m.root = t[1];
+    size_t pos = 2;
+    std::function<Pattern()> node = [&]() -> Pattern {
+        if (pos >= t.size() || t[pos] != "(") throw Panic("cannot parse " + line);
+        pos++;
+        Pattern p;
+        for (int k = 0; k < 2; k++) {
+            if (pos >= t.size()) throw Panic("cannot parse " + line);
+            if (t[pos] == "(") p.kids.push_back(node());
+            else if (is_var(t[pos], 'W')) {
+                m.wtns.push_back(t[pos++]);
+                Pattern l;
+                l.leaf = 'W';
+                p.kids.push_back(l);
+            } else if (is_var(t[pos], 'I')) {
+                m.inst.push_back(t[pos++]);
+                Pattern l;
+                l.leaf = 'I';
+                p.kids.push_back(l);
+            } else
+                throw Panic("cannot parse " + line);
+        }
+        if (pos >= t.size() || t[pos] != ")") throw Panic("cannot parse " + line);
+        pos++;
+        return p;
+    };
+    m.pat = node();
+    if (pos != t.size()) throw Panic("cannot parse " + line);
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------- flat statement
+struct Flat {
+    std::vector<S> v, vbl;       // prover
+    std::vector<Bytes> V;        // verifier
+    std::vector<std::string> com_names;
+    std::vector<S> aL, aR;
+    uint32_t n = 0;
+    std::vector<uint32_t> row_start{0}, term_var;
+    std::vector<S> term_coef;
+
+    S eval(const LC& lc) const {
+        S acc = s_zero();
+        for (auto& e : lc.t) {
+            const uint32_t k = e.first >> 29, i = e.first & ((1u << 29) - 1);
+            S val;
+            switch (k) {
+                case K_LEFT: if (i >= aL.size()) throw Panic("unallocated multiplier in a linear combination"); val = aL[i]; break;
+                case K_RIGHT: if (i >= aR.size()) throw Panic("unallocated multiplier in a linear combination"); val = aR[i]; break;
+                case K_OUT: if (i >= aL.size()) throw Panic("unallocated multiplier in a linear combination"); val = s_mul(aL[i], aR[i]); break;
+                case K_COMMITTED: if (i >= v.size()) throw Panic("unknown committed variable"); val = v[i]; break;
+                default: val = s_one();
+            }
+            acc = sc_add(acc, s_mul(e.second, val));
+        }
+        return acc;
+    }
+    void constrain(const LC& lc) {
+        for (auto& e : lc.t) {
+            term_var.push_back(e.first);
+            term_coef.push_back(e.second);
+        }
+        row_start.push_back((uint32_t)term_var.size());
+    }
+    void replay(const std::vector<Op>& ops, bool proving) {  // assign_buffer (prove.rs:84-99 / verify.rs:75-90)
+        for (auto& o : ops) {
+            if (o.kind == Op::MUL) {
+                const uint32_t i = n;
+                if (proving) {
+                    const S l = eval(o.a), r = eval(o.b);
+                    aL.push_back(l);
+                    aR.push_back(r);
+                }
+                n++;
+                constrain(o.a - LC::var(mkvar(K_LEFT, i)));
+                constrain(o.b - LC::var(mkvar(K_RIGHT, i)));
+            } else if (o.kind == Op::ALLOC) {
+                if (proving) {
+                    aL.push_back(o.l);
+                    aR.push_back(o.r);
+                }
+                n++;
+            } else if (o.kind == Op::CON) {
+                constrain(o.a);
+            }
+        }
+    }
+};
+
+struct Witness {
+    std::vector<S> scalars;
+    std::vector<Var> vars;
+    Bytes raw;
+};
+
+// one side (prover or verifier) of the statement walk
+struct Side {
+    bool proving;
+    Flat st;
+    std::map<std::string, Bytes> instance;
+    std::map<std::string, Witness> witness;  // prover
+    std::map<std::string, Var> coms;         // verifier
+    std::function<S(uint64_t)> blinding;
+
+    // ---- prover helpers
+    Var commit(const S& s, const std::string& name) {
+        const Var var = mkvar(K_COMMITTED, (uint32_t)st.v.size());
+        st.vbl.push_back(blinding(st.v.size()));
+        st.v.push_back(s);
+        st.com_names.push_back(name);
+        return var;
+    }
+    std::vector<Derived> setup(const std::vector<S>& derived_scalars, size_t index, size_t sub, size_t first = 0) {
+        std::vector<Derived> d;
+        for (size_t k = 0; k < derived_scalars.size(); k++) {
+            const std::string nm = "D" + std::to_string(index) + "-" + std::to_string(sub) + "-" + std::to_string(first + k);
+            d.push_back({true, derived_scalars[k], commit(derived_scalars[k], nm)});
+        }
+        return d;
+    }
+    const Witness& get_witness(const std::string& name, bool single = false) {
+        auto it = witness.find(name);
+        if (it == witness.end()) throw Panic("missing witness var " + name);
+        if (single && it->second.scalars.size() != 1) throw Panic("witness var " + name + " is longer than 32 bytes");
+        return it->second;
+    }
+    const Bytes& get_instance(const std::string& name, bool max32 = false) {
+        auto it = instance.find(name);
+        if (it == instance.end()) throw Panic("missing instance var " + name);
+        if (max32 && it->second.size() > 32) throw Panic("instance var " + name + " is longer than 32 bytes");
+        return it->second;
+    }
+    // ---- verifier helpers
+    Var get_commitment(const std::string& name, size_t index) {
+        const std::string key = "C" + name.substr(1) + "-" + std::to_string(index);
+        auto it = coms.find(key);
+        if (it == coms.end()) throw Panic("missing commitment " + key);
+        return it->second;
+    }
+    std::vector<Var> all_commitments(const std::string& name) {
+        std::vector<Var> out;
+        for (size_t i = 0;; i++) {
+            auto it = coms.find("C" + name.substr(1) + "-" + std::to_string(i));
+            if (it == coms.end()) break;
+            out.push_back(it->second);
+        }
+        return out;
+    }
+    bool derived(size_t gadget, size_t index, size_t sub, Var* out, bool optional = false) {
+        const std::string key = "D" + std::to_string(gadget) + "-" + std::to_string(sub) + "-" + std::to_string(index);
+        auto it = coms.find(key);
+        if (it == coms.end()) {
+            if (optional) return false;
+            throw Panic("missing commitment " + key);
+        }
+        *out = it->second;
+        return true;
+    }
+    Derived dv(size_t gadget, size_t index, size_t sub) {
+        Var v;
+        derived(gadget, index, sub, &v);
+        return {false, s_zero(), v};
+    }
+
+    // ---- shared
+    LC single_lc(const std::string& name) {
+        if (name[0] == 'W') return LC::var(proving ? get_witness(name, true).vars[0] : get_commitment(name, 0));
+        return LC::cst(be_to_scalar(get_instance(name, true)));
+    }
+    // scalars (prover only) and LCs of a witness / instance variable, one per 32-byte limb
+    void multi(const std::string& name, std::vector<S>* sc_out, std::vector<LC>* lc_out, std::vector<Var>* var_out = nullptr) {
+        if (name[0] == 'W') {
+            std::vector<Var> vars;
+            if (proving) {
+                const Witness& w = get_witness(name);
+                if (sc_out) *sc_out = w.scalars;
+                vars = w.vars;
+            } else {
+                vars = all_commitments(name);
+            }
+            for (Var v : vars) lc_out->push_back(LC::var(v));
+            if (var_out) *var_out = vars;
+        } else {
+            std::vector<S> s = be_to_scalars(get_instance(name));
+            for (auto& x : s) lc_out->push_back(LC::cst(x));
+            if (sc_out) *sc_out = s;
+        }
+    }
+    // hash_witness: prove.rs:142-172 / verify.rs:397-415.  Returns the image variable (and scalar when proving).
+    Var hash_witness(Buffer& buf, const std::string& name, size_t index, size_t sub, S* image_out) {
+        if (proving) {
+            const Witness w = get_witness(name);
+            const S image = mimc_hash(w.raw);
+            const Var image_var = commit(image, "D" + std::to_string(index) + "-" + std::to_string(sub) + "-0");
+            buf.commit_drvd();
+            MimcHash256 g(LC::var(image_var));
+            std::vector<Derived> d = setup(g.preprocess(w.scalars), index, sub, 1);
+            buf.commit_drvd();
+            g.assemble(buf, w.vars, d);
+            if (image_out) *image_out = image;
+            return image_var;
+        }
+        std::vector<Var> pre = all_commitments(name);
+        Var image;
+        derived(index, 0, sub, &image);
+        std::vector<Derived> d{dv(index, 1, sub)};
+        Var d2;
+        if (derived(index, 2, sub, &d2, true)) d.push_back({false, s_zero(), d2});
+        MimcHash256(LC::var(image)).assemble(buf, pre, d);
+        return image;
+    }
+
+    void gadget_line(const std::string& line, Buffer& buf, size_t index) {
+        const std::string op = gadget_op(line);
+        if (op == "BOUND") {
+            auto t = split_ws(line);
+            if (t.size() != 4 || !is_var(t[1], 'W') || !is_var(t[2], 'I') || !is_var(t[3], 'I')) throw Panic("cannot parse " + line);
+            if (proving) {
+                const Witness w = get_witness(t[1], true);
+                BoundsCheck g(get_instance(t[2], true), get_instance(t[3], true));
+                std::vector<Derived> d = setup(g.preprocess(w.scalars), index, 0);
+                buf.commit_drvd();
+                g.assemble(buf, d);
+            } else {
+                get_commitment(t[1], 0);
+                BoundsCheck g(get_instance(t[2], true), get_instance(t[3], true));
+                g.assemble(buf, {dv(index, 0, 0), dv(index, 1, 0)});
+            }
+        } else if (op == "HASH") {
+            std::string img, pre;
+            parse_two(line, "HASH", "WWIW", &img, &pre);
+            const LC image = single_lc(img);
+            MimcHash256 g(image);
+            if (proving) {
+                const Witness w = get_witness(pre);
+                std::vector<Derived> d = setup(g.preprocess(w.scalars), index, 0);
+                buf.commit_drvd();
+                g.assemble(buf, w.vars, d);
+            } else {
+                std::vector<Var> pv = all_commitments(pre);
+                std::vector<Derived> d{dv(index, 0, 0)};
+                Var d2;
+                if (derived(index, 1, 0, &d2, true)) d.push_back({false, s_zero(), d2});
+                g.assemble(buf, pv, d);
+            }
+        } else if (op == "MERKLE") {
+            MerkleLine m = parse_tree(line);
+            MerkleTree256 g;
+            g.root = single_lc(m.root);
+            for (auto& i : m.inst) g.i_vals.push_back(LC::cst(mimc_hash(get_instance(i))));
+            for (size_t k = 0; k < m.wtns.size(); k++) g.w_vals.push_back(LC::var(hash_witness(buf, m.wtns[k], index, k, nullptr)));
+            g.pat = m.pat;
+            g.assemble(buf);
+        } else if (op == "EQUALS") {
+            std::string a, b;
+            parse_two(line, "EQUALS", "WIIWWW", &a, &b);
+            if (a[0] == 'I') std::swap(a, b);
+            std::vector<LC> right, left_lcs;
+            std::vector<Var> left;
+            multi(a, nullptr, &left_lcs, &left);
+            multi(b, nullptr, &right);
+            equality_assemble(buf, right, left);
+        } else if (op == "LESS_THAN") {
+            std::string l, r;
+            parse_two(line, "LESS_THAN", "WW", &l, &r);
+            if (proving) {
+                const Witness wl = get_witness(l, true), wr = get_witness(r, true);
+                const S delta = s_sub(wr.scalars[0], wl.scalars[0]);
+                std::vector<Derived> d = setup({delta, s_is_zero(delta) ? s_zero() : s_invert(delta)}, index, 0);
+                buf.commit_drvd();
+                less_than_assemble(buf, LC::var(wl.vars[0]), true, wl.scalars[0], LC::var(wr.vars[0]), wr.scalars[0], d);
+            } else {
+                const Var lv = get_commitment(l, 0), rv = get_commitment(r, 0);
+                less_than_assemble(buf, LC::var(lv), false, s_zero(), LC::var(rv), s_zero(), {dv(index, 0, 0), dv(index, 1, 0)});
+            }
+        } else if (op == "UNEQUAL") {
+            std::string a, b;
+            parse_two(line, "UNEQUAL", "WIIWWW", &a, &b);
+            if (a[0] == 'I') std::swap(a, b);
+            std::vector<S> lsc, rsc;
+            std::vector<LC> llc, rlc;
+            std::vector<Var> lvars;
+            multi(a, &lsc, &llc, &lvars);
+            multi(b, &rsc, &rlc);
+            std::vector<Derived> d;
+            if (proving) {
+                d = setup(inequality_preprocess(lsc, rsc), index, 0);
+                buf.commit_drvd();
+            } else {
+                for (size_t i = 0; i < 2 * lvars.size(); i++) d.push_back(dv(index, i, 0));
+                d.push_back(dv(index, 2 * lvars.size(), 0));
+            }
+            inequality_assemble(buf, rlc, lvars, d);
+        } else if (op == "SET_MEMBER") {
+            set_member(line, buf, index);
+        }
+    }
+
+    void set_member(const std::string& line, Buffer& buf, size_t index) {
+        auto t = split_ws(line);
+        if (t.size() < 3) throw Panic("cannot parse " + line);
+        for (size_t i = 1; i < t.size(); i++)
+            if (!is_var(t[i], 'W') && !is_var(t[i], 'I')) throw Panic("cannot parse " + line);
+        const std::string member = t[1];
+        std::vector<std::string> elems(t.begin() + 2, t.end());
+        std::vector<S> m_sc;
+        std::vector<LC> m_lcs;
+        multi(member, &m_sc, &m_lcs);
+        if (m_lcs.empty()) throw Panic("empty member");
+        S member_scalar = proving || member[0] == 'I' ? (m_sc.empty() ? s_zero() : m_sc[0]) : s_zero();
+        LC member_lc = m_lcs[0];
+        bool hashing = proving ? m_lcs.size() > 1 : false;
+        std::vector<Var> w_vars;
+        std::vector<S> w_sc, i_sc;
+        std::vector<LC> i_lcs;
+        if (!hashing) {
+            for (auto& e : elems) {
+                std::vector<S> sc_;
+                std::vector<LC> lcs;
+                std::vector<Var> vars;
+                multi(e, &sc_, &lcs, &vars);
+                if (lcs.size() == 1) {
+                    if (e[0] == 'W') {
+                        w_vars.push_back(vars[0]);
+                        if (proving) w_sc.push_back(sc_[0]);
+                    } else {
+                        i_lcs.push_back(lcs[0]);
+                        i_sc.push_back(sc_[0]);
+                    }
+                } else {
+                    hashing = true;
+                }
+            }
+        }
+        if (m_lcs.size() > 1) hashing = true;
+        std::vector<Derived> one_hot;
+        if (!proving)
+            for (size_t k = 0; k < elems.size(); k++) one_hot.push_back(dv(index, k, 0));  // looked up before any hashing (verify.rs:352-355)
+        if (hashing) {
+            size_t sub = 1;
+            if (member[0] == 'W') {
+                member_lc = LC::var(hash_witness(buf, member, index, sub, &member_scalar));
+                sub++;
+            } else {
+                member_scalar = mimc_hash(get_instance(member));
+                member_lc = LC::cst(member_scalar);
+            }
+            w_vars.clear();
+            w_sc.clear();
+            i_lcs.clear();
+            i_sc.clear();
+            for (auto& e : elems) {
+                if (e[0] == 'W') {
+                    S s = s_zero();
+                    w_vars.push_back(hash_witness(buf, e, index, sub, &s));
+                    sub++;
+                    w_sc.push_back(s);
+                } else {
+                    const S s = mimc_hash(get_instance(e));
+                    i_lcs.push_back(LC::cst(s));
+                    i_sc.push_back(s);
+                }
+            }
+        }
+        if (proving) {
+            std::vector<S> hot;
+            for (auto& s : w_sc) hot.push_back(s_eq(s, member_scalar) ? s_one() : s_zero());
+            for (auto& s : i_sc) hot.push_back(s_eq(s, member_scalar) ? s_one() : s_zero());
+            one_hot = setup(hot, index, 0);
+            buf.commit_drvd();
+        }
+        set_membership_assemble(buf, member_lc, i_lcs, w_vars, one_hot);
+    }
+};
+
+// the `.gadgets` walk shared by prove.rs:62-70 / verify.rs:57-65 incl. OR blocks (prove.rs:184-220, verify.rs:129-158)
+struct Walker {
+    Side& side;
+    std::vector<std::string> lines;
+    size_t pos = 0;
+    void conjunction(Buffer& parent, const std::vector<const std::vector<Op>*>& initialization) {
+        Buffer inner(parent.proving);
+        inner.initialize_from(initialization);
+        if (pos >= lines.size()) throw Panic("unexpected end of input");
+        while (pos < lines.size()) {
+            const size_t idx = pos;
+            const std::string line = lines[pos++];
+            const std::string op = gadget_op(line);
+            if (op == "]") break;
+            if (op == "}") {
+                inner.rewind();
+                continue;
+            }
+            if (op == "OR") {
+                const std::vector<Op> snapshot = inner.ops;  // local_initialization: enclosing scopes + this clause so far
+                std::vector<const std::vector<Op>*> local = initialization;
+                local.push_back(&snapshot);
+                conjunction(inner, local);
+            }
+            side.gadget_line(line, inner, idx);
+        }
+        for (auto& ops : inner.cache)  // add_commitments_to_parent (Commit ops never reach the real constraint system)
+            for (auto& o : ops)
+                if (o.kind == Op::COMMIT) parent.commit_drvd();
+        or_combine(parent, inner);
+    }
+    void run(Buffer& top) {
+        while (pos < lines.size()) {
+            const size_t idx = pos;
+            const std::string line = lines[pos++];
+            const std::string op = gadget_op(line);
+            if (op == "OR") {
+                const std::vector<Op> snapshot = top.ops;
+                conjunction(top, {&snapshot});
+            }
+            side.gadget_line(line, top, idx);
+        }
+    }
+};
+
+std::function<S(uint64_t)> blinding_stream(const uint8_t seed[32]) {
+    Bytes s(seed, seed + 32);
+    return [s](uint64_t k) {
+        bpg::Sponge sp = bpg::shake256();
+        sp.absorb(s.data(), s.size());
+        uint8_t le[8];
+        for (int i = 0; i < 8; i++) le[i] = (uint8_t)(k >> (8 * i));
+        sp.absorb(le, 8);
+        uint8_t wide[64];
+        sp.squeeze(wide, 64);
+        return bpg::Scalar::from_bytes_wide(wide).s;
+    };
+}
+
+void compile_prover(const char* instance, const char* witness, const char* gadgets, const uint8_t* blinding_seed32, Side* side) {
+    side->proving = true;
+    uint8_t seed[32];
+    if (blinding_seed32) memcpy(seed, blinding_seed32, 32);
+    else {
+        std::random_device rd;
+        for (int i = 0; i < 8; i++) {
+            uint32_t x = rd();
+            memcpy(seed + 4 * i, &x, 4);
+        }
+    }
+    side->blinding = blinding_stream(seed);
+    for (auto& line : split_lines(instance)) {
+        auto kv = parse_var_line('I', line);
+        side->instance[kv.first] = kv.second;
+    }
+    for (auto& line : split_lines(witness)) {
+        auto kv = parse_var_line('W', line);
+        Witness w;
+        w.raw = kv.second;
+        w.scalars = be_to_scalars(kv.second);
+        for (size_t k = 0; k < w.scalars.size(); k++)
+            w.vars.push_back(side->commit(w.scalars[k], "C" + kv.first.substr(1) + "-" + std::to_string(k)));
+        side->witness[kv.first] = w;
+    }
+    Buffer top(true);
+    Walker wk{*side, split_lines(gadgets)};
+    wk.run(top);
+    side->st.replay(top.ops, true);
+}
+
+void compile_verifier(const char* instance, const char* commitments, const char* gadgets, Side* side) {
+    side->proving = false;
+    for (auto& line : split_lines(instance)) {
+        auto kv = parse_var_line('I', line);
+        side->instance[kv.first] = kv.second;
+    }
+    for (auto& line : split_lines(commitments)) {
+        auto kv = parse_var_line('C', line);
+        if (kv.second.size() != 32) throw Panic("commitment " + kv.first + " is not 32 bytes");
+        side->coms[kv.first] = mkvar(K_COMMITTED, (uint32_t)side->st.V.size());
+        side->st.V.push_back(kv.second);
+        side->st.com_names.push_back(kv.first);
+    }
+    Buffer top(false);
+    Walker wk{*side, split_lines(gadgets)};
+    wk.run(top);
+    side->st.replay(top.ops, false);
+}
+
+template <typename T>
+T* dup(const std::vector<T>& v) {
+    T* p = (T*)malloc(sizeof(T) * (v.size() ? v.size() : 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+uint8_t* dup_scalars(const std::vector<S>& v) {
+    uint8_t* p = (uint8_t*)malloc(32 * (v.size() ? v.size() : 1));
+    for (size_t i = 0; i < v.size(); i++) memcpy(p + 32 * i, v[i].v, 32);
+    return p;
+}
+
+bpg_flat_statement* export_flat(const Flat& st, bool proving) {
+    bpg_flat_statement* f = (bpg_flat_statement*)calloc(1, sizeof(bpg_flat_statement));
+    f->n = st.n;
+    f->m = proving ? st.v.size() : st.V.size();
+    f->q = st.row_start.size() - 1;
+    f->nnz = st.term_var.size();
+    if (proving) {
+        f->v32m = dup_scalars(st.v);
+        f->vbl32m = dup_scalars(st.vbl);
+        f->aL32n = dup_scalars(st.aL);
+        f->aR32n = dup_scalars(st.aR);
+    } else {
+        f->V32m = (uint8_t*)malloc(32 * (st.V.size() ? st.V.size() : 1));
+        for (size_t i = 0; i < st.V.size(); i++) memcpy(f->V32m + 32 * i, st.V[i].data(), 32);
+    }
+    f->row_start = dup(st.row_start);
+    f->term_var = dup(st.term_var);
+    f->term_coef32 = dup_scalars(st.term_coef);
+    std::string names;
+    for (auto& n : st.com_names) names += n + "\n";
+    f->com_names = strdup(names.c_str());
+    return f;
+}
+
+template <typename F>
+int guarded(F&& fn) {
+    try {
+        return fn();
+    } catch (const Panic& e) {
+        bpg_set_error("front end: %s", e.what());
+        return BPG_E_GADGET;
+    } catch (const std::exception& e) {
+        bpg_set_error("front end: %s", e.what());
+        return BPG_E_GADGET;
+    }
+}
+
+}  // namespace
+
 extern "C" {
-int bpg_prove(bpg_ctx*, const char*, const char*, const char*, const char*, const uint8_t*, const uint8_t*,
-              bpg_proof_artifacts** out) {
-    if (out) *out = nullptr;
-    bpg_set_error("bpg_prove: statement front end not built yet");
-    return BPG_E_GADGET;
+
+int bpg_frontend_flatten_prover(const char* name, const char* instance, const char* witness, const char* gadgets,
+                                const uint8_t* blinding_seed32, bpg_flat_statement** out) {
+    if (!name || !instance || !witness || !gadgets || !out) return BPG_E_ARG;
+    *out = nullptr;
+    return guarded([&]() {
+        Side side;
+        compile_prover(instance, witness, gadgets, blinding_seed32, &side);
+        *out = export_flat(side.st, true);
+        return BPG_OK;
+    });
 }
-int bpg_verify(bpg_ctx*, const char*, const char*, const char*, const char*, const uint8_t*, size_t, const uint8_t*,
-               int* accepted) {
-    if (accepted) *accepted = 0;
-    bpg_set_error("bpg_verify: statement front end not built yet");
-    return BPG_E_GADGET;
+
+int bpg_frontend_flatten_verifier(const char* name, const char* instance, const char* commitments, const char* gadgets,
+                                  bpg_flat_statement** out) {
+    if (!name || !instance || !commitments || !gadgets || !out) return BPG_E_ARG;
+    *out = nullptr;
+    return guarded([&]() {
+        Side side;
+        compile_verifier(instance, commitments, gadgets, &side);
+        *out = export_flat(side.st, false);
+        return BPG_OK;
+    });
 }
+
+void bpg_flat_statement_free(bpg_flat_statement* f) {
+    if (!f) return;
+    free(f->v32m);
+    free(f->vbl32m);
+    free(f->V32m);
+    free(f->aL32n);
+    free(f->aR32n);
+    free(f->row_start);
+    free(f->term_var);
+    free(f->term_coef32);
+    free(f->com_names);
+    free(f);
+}
+
+int bpg_prove(bpg_ctx* ctx, const char* name, const char* instance, const char* witness, const char* gadgets,
+              const uint8_t* blinding_seed32, const uint8_t* rng_seed32, bpg_proof_artifacts** out) {
+    if (!ctx || !name || !instance || !witness || !gadgets || !out) return BPG_E_ARG;
+    *out = nullptr;
+    return guarded([&]() -> int {
+        Side side;
+        compile_prover(instance, witness, gadgets, blinding_seed32, &side);
+        const Flat& st = side.st;
+        bpg_transcript* t = bpg_transcript_new(reinterpret_cast<const uint8_t*>(name), strlen(name));
+        bpg_prover* p = nullptr;
+        int rc = bpg_prover_new(ctx, t, &p);
+        std::vector<uint8_t> V(32 * (st.v.size() ? st.v.size() : 1)), proof(1 + 14 * 32 + 66 * 32);
+        size_t proof_len = 0;
+        if (!rc) {
+            uint8_t *v = dup_scalars(st.v), *vb = dup_scalars(st.vbl), *aL = dup_scalars(st.aL), *aR = dup_scalars(st.aR),
+                    *coef = dup_scalars(st.term_coef);
+            // every commitment precedes every challenge, so one batched launch keeps the transcript order
+            rc = bpg_prover_commit_batch(p, v, vb, st.v.size(), V.data(), nullptr);
+            if (!rc) rc = bpg_prover_load_cs(p, aL, aR, st.n, st.row_start.data(), st.term_var.data(), coef, st.row_start.size() - 1);
+            if (!rc) rc = bpg_prover_prove(p, rng_seed32, proof.data(), proof.size(), &proof_len);
+            free(v), free(vb), free(aL), free(aR), free(coef);
+        }
+        if (p) bpg_prover_free(p);
+        bpg_transcript_free(t);
+        if (rc) return rc;
+        std::string text;
+        static const char* HEX = "0123456789abcdef";
+        for (size_t i = 0; i < st.v.size(); i++) {
+            text += st.com_names[i] + " = 0x";
+            for (int k = 0; k < 32; k++) {
+                text += HEX[V[32 * i + k] >> 4];
+                text += HEX[V[32 * i + k] & 15];
+            }
+            text += "\n";
+        }
+        bpg_proof_artifacts* a = (bpg_proof_artifacts*)calloc(1, sizeof(bpg_proof_artifacts));
+        a->commitments = strdup(text.c_str());
+        a->proof = (uint8_t*)malloc(proof_len ? proof_len : 1);
+        memcpy(a->proof, proof.data(), proof_len);
+        a->proof_len = proof_len;
+        a->num_constraints = st.row_start.size() - 1;
+        *out = a;
+        return BPG_OK;
+    });
+}
+
+int bpg_verify(bpg_ctx* ctx, const char* name, const char* instance, const char* gadgets, const char* commitments,
+               const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32, int* accepted) {
+    if (!ctx || !name || !instance || !gadgets || !commitments || !proof || !accepted) return BPG_E_ARG;
+    *accepted = 0;
+    return guarded([&]() -> int {
+        Side side;
+        compile_verifier(instance, commitments, gadgets, &side);
+        const Flat& st = side.st;
+        bpg_transcript* t = bpg_transcript_new(reinterpret_cast<const uint8_t*>(name), strlen(name));
+        bpg_verifier* v = nullptr;
+        int rc = bpg_verifier_new(ctx, t, &v);
+        if (!rc) {
+            std::vector<uint8_t> V(32 * (st.V.size() ? st.V.size() : 1));
+            for (size_t i = 0; i < st.V.size(); i++) memcpy(&V[32 * i], st.V[i].data(), 32);
+            uint8_t* coef = dup_scalars(st.term_coef);
+            rc = bpg_verifier_commit_batch(v, V.data(), st.V.size(), nullptr);
+            if (!rc) rc = bpg_verifier_load_cs(v, st.n, st.row_start.data(), st.term_var.data(), coef, st.row_start.size() - 1);
+            if (!rc) rc = bpg_verifier_verify(v, proof, proof_len, rng_seed32);
+            free(coef);
+        }
+        if (v) bpg_verifier_free(v);
+        bpg_transcript_free(t);
+        if (rc == BPG_OK) {
+            *accepted = 1;
+            return BPG_OK;
+        }
+        if (rc == BPG_E_VERIFY) return BPG_OK;  // verify() maps every R1CSError of the check itself to Ok(false) (verify.rs:71-72)
+        return rc;
+    });
+}
+
 void bpg_free_proof(bpg_proof_artifacts* a) {
     if (!a) return;
     free(a->commitments);
     free(a->proof);
-    delete a;
+    free(a);
 }
-}
+
+}  // extern "C"

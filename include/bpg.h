@@ -187,6 +187,28 @@ int bpg_verify(bpg_ctx* ctx, const char* name, const char* instance, const char*
                const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32, int* accepted);
 void bpg_free_proof(bpg_proof_artifacts* a);
 
+/* The flat statement the real Prover / Verifier hold after assign_buffer (/root/reference/src/prove.rs:84-99,
+ * /root/reference/src/verify.rs:75-90), as produced by the front end from the text formats.  Pure host code (no
+ * GPU needed): lets a caller inspect / cache the circuit, or feed the bulk loaders itself.
+ * Prover side: v32m, vbl32m, aL32n, aR32n set, V32m NULL.  Verifier side: V32m set, the others NULL. */
+typedef struct bpg_flat_statement {
+    uint64_t n, m, q, nnz;
+    uint8_t* v32m;
+    uint8_t* vbl32m;
+    uint8_t* V32m;
+    uint8_t* aL32n;
+    uint8_t* aR32n;
+    uint32_t* row_start;   /* q + 1 */
+    uint32_t* term_var;    /* nnz variable tags */
+    uint8_t* term_coef32;  /* nnz * 32 */
+    char* com_names;       /* '\n'-terminated .coms names (C<w>-<limb>, D<line>-<sub>-<k>) in commit order */
+} bpg_flat_statement;
+int bpg_frontend_flatten_prover(const char* name, const char* instance, const char* witness, const char* gadgets,
+                                const uint8_t* blinding_seed32, bpg_flat_statement** out);
+int bpg_frontend_flatten_verifier(const char* name, const char* instance, const char* commitments, const char* gadgets,
+                                  bpg_flat_statement** out);
+void bpg_flat_statement_free(bpg_flat_statement* f);
+
 #ifdef __cplusplus
 }
 #endif

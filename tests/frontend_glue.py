@@ -7,7 +7,8 @@ from oracle.pyref.merlin import L
 FIXDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures")
 STEMS = ["example", "bounds_check", "equality", "inequality", "less_than", "merkle_tree", "mimc_hash", "set_membership",
          "or", "or2", "or3", "or4", "or5"]
-SEED_BLIND, SEED_PROVE, SEED_VERIFY = b"fixture-blindings", b"\x07" * 32, b"\x09" * 32
+SEED_BLIND, SEED_PROVE, SEED_VERIFY = b"fixture-blindings--bpg-golden-01", b"\x07" * 32, b"\x09" * 32
+assert len(SEED_BLIND) == 32  # also handed to the C ABI (bpg_prove blinding_seed32)
 
 
 def blinding(seed=SEED_BLIND):
