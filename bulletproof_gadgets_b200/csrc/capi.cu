@@ -88,13 +88,11 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     MsmWork& w = ctx->work;
     w.hist.release();
     w.bucket_off.release();
-    w.task_off.release();
+    w.chunk_bucket.release();
     w.entries.release();
-    w.tasks.release();
     w.partials.release();
     w.blockres.release();
-    w.meta.release();
-    w.tile_sum.release();
+    w.scan_tmp.release();
     ctx->d_scalars.release();
     ctx->d_points.release();
     r1cs_release_work(ctx);

@@ -88,15 +88,13 @@ struct GensStore {
 };
 
 struct MsmWork {
-    DevBuf<uint32_t> hist;       // [nsets*nb] counts, then reused as scatter cursors
-    DevBuf<uint32_t> bucket_off; // [nsets*nb]
-    DevBuf<uint32_t> task_off;   // [nsets*nb]
-    DevBuf<uint32_t> entries;    // [K*N]
-    DevBuf<uint2> tasks;         // {start, bucket<<8 | count}
-    DevBuf<ge_ext> partials;     // one per task
-    DevBuf<ge_ext> blockres;     // [nsets][REDUCE_BLOCKS]
-    DevBuf<uint64_t> tile_sum;   // scan scratch (entries | tasks << 32 per 2048-bucket tile)
-    DevBuf<uint32_t> meta;       // [0]=ntasks total, [1+s]=task start of set s, ... see msm.cu
+    DevBuf<uint32_t> hist;          // [nsets*nb] counts, then reused as scatter cursors
+    DevBuf<uint32_t> bucket_off;    // [nsets*nb + 1] exclusive scan of the counts
+    DevBuf<uint32_t> chunk_bucket;  // bucket of the first entry of each fixed-length chunk
+    DevBuf<uint32_t> entries;       // [K*N] (row | sign << 31), sorted by bucket
+    DevBuf<ge_ext> partials;        // slot (chunk t, bucket b) = t + b
+    DevBuf<ge_ext> blockres;        // [nsets][REDUCE_BLOCKS]
+    DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan
 };
 
 struct bpg_ctx {

@@ -14,11 +14,16 @@
 //
 // Stages (all on ctx->stream, no host round trip until the final 128-byte result):
 //   1 digits+histogram   signed c-bit digits, one global-atomic histogram per bucket set  [HBM/L2]
-//   2 scan               bucket offsets + balanced task split (<= task_len entries each)
+//   2 scan               bucket offsets (multi-CTA exclusive scan)
 //   3 digits+scatter     counting-sort of (row | sign) entries by bucket                  [HBM/L2]
-//   4 tasks              task descriptors
-//   5 accumulate         one thread per task: mixed adds of gathered Niels rows           [IMAD]
-//   6 reduce             weighted running sums over task partials, block tree, final tree
+//   4 chunks             bucket of the first entry of every fixed-length chunk
+//   5 accumulate         one thread per chunk of exactly `task_len` sorted entries: mixed adds of gathered
+//                        Niels rows; a chunk that crosses bucket boundaries emits one partial per bucket,
+//                        so every lane runs the same number of additions (no divergence)   [IMAD]
+//   6 reduce             weighted running sums over bucket partials, block tree, final tree
+#include <stdlib.h>
+
+#include "circuit.hpp"
 #include "ctx.hpp"
 
 #define REDUCE_BLOCKS 128
@@ -79,116 +84,14 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 2: exclusive scans (entries, tasks) over all buckets of all sets.  The two sums ride one
-// 64-bit word (entries low, tasks high; both < 2^32), tiles of 2048 buckets, three small launches.
+// stage 4: chunk t covers sorted entries [t*CL, (t+1)*CL); chunk_bucket[t] = bucket holding entry t*CL
 // ------------------------------------------------------------------------------------------
-#define BS_THREADS 256
-#define BS_ITEMS 8
-#define BS_TILE (BS_THREADS * BS_ITEMS)
-__device__ __forceinline__ uint64_t bs_block_exclusive(uint64_t v, uint64_t* total, uint64_t* sh /*[32]*/) {
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint64_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (uint32_t)o) inc += t;
-    }
-    if (lane == 31) sh[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        uint64_t w = lane < nw ? sh[lane] : 0ull;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint64_t t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= (uint32_t)o) w += t;
-        }
-        sh[lane] = w;
-    }
-    __syncthreads();
-    const uint64_t base = wid ? sh[wid - 1] : 0ull;
-    *total = sh[nw - 1];
-    __syncthreads();
-    return base + inc - v;
-}
-__global__ void __launch_bounds__(BS_THREADS) k_bscan_tiles(const uint32_t* __restrict__ hist, uint32_t* __restrict__ bucket_off,
-                                                            uint32_t* __restrict__ task_off, uint64_t* __restrict__ tile_sum,
-                                                            uint32_t G, uint32_t task_len) {
-    __shared__ uint64_t sh[32];
-    const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_ITEMS;
-    uint64_t v[BS_ITEMS], s = 0;
-#pragma unroll
-    for (int k = 0; k < BS_ITEMS; k++) {
-        const uint32_t cnt = base + k < G ? hist[base + k] : 0u;
-        v[k] = (uint64_t)cnt | ((uint64_t)((cnt + task_len - 1) / task_len) << 32);
-        s += v[k];
-    }
-    uint64_t total;
-    uint64_t pre = bs_block_exclusive(s, &total, sh);
-#pragma unroll
-    for (int k = 0; k < BS_ITEMS; k++) {
-        if (base + k < G) {
-            bucket_off[base + k] = (uint32_t)pre;
-            task_off[base + k] = (uint32_t)(pre >> 32);
-        }
-        pre += v[k];
-    }
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(1024) k_bscan_top(uint64_t* __restrict__ tile_sum, uint32_t ntiles) {
-    __shared__ uint64_t sh[32];
-    uint64_t carry = 0;
-    for (uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
-        const uint32_t i = b0 + threadIdx.x;
-        const uint64_t v = i < ntiles ? tile_sum[i] : 0ull;
-        uint64_t total;
-        const uint64_t pre = bs_block_exclusive(v, &total, sh);
-        if (i < ntiles) tile_sum[i] = carry + pre;
-        carry += total;
-    }
-    if (threadIdx.x == 0) tile_sum[ntiles] = carry;
-}
-// adds the tile offsets, clears the histogram (it becomes the scatter cursor) and writes
-// meta[0] = #tasks, meta[1+s] = first task of set s, meta[1+nsets] = #tasks
-__global__ void __launch_bounds__(BS_THREADS) k_bscan_finish(uint32_t* __restrict__ hist, uint32_t* __restrict__ bucket_off,
-                                                             uint32_t* __restrict__ task_off, const uint64_t* __restrict__ tile_sum,
-                                                             uint32_t* __restrict__ meta, uint32_t G, uint32_t nb, uint32_t nsets,
-                                                             uint32_t ntiles) {
-    const uint64_t add = tile_sum[blockIdx.x];
-    const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_ITEMS;
-#pragma unroll
-    for (int k = 0; k < BS_ITEMS; k++) {
-        const uint32_t b = base + k;
-        if (b < G) {
-            const uint32_t to = task_off[b] + (uint32_t)(add >> 32);
-            bucket_off[b] += (uint32_t)add;
-            task_off[b] = to;
-            hist[b] = 0;
-            if (b % nb == 0) meta[1 + b / nb] = to;
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const uint64_t tot = tile_sum[ntiles];
-        bucket_off[G] = (uint32_t)tot;
-        task_off[G] = (uint32_t)(tot >> 32);
-        meta[0] = (uint32_t)(tot >> 32);
-        meta[1 + nsets] = (uint32_t)(tot >> 32);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// stage 4: task descriptors (balanced split of each bucket)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tasks(const uint32_t* __restrict__ bucket_off,
-                                               const uint32_t* __restrict__ task_off, uint2* __restrict__ tasks,
-                                               uint32_t G) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_chunks(const uint32_t* __restrict__ bucket_off, uint32_t* __restrict__ chunk_bucket,
+                                                uint32_t G, uint32_t CL) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= G) return;
-    const uint32_t off = bucket_off[b], cnt = bucket_off[b + 1] - off;
-    const uint32_t t0 = task_off[b], nt = task_off[b + 1] - t0;
-    for (uint32_t k = 0; k < nt; k++) {
-        uint32_t a = (uint32_t)(((uint64_t)k * cnt) / nt), e = (uint32_t)(((uint64_t)(k + 1) * cnt) / nt);
-        tasks[t0 + k] = make_uint2(off + a, (b << 8) | (e - a));
-    }
+    const uint32_t lo = bucket_off[b], hi = bucket_off[b + 1];
+    for (uint32_t t = (lo + CL - 1) / CL; t * CL < hi; t++) chunk_bucket[t] = b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,24 +131,44 @@ __device__ __forceinline__ ge_ext load_ext(const ge_ext* src) {
     return p;
 }
 
+// partial slot of (chunk t, bucket b) = t + b: buckets are sorted along the entries, so the sum is unique, and the
+// slots of one bucket are contiguous: chunks off[b]/CL .. (off[b+1]-1)/CL.
 __global__ void __launch_bounds__(ACC_THREADS, 4)
     k_accumulate(const ge_niels* __restrict__ rows, const uint32_t* __restrict__ entries,
-                 const uint2* __restrict__ tasks, const uint32_t* __restrict__ meta, ge_ext* __restrict__ partials) {
+                 const uint32_t* __restrict__ bucket_off, const uint32_t* __restrict__ chunk_bucket, uint32_t G, uint32_t CL,
+                 ge_ext* __restrict__ partials) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= meta[0]) return;
-    const uint2 td = tasks[t];
-    const uint32_t cnt = td.y & 0xffu;
-    const uint32_t* ep = entries + td.x;
+    const uint32_t E = bucket_off[G];
+    const uint32_t e0 = t * CL;
+    if (e0 >= E) return;
+    const uint32_t e1 = min(e0 + CL, E);
+    uint32_t b = chunk_bucket[t];
+    uint32_t next = bucket_off[b + 1];
     ge_ext acc = ge_identity();
-    uint32_t ent = __ldg(ep);
+    uint32_t ent = __ldg(entries + e0);
 #pragma unroll 1
-    for (uint32_t e = 0; e < cnt; e++) {
+    for (uint32_t e = e0; e < e1; e++) {
+        if (e == next) {  // bucket boundary inside the chunk: emit the partial of the finished bucket
+            store_ext(partials + t + b, acc);
+            acc = ge_identity();
+            b++;
+            next = bucket_off[b + 1];
+            if (next == e) {  // run of empty buckets (sparse digit sets): bucket of entry e by bisection
+                uint32_t lo = b + 1, hi = G;  // smallest j in (b, G] with bucket_off[j] > e; entry e lives in bucket j-1
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (bucket_off[mid] > e) hi = mid; else lo = mid + 1;
+                }
+                b = lo - 1;
+                next = bucket_off[lo];
+            }
+        }
         ge_niels q = load_niels(rows, ent & 0x7fffffffu);
         const bool neg = ent >> 31;
-        if (e + 1 < cnt) ent = __ldg(ep + e + 1);
+        if (e + 1 < e1) ent = __ldg(entries + e + 1);
         acc = ge_madd(acc, q, neg);
     }
-    store_ext(partials + t, acc);
+    store_ext(partials + t + b, acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -277,33 +200,35 @@ __device__ __forceinline__ void block_tree_reduce(ge_ext* sh, ge_ext& mine, uint
     }
 }
 
+// one thread per contiguous range of buckets of one set, walking from the top bucket down:
+//   R = sum B_b ;  S = sum (b - lo + 1) B_b ;  contribution = S + (lo - set_base) * R
 __global__ void __launch_bounds__(REDUCE_THREADS)
-    k_reduce_chunks(const ge_ext* __restrict__ partials, const uint2* __restrict__ tasks,
-                    const uint32_t* __restrict__ meta, uint32_t nb, ge_ext* __restrict__ blockres) {
+    k_reduce_chunks(const ge_ext* __restrict__ partials, const uint32_t* __restrict__ bucket_off, uint32_t nb, uint32_t CL,
+                    ge_ext* __restrict__ blockres) {
     __shared__ ge_ext sh[REDUCE_THREADS];
     const uint32_t s = blockIdx.y;
-    const uint32_t tb = meta[1 + s], te = meta[2 + s];
-    const uint32_t nt = te - tb, nchunks = REDUCE_BLOCKS * REDUCE_THREADS;
-    const uint32_t per = (nt + nchunks - 1) / nchunks;
+    const uint32_t nthreads = REDUCE_BLOCKS * REDUCE_THREADS;
+    const uint32_t per = (nb + nthreads - 1) / nthreads;
     const uint32_t cidx = blockIdx.x * REDUCE_THREADS + threadIdx.x;
-    const uint64_t a64 = (uint64_t)tb + (uint64_t)cidx * per;
+    const uint32_t lo_local = cidx * per;
     ge_ext total = ge_identity();
-    if (per > 0 && a64 < te) {
-        const uint32_t a = (uint32_t)a64, b = min(a + per, te);
-        const uint32_t wbase = s * nb;
+    if (lo_local < nb) {
+        const uint32_t hi_local = min(lo_local + per, nb);
+        const uint32_t base = s * nb;
         ge_ext R = ge_identity(), S = ge_identity();
-        uint32_t wprev = (tasks[b - 1].y >> 8) - wbase + 1;
+        bool any = false;
 #pragma unroll 1
-        for (uint32_t t = b; t-- > a;) {
-            uint32_t w = (tasks[t].y >> 8) - wbase + 1;
-            if (w != wprev) {
-                uint32_t gap = wprev - w;
-                S = ge_add(S, gap == 1 ? R : ge_mul_small(R, gap));
-                wprev = w;
+        for (uint32_t bl = hi_local; bl-- > lo_local;) {
+            const uint32_t b = base + bl;
+            const uint32_t o0 = bucket_off[b], o1 = bucket_off[b + 1];
+            if (o1 > o0) {
+                const uint32_t t0 = o0 / CL, t1 = (o1 - 1) / CL;
+#pragma unroll 1
+                for (uint32_t t = t0; t <= t1; t++) R = any ? ge_add(R, load_ext(partials + t + b)) : load_ext(partials + t + b), any = true;
             }
-            R = ge_add(R, load_ext(partials + t));
+            if (any) S = ge_add(S, R);
         }
-        total = ge_add(S, ge_mul_small(R, wprev));
+        if (any) total = lo_local ? ge_add(S, ge_mul_small(R, lo_local)) : S;
     }
     block_tree_reduce(sh, total, threadIdx.x, REDUCE_THREADS);
     if (threadIdx.x == 0) store_ext(blockres + s * REDUCE_BLOCKS + blockIdx.x, load_ext(sh));
@@ -338,17 +263,17 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
     const uint64_t total = segs.total;
     const uint64_t max_entries = (uint64_t)tb.K * total;
     const uint32_t T = (uint32_t)ctx->task_len;
-    const uint64_t max_tasks = max_entries / T + G + 1;
+    const uint64_t max_chunks = max_entries / T + 1;
+    const uint64_t max_partials = max_chunks + G + 1;
     if (max_entries >= (1ull << 32) || (uint64_t)tb.K * tb.n_points >= (1ull << 31)) {
         bpg_set_error("msm_run: problem too large for 32-bit entry indices");
         return BPG_E_ARG;
     }
     MsmWork& w = ctx->work;
     int rc;
-    if ((rc = w.hist.ensure(G)) || (rc = w.bucket_off.ensure(G + 1)) || (rc = w.task_off.ensure(G + 1)) ||
-        (rc = w.entries.ensure(max_entries + 1)) || (rc = w.tasks.ensure(max_tasks)) ||
-        (rc = w.partials.ensure(max_tasks)) || (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS)) ||
-        (rc = w.meta.ensure(nsets + 3)) || (rc = w.tile_sum.ensure(G / BS_TILE + 3)))
+    if ((rc = w.hist.ensure(G + 1)) || (rc = w.bucket_off.ensure(G + 2)) || (rc = w.chunk_bucket.ensure(max_chunks + 1)) ||
+        (rc = w.entries.ensure(max_entries + 1)) || (rc = w.partials.ensure(max_partials)) ||
+        (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS)) || (rc = w.scan_tmp.ensure(G / 2048 + 4)))
         return rc;
 
     CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));
@@ -357,31 +282,25 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
         k_digits<false><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, nullptr, nullptr);
         ctx->launches++;
     }
-    {
-        const uint32_t ntiles = (G + BS_TILE - 1) / BS_TILE;
-        k_bscan_tiles<<<ntiles, BS_THREADS, 0, st>>>(w.hist.p, w.bucket_off.p, w.task_off.p, w.tile_sum.p, G, T);
-        k_bscan_top<<<1, 1024, 0, st>>>(w.tile_sum.p, ntiles);
-        k_bscan_finish<<<ntiles, BS_THREADS, 0, st>>>(w.hist.p, w.bucket_off.p, w.task_off.p, w.tile_sum.p, w.meta.p, G, nb,
-                                                      nsets, ntiles);
-        ctx->launches += 3;
-    }
+    dev_exclusive_scan_u32(st, w.hist.p, w.bucket_off.p, G, w.scan_tmp.p);
+    CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));  // becomes the scatter cursor
+    ctx->launches += 3;
     if (total > 0) {
         const uint32_t blocks = (uint32_t)((total + 255) / 256);
         k_digits<true><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, w.bucket_off.p,
                                               w.entries.p);
         ctx->launches++;
     }
-    k_tasks<<<(G + 255) / 256, 256, 0, st>>>(w.bucket_off.p, w.task_off.p, w.tasks.p, G);
+    k_chunks<<<(G + 255) / 256, 256, 0, st>>>(w.bucket_off.p, w.chunk_bucket.p, G, T);
     ctx->launches++;
     {
-        const uint32_t blocks = (uint32_t)((max_tasks + ACC_THREADS - 1) / ACC_THREADS);
+        const uint32_t blocks = (uint32_t)((max_chunks + ACC_THREADS - 1) / ACC_THREADS);
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_a, st));
-        k_accumulate<<<blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.tasks.p, w.meta.p, w.partials.p);
+        k_accumulate<<<blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.chunk_bucket.p, G, T, w.partials.p);
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_b, st));
         ctx->launches++;
     }
-    k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.tasks.p, w.meta.p, nb,
-                                                                          w.blockres.p);
+    k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.bucket_off.p, nb, T, w.blockres.p);
     k_reduce_final<<<nsets, REDUCE_BLOCKS, 0, st>>>(w.blockres.p, d_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -393,6 +312,9 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
         ctx->last_entries = ne;
         ctx->sum_accum_ms += ctx->last_accum_ms;
         ctx->sum_entries += ne;
+        if (getenv("BPG_ACC_TRACE"))
+            fprintf(stderr, "[bpg acc] sets %u points %llu entries %u accumulate %.1f us\n", nsets, (unsigned long long)total, ne,
+                    ctx->last_accum_ms * 1e3);
     }
     return BPG_OK;
 }
