@@ -91,6 +91,7 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     w.chunk_bucket.release();
     w.entries.release();
     w.partials.release();
+    w.slot_bucket.release();
     w.blockres.release();
     w.scan_tmp.release();
     ctx->d_scalars.release();

@@ -93,6 +93,7 @@ struct MsmWork {
     DevBuf<uint32_t> chunk_bucket;  // bucket of the first entry of each fixed-length chunk
     DevBuf<uint32_t> entries;       // [K*N] (row | sign << 31), sorted by bucket
     DevBuf<ge_ext> partials;        // slot (chunk t, bucket b) = t + b
+    DevBuf<uint32_t> slot_bucket;   // bucket of each used partial slot (0xffffffff = unused)
     DevBuf<ge_ext> blockres;        // [nsets][REDUCE_BLOCKS]
     DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan
 };

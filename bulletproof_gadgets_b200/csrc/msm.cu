@@ -136,7 +136,7 @@ __device__ __forceinline__ ge_ext load_ext(const ge_ext* src) {
 __global__ void __launch_bounds__(ACC_THREADS, 4)
     k_accumulate(const ge_niels* __restrict__ rows, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ bucket_off, const uint32_t* __restrict__ chunk_bucket, uint32_t G, uint32_t CL,
-                 ge_ext* __restrict__ partials) {
+                 ge_ext* __restrict__ partials, uint32_t* __restrict__ slot_bucket) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t E = bucket_off[G];
     const uint32_t e0 = t * CL;
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 4)
     for (uint32_t e = e0; e < e1; e++) {
         if (e == next) {  // bucket boundary inside the chunk: emit the partial of the finished bucket
             store_ext(partials + t + b, acc);
+            slot_bucket[t + b] = b;
             acc = ge_identity();
             b++;
             next = bucket_off[b + 1];
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 4)
         acc = ge_madd(acc, q, neg);
     }
     store_ext(partials + t + b, acc);
+    slot_bucket[t + b] = b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,35 +202,47 @@ __device__ __forceinline__ void block_tree_reduce(ge_ext* sh, ge_ext& mine, uint
     }
 }
 
-// one thread per contiguous range of buckets of one set, walking from the top bucket down:
-//   R = sum B_b ;  S = sum (b - lo + 1) B_b ;  contribution = S + (lo - set_base) * R
+// One thread per contiguous range of partial SLOTS of one set (slots are ordered by bucket; a heavy bucket -- e.g. the
+// digit-1 bucket of a 0/1-valued a_L vector -- spreads over many threads).  Walking down from the top slot with
+// running sums:  invariant  S + w_prev * R = sum of weight * partial over the slots seen so far.
+#define SLOT_EMPTY 0xffffffffu
 __global__ void __launch_bounds__(REDUCE_THREADS)
-    k_reduce_chunks(const ge_ext* __restrict__ partials, const uint32_t* __restrict__ bucket_off, uint32_t nb, uint32_t CL,
+    k_reduce_chunks(const ge_ext* __restrict__ partials, const uint32_t* __restrict__ slot_bucket,
+                    const uint32_t* __restrict__ bucket_off, uint32_t nb, uint32_t nsets, uint32_t CL,
                     ge_ext* __restrict__ blockres) {
     __shared__ ge_ext sh[REDUCE_THREADS];
     const uint32_t s = blockIdx.y;
+    const uint32_t G = nb * nsets, base = s * nb;
+    const uint32_t E = bucket_off[G];
+    const uint32_t p0 = bucket_off[base] / CL + base;
+    const uint32_t p1 = s + 1 < nsets ? bucket_off[base + nb] / CL + base + nb : (E + CL - 1) / CL + G;
     const uint32_t nthreads = REDUCE_BLOCKS * REDUCE_THREADS;
-    const uint32_t per = (nb + nthreads - 1) / nthreads;
+    const uint32_t per = (p1 - p0 + nthreads - 1) / nthreads;
     const uint32_t cidx = blockIdx.x * REDUCE_THREADS + threadIdx.x;
-    const uint32_t lo_local = cidx * per;
+    const uint64_t lo64 = (uint64_t)p0 + (uint64_t)cidx * per;
     ge_ext total = ge_identity();
-    if (lo_local < nb) {
-        const uint32_t hi_local = min(lo_local + per, nb);
-        const uint32_t base = s * nb;
+    if (per > 0 && lo64 < p1) {
+        const uint32_t lo = (uint32_t)lo64, hi = min(lo + per, p1);
         ge_ext R = ge_identity(), S = ge_identity();
-        bool any = false;
+        uint32_t wprev = 0;
 #pragma unroll 1
-        for (uint32_t bl = hi_local; bl-- > lo_local;) {
-            const uint32_t b = base + bl;
-            const uint32_t o0 = bucket_off[b], o1 = bucket_off[b + 1];
-            if (o1 > o0) {
-                const uint32_t t0 = o0 / CL, t1 = (o1 - 1) / CL;
-#pragma unroll 1
-                for (uint32_t t = t0; t <= t1; t++) R = any ? ge_add(R, load_ext(partials + t + b)) : load_ext(partials + t + b), any = true;
+        for (uint32_t p = hi; p-- > lo;) {
+            const uint32_t b = slot_bucket[p];
+            if (b == SLOT_EMPTY || b < base || b >= base + nb) continue;
+            const uint32_t w = b - base + 1;
+            if (wprev == 0) {
+                wprev = w;
+                R = load_ext(partials + p);
+                continue;
             }
-            if (any) S = ge_add(S, R);
+            if (w != wprev) {
+                const uint32_t gap = wprev - w;
+                S = ge_add(S, gap == 1 ? R : ge_mul_small(R, gap));
+                wprev = w;
+            }
+            R = ge_add(R, load_ext(partials + p));
         }
-        if (any) total = lo_local ? ge_add(S, ge_mul_small(R, lo_local)) : S;
+        if (wprev) total = ge_add(S, ge_mul_small(R, wprev));
     }
     block_tree_reduce(sh, total, threadIdx.x, REDUCE_THREADS);
     if (threadIdx.x == 0) store_ext(blockres + s * REDUCE_BLOCKS + blockIdx.x, load_ext(sh));
@@ -272,7 +286,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
     MsmWork& w = ctx->work;
     int rc;
     if ((rc = w.hist.ensure(G + 1)) || (rc = w.bucket_off.ensure(G + 2)) || (rc = w.chunk_bucket.ensure(max_chunks + 1)) ||
-        (rc = w.entries.ensure(max_entries + 1)) || (rc = w.partials.ensure(max_partials)) ||
+        (rc = w.entries.ensure(max_entries + 1)) || (rc = w.partials.ensure(max_partials)) || (rc = w.slot_bucket.ensure(max_partials)) ||
         (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS)) || (rc = w.scan_tmp.ensure(G / 2048 + 4)))
         return rc;
 
@@ -293,14 +307,17 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
     }
     k_chunks<<<(G + 255) / 256, 256, 0, st>>>(w.bucket_off.p, w.chunk_bucket.p, G, T);
     ctx->launches++;
+    CUDA_TRY(cudaMemsetAsync(w.slot_bucket.p, 0xff, (size_t)max_partials * 4, st));
     {
         const uint32_t blocks = (uint32_t)((max_chunks + ACC_THREADS - 1) / ACC_THREADS);
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_a, st));
-        k_accumulate<<<blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.chunk_bucket.p, G, T, w.partials.p);
+        k_accumulate<<<blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.chunk_bucket.p, G, T, w.partials.p,
+                                                     w.slot_bucket.p);
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_b, st));
         ctx->launches++;
     }
-    k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.bucket_off.p, nb, T, w.blockres.p);
+    k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.slot_bucket.p, w.bucket_off.p, nb, nsets,
+                                                                          T, w.blockres.p);
     k_reduce_final<<<nsets, REDUCE_BLOCKS, 0, st>>>(w.blockres.p, d_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());

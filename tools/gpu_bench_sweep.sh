@@ -1,12 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for d in 1 2 4 6 8 12; do
-  python bench.py --steps 24 --warmup 3 --inflight $d --no-cpu-baseline > gpurun_out/sweep_$d.json 2> gpurun_out/sweep_$d.err
+for d in ${SWEEP:-8 12 16 24}; do
+  python bench.py --steps 48 --warmup 3 --inflight $d --no-cpu-baseline > gpurun_out/sweep_$d.json 2> gpurun_out/sweep_$d.err
   python - <<PY
 import json
 try:
     l = json.loads(open('gpurun_out/sweep_$d.json').read().strip().splitlines()[-1])
-    print('inflight', $d, 'value %.2f' % l['value'], 'e2e %.2f' % l['e2e']['value'], 'lat %.1f ms' % l['latency']['ms_per_step'], 'roof %.3f' % l['roofline']['frac'], l['clocks'])
+    print('inflight', $d, 'value %.2f' % l['value'], 'e2e %.2f' % l['e2e']['value'], 'lat %.1f ms' % l['latency']['ms_per_step'], 'roof %.3f' % l['roofline']['frac'])
 except Exception as e:
     print('inflight', $d, 'FAILED', e); print(open('gpurun_out/sweep_$d.err').read()[-2000:])
 PY
