@@ -19,6 +19,10 @@ from .api import (  # noqa: F401
     Transcript,
     Variable,
     Verifier,
+    flatten_prover,
+    flatten_verifier,
+    mimc_hash,
+    mimc_sponge,
     pinned_copy,
     pinned_empty,
     prove,

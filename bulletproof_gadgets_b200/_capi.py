@@ -94,6 +94,8 @@ PROTOTYPES = {
                                             POINTER(POINTER(FlatStatementC))]),
     "bpg_frontend_flatten_verifier": (c_int, [c_char_p, c_char_p, c_char_p, c_char_p, POINTER(POINTER(FlatStatementC))]),
     "bpg_flat_statement_free": (None, [POINTER(FlatStatementC)]),
+    "bpg_mimc_hash": (c_int, [c_char_p, c_size_t, c_char_p]),
+    "bpg_mimc_sponge": (c_int, [c_char_p, c_size_t, c_char_p]),
 }
 
 

@@ -430,3 +430,57 @@ def verify(ctx, name, instance, proof, commitments, gadgets, rng_seed=None):
     check(lib().bpg_verify(ctx._h, name.encode(), instance.encode(), gadgets.encode(), commitments.encode(), proof,
                            len(proof), rng_seed, byref(acc)))
     return bool(acc.value)
+
+
+def mimc_hash(data):
+    """mimc_hash of /root/reference/src/mimc_hash/mimc.rs:61-75 -> scalar (int)."""
+    out = ctypes.create_string_buffer(32)
+    check(lib().bpg_mimc_hash(bytes(data), len(data), out))
+    return int.from_bytes(out.raw, "little")
+
+
+def mimc_sponge(scalars):
+    """Un-padded MiMC sponge over scalars (Merkle inner nodes; mimc.rs:24-40) -> scalar (int)."""
+    out = ctypes.create_string_buffer(32)
+    check(lib().bpg_mimc_sponge(b"".join(_sb(s) for s in scalars), len(scalars), out))
+    return int.from_bytes(out.raw, "little")
+
+
+def _take_flat(out, proving, label):
+    import numpy as np
+    from .workloads import FlatStatement
+    f = out.contents
+    n, m, q, nnz = f.n, f.m, f.q, f.nnz
+
+    def get(p, k):
+        return bytes(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8 * k)).contents) if k and p else b""
+
+    st = FlatStatement.__new__(FlatStatement)
+    st.label, st.n, st.q, st.m = label, n, q, m
+    st.v_bytes, st.vbl_bytes = (get(f.v32m, 32 * m), get(f.vbl32m, 32 * m)) if proving else (b"", b"")
+    st.v = [int.from_bytes(st.v_bytes[32 * i: 32 * i + 32], "little") for i in range(m)] if proving else []
+    st.vbl = [int.from_bytes(st.vbl_bytes[32 * i: 32 * i + 32], "little") for i in range(m)] if proving else []
+    st.V = [get(f.V32m, 32 * m)[32 * i: 32 * i + 32] for i in range(m)] if not proving else []
+    st.aL, st.aR = (get(f.aL32n, 32 * n), get(f.aR32n, 32 * n)) if proving else (b"", b"")
+    st.row_start = np.frombuffer(get(f.row_start, 4 * (q + 1)), dtype=np.uint32).copy()
+    st.term_var = np.frombuffer(get(f.term_var, 4 * nnz), dtype=np.uint32).copy() if nnz else np.zeros(1, dtype=np.uint32)
+    st.term_coef = get(f.term_coef32, 32 * nnz) or bytes(32)
+    st.com_names = f.com_names.decode().split("\n")[:-1]
+    lib().bpg_flat_statement_free(out)
+    return st
+
+
+def flatten_prover(name, instance, witness, gadgets, blinding_seed=None):
+    """The flat statement the real prover holds after assign_buffer (/root/reference/src/prove.rs:84-99), built by the
+    library's own front end from the text formats.  Host only."""
+    out = ctypes.POINTER(_capi.FlatStatementC)()
+    check(lib().bpg_frontend_flatten_prover(name.encode(), instance.encode(), witness.encode(), gadgets.encode(),
+                                            blinding_seed, byref(out)))
+    return _take_flat(out, True, name.encode())
+
+
+def flatten_verifier(name, instance, commitments, gadgets):
+    out = ctypes.POINTER(_capi.FlatStatementC)()
+    check(lib().bpg_frontend_flatten_verifier(name.encode(), instance.encode(), commitments.encode(), gadgets.encode(),
+                                              byref(out)))
+    return _take_flat(out, False, name.encode())

@@ -1135,6 +1135,23 @@ int bpg_frontend_flatten_verifier(const char* name, const char* instance, const 
     });
 }
 
+// mimc_hash / the un-padded sponge over scalars (mimc.rs:24-40,61-75): host-only helpers for callers that build
+// statements (hash images, Merkle roots)
+int bpg_mimc_hash(const uint8_t* preimage, size_t len, uint8_t out32[32]) {
+    if (!out32 || (len && !preimage)) return BPG_E_ARG;
+    return guarded([&]() {
+        s_bytes(mimc_hash(Bytes(preimage, preimage + len)), out32);
+        return BPG_OK;
+    });
+}
+int bpg_mimc_sponge(const uint8_t* scalars32n, size_t n, uint8_t out32[32]) {
+    if (!out32 || (n && !scalars32n)) return BPG_E_ARG;
+    std::vector<S> pre;
+    for (size_t i = 0; i < n; i++) pre.push_back(s_from_bits(scalars32n + 32 * i));
+    s_bytes(mimc_sponge(pre), out32);
+    return BPG_OK;
+}
+
 void bpg_flat_statement_free(bpg_flat_statement* f) {
     if (!f) return;
     free(f->v32m);

@@ -27,6 +27,7 @@
 #include "ctx.hpp"
 
 #define REDUCE_BLOCKS 128
+#define FINAL_THREADS 128
 #define REDUCE_THREADS 64
 #define ACC_THREADS 128
 
@@ -63,6 +64,43 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
     const uint32_t point = sg.point_base + i;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
     uint32_t carry = 0;
+    if (K <= 16) {
+        // all digits first, then all atomics back to back (16 independent L2 round trips in flight instead of a
+        // dependent chain), then the scattered stores
+        uint32_t gbv[16], entv[16];
+#pragma unroll
+        for (int w = 0; w < 16; w++) {
+            gbv[w] = 0xffffffffu;
+            entv[w] = 0;
+            if (w < K) {
+                uint32_t raw = (s[0] & mask) + carry;
+#pragma unroll
+                for (int k = 0; k < 7; k++) s[k] = __funnelshift_r(s[k], s[k + 1], c);
+                s[7] >>= c;
+                const uint32_t neg = raw > half;
+                const uint32_t mag = neg ? ((1u << c) - raw) : raw;
+                carry = neg;
+                if (mag != 0) {
+                    gbv[w] = set * nb + (mag - 1);
+                    entv[w] = ((uint32_t)w * n_points + point) | (neg << 31);
+                }
+            }
+        }
+        if (!SCATTER) {
+#pragma unroll
+            for (int w = 0; w < 16; w++)
+                if (gbv[w] != 0xffffffffu) atomicAdd(&hist[gbv[w]], 1u);
+        } else {
+            uint32_t pos[16];
+#pragma unroll
+            for (int w = 0; w < 16; w++)
+                if (gbv[w] != 0xffffffffu) pos[w] = bucket_off[gbv[w]] + atomicAdd(&hist[gbv[w]], 1u);
+#pragma unroll
+            for (int w = 0; w < 16; w++)
+                if (gbv[w] != 0xffffffffu) entries[pos[w]] = entv[w];
+        }
+        return;
+    }
     for (int w = 0; w < K; w++) {
         uint32_t raw = (s[0] & mask) + carry;
 #pragma unroll
@@ -248,12 +286,15 @@ __global__ void __launch_bounds__(REDUCE_THREADS)
     if (threadIdx.x == 0) store_ext(blockres + s * REDUCE_BLOCKS + blockIdx.x, load_ext(sh));
 }
 
-__global__ void __launch_bounds__(REDUCE_BLOCKS) k_reduce_final(const ge_ext* __restrict__ blockres,
-                                                                  ge_ext* __restrict__ result) {
-    __shared__ ge_ext sh[REDUCE_BLOCKS];
+__global__ void __launch_bounds__(FINAL_THREADS) k_reduce_final(const ge_ext* __restrict__ blockres,
+                                                                 ge_ext* __restrict__ result) {
+    __shared__ ge_ext sh[FINAL_THREADS];
     const uint32_t s = blockIdx.x;
     ge_ext mine = load_ext(blockres + s * REDUCE_BLOCKS + threadIdx.x);
-    block_tree_reduce(sh, mine, threadIdx.x, REDUCE_BLOCKS);
+#pragma unroll 1
+    for (uint32_t k = threadIdx.x + FINAL_THREADS; k < REDUCE_BLOCKS; k += FINAL_THREADS)
+        mine = ge_add(mine, load_ext(blockres + s * REDUCE_BLOCKS + k));
+    block_tree_reduce(sh, mine, threadIdx.x, FINAL_THREADS);
     if (threadIdx.x == 0) store_ext(result + s, load_ext(sh));
 }
 
@@ -318,7 +359,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
     }
     k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.slot_bucket.p, w.bucket_off.p, nb, nsets,
                                                                           T, w.blockres.p);
-    k_reduce_final<<<nsets, REDUCE_BLOCKS, 0, st>>>(w.blockres.p, d_out);
+    k_reduce_final<<<nsets, FINAL_THREADS, 0, st>>>(w.blockres.p, d_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     if (ctx->time_accum) {  // diagnostic mode: synchronous, reads back the entry count

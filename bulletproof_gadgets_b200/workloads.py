@@ -100,6 +100,53 @@ def bounds_check_statement(count=1024, max_bytes=8, seed=20261018, label=b"bench
                          np.asarray(tvar, dtype=np.uint32), b"".join(tcoef), n, len(row_start) - 1)
 
 
+def _hex(b):
+    return "0x" + bytes(b).hex()
+
+
+def merkle_text(depth=32, seed=20261018, witness_siblings=False):
+    """BASELINE config 3: `MERKLE I0 (((..(W0 I1) I2)..) I<depth>)` -- membership of leaf W0 under root I0 with MiMC
+    (/root/reference/src/merkle_tree/merkle_tree_gadget.rs:39-114, /root/reference/src/prove.rs:289-321).
+    Leaves are 4..32 random bytes; the root is computed with the library's mimc_hash / sponge.  With
+    witness_siblings the siblings are W1..W<depth> (each hashed in-circuit).  Returns (gadgets, inst, wtns) text."""
+    from . import api
+    rng = np.random.default_rng(seed)
+    leaves = [rng.integers(0, 256, size=int(rng.integers(4, 33)), dtype=np.uint8).tobytes() for _ in range(depth + 1)]
+    leaves = [b if b.strip(b"\0") else b"\x01" + b[1:] for b in leaves]
+    node = api.mimc_hash(leaves[0])
+    for k in range(1, depth + 1):
+        node = api.mimc_sponge([node, api.mimc_hash(leaves[k])])
+    root = node.to_bytes(32, "big")
+    sib = "W" if witness_siblings else "I"
+    tree = "(W0 %s1)" % sib
+    for k in range(2, depth + 1):
+        tree = "(%s %s%d)" % (tree, sib, k)
+    gadgets = "MERKLE I0 " + tree
+    inst = ["I0 = " + _hex(root)]
+    wtns = ["W0 = " + _hex(leaves[0])]
+    for k in range(1, depth + 1):
+        (wtns if witness_siblings else inst).append("%s%d = %s" % (sib, k, _hex(leaves[k])))
+    return gadgets, "\n".join(inst), "\n".join(wtns)
+
+
+def batch_texts(count=4096, seed=4096):
+    """BASELINE config 4: independent proofs, alternating `LESS_THAN W0 W1` (15-byte values, W0 < W1; n = 379) and
+    `SET_MEMBER W0 I0..I15` (member at a random index; n = 32).  Returns a list of (gadgets, inst, wtns)."""
+    out = []
+    for i in range(count):
+        rng = np.random.default_rng(seed + i)
+        if i % 2 == 0:
+            a = int.from_bytes(rng.integers(0, 256, size=15, dtype=np.uint8).tobytes(), "big") >> 1
+            b = a + 1 + (int.from_bytes(rng.integers(0, 256, size=14, dtype=np.uint8).tobytes(), "big"))
+            out.append(("LESS_THAN W0 W1", "", "W0 = 0x%030x\nW1 = 0x%030x" % (a, b)))
+        else:
+            elems = [rng.integers(0, 256, size=15, dtype=np.uint8).tobytes() for _ in range(16)]
+            member = elems[int(rng.integers(0, 16))]
+            inst = "\n".join("I%d = %s" % (k, _hex(e)) for k, e in enumerate(elems))
+            out.append(("SET_MEMBER W0 " + " ".join("I%d" % k for k in range(16)), inst, "W0 = " + _hex(member)))
+    return out
+
+
 def prove_statement(bpg, ctx, st, seed=b"\x07" * 32):
     """Drives one statement through the C ABI prover: returns (proof bytes, commitments)."""
     T = bpg.Transcript(st.label)

@@ -208,6 +208,10 @@ int bpg_frontend_flatten_prover(const char* name, const char* instance, const ch
 int bpg_frontend_flatten_verifier(const char* name, const char* instance, const char* commitments, const char* gadgets,
                                   bpg_flat_statement** out);
 void bpg_flat_statement_free(bpg_flat_statement* f);
+/* mimc_hash(bytes) (big-endian 32-byte image as 32 LE scalar bytes) and the un-padded MiMC sponge over scalars
+ * -- /root/reference/src/mimc_hash/mimc.rs:24-40,61-75.  Host only. */
+int bpg_mimc_hash(const uint8_t* preimage, size_t len, uint8_t out32[32]);
+int bpg_mimc_sponge(const uint8_t* scalars32n, size_t n, uint8_t out32[32]);
 
 #ifdef __cplusplus
 }
