@@ -249,6 +249,21 @@ def main():
     acc_ns, acc_entries = ctx0.get("sum_accum_ns"), ctx0.get("sum_entries")
     ctx0.set("time_accum", 0)
 
+    # second half of the BASELINE metric: raw fixed-base MSM (verifier mega-MSM shape), 2n' = 2^18 points, uniform
+    # scalars resident in HBM; whole MSM (all stages + 128-byte read-back + host ristretto compression)
+    import numpy as np
+    npts = 2 * st.n
+    sc_np = np.random.default_rng(7).integers(0, 256, size=(npts, 32), dtype=np.uint8)
+    sc_np[:, 31] &= 0x0F
+    d_sc = torch.from_numpy(sc_np).to(dev)
+    for _ in range(3):
+        ctx0.msm_gens_dev(d_sc.data_ptr(), st.n, d_sc.data_ptr() + 32 * st.n, st.n)
+    streams[0].synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx0.msm_gens_dev(d_sc.data_ptr(), st.n, d_sc.data_ptr() + 32 * st.n, st.n)
+    msm_s = (time.perf_counter() - t0) / 10
+
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -281,11 +296,14 @@ def main():
         "latency": {"ms_per_step": ms_lat / lat_steps, "steps": lat_steps,
                     "note": "one step at a time on one context; the prover waits on the host for the sequential "
                             "Merlin TranscriptRng stream (2n Keccak-f permutations)"},
+        "msm": {"points": npts, "mpoints_per_s": npts / msm_s / 1e6, "ms": msm_s * 1e3, "scalars": "uniform mod l",
+                "frac_of_imad_peak_whole_msm": 16 * npts * IMAD_PER_MADD / msm_s / (IMAD_WIDE_PEAK_TOPS * 1e12),
+                "note": "one GPU; sweep 2^10..2^22 in profiles/r01_configs_1gpu.jsonl (tools/bench_configs.py)"},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_accumulate (MSM bucket accumulation, mixed Edwards adds)", "bound": "imad",
                      "achieved": achieved, "peak": IMAD_WIDE_PEAK_TOPS, "unit": "T IMAD.WIDE/s",
-                     "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": 659e6,
-                     "traffic_note": "dram bytes read+write per launch from profiles/r01_accumulate_ncu_details.csv "
+                     "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": 719.5e6,
+                     "traffic_note": "dram bytes read+write per launch from profiles/r01_accumulate_ncu_details_v2.csv "
                                      "(IPP-round MSM, 4.19 M entries x 96 B = 403 MB algorithmic gather)",
                      "peak_source": "tools/imad_peak.cu on this pool (profiles/r01_imad_peak.jsonl); IMAD.WIDE.U32 issues at "
                                     "28/clk/SM vs 64 for 32-bit IMAD; not in MEASURED_PEAKS.json",
