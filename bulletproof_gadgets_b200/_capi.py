@@ -58,6 +58,8 @@ PROTOTYPES = {
     "bpg_transcript_free": (None, [c_void_p]),
     "bpg_transcript_append_message": (None, [c_void_p, c_char_p, c_size_t, c_char_p, c_size_t]),
     "bpg_transcript_challenge_bytes": (None, [c_void_p, c_char_p, c_size_t, c_char_p, c_size_t]),
+    "bpg_transcript_rng_fill64": (c_int, [c_void_p, c_char_p, c_size_t, c_char_p, c_size_t, c_char_p, c_size_t]),
+    "bpg_rng_batcher_stat": (c_int64, [c_int]),
     "bpg_prover_new": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "bpg_prover_free": (None, [c_void_p]),
     "bpg_prover_commit": (c_int, [c_void_p, c_char_p, c_char_p, c_char_p, _u32p]),

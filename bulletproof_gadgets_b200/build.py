@@ -52,7 +52,10 @@ def _stamp():
 
 def _compile(src):
     obj = os.path.join(OBJDIR, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+    if src.endswith("_native.cpp"):   # host-only translation units with SIMD intrinsics: straight to g++
+        cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-march=x86-64-v3", "-Wall", "-c", src, "-o", obj]
+    else:
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -286,4 +286,23 @@ void bpg_transcript_challenge_bytes(bpg_transcript* t, const uint8_t* label, siz
     t->t.challenge_bytes(label, label_len, out, out_len);
 }
 
+// TranscriptRngBuilder::{rekey_with_witness_bytes("v_blinding", w)}*.finalize(seed) followed by n x fill_bytes(64):
+// the s_L / s_R stream of Prover::prove (host only; concurrent callers are batched eight streams at a time).
+int bpg_transcript_rng_fill64(const bpg_transcript* t, const uint8_t* witness32k, size_t k, const uint8_t seed32[32],
+                              size_t warm, uint8_t* out64n, size_t n) {
+    if (!t || !seed32 || (k && !witness32k) || (n && !out64n)) return BPG_E_ARG;
+    std::vector<const uint8_t*> wit;
+    for (size_t i = 0; i < k; i++) wit.push_back(witness32k + 32 * i);
+    bpg::TranscriptRng rng = t->t.build_rng(wit, seed32);
+    uint8_t tmp[64];
+    for (size_t i = 0; i < warm; i++) rng.fill_bytes(tmp, 64);  // e.g. the three blinding draws that come first
+    rng.fill_many64(out64n, n);
+    return BPG_OK;
+}
+int64_t bpg_rng_batcher_stat(int which) {
+    uint64_t s[3];
+    bpg::rng_batcher_stats(s);
+    return which >= 0 && which < 3 ? (int64_t)s[which] : -1;
+}
+
 }  // extern "C"

@@ -51,7 +51,12 @@ struct TranscriptRng {
     Strobe128 strobe;
     explicit TranscriptRng(const Strobe128& s) : strobe(s) {}
     void fill_bytes(uint8_t* out, size_t n);
+    // `count` consecutive fill_bytes(64) calls (the s_L / s_R draws of Prover::prove).  Same bytes as the loop;
+    // when several proofs are in flight in this process their streams are run eight at a time (keccak_x8_native.cpp).
+    void fill_many64(uint8_t* out, size_t count);
 };
+// statistics of the stream batcher: [0] streams served, [1] vector batches, [2] streams that ran alone (scalar)
+void rng_batcher_stats(uint64_t out[3]);
 
 struct Transcript {
     Strobe128 strobe;

@@ -339,7 +339,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     // the sequential STROBE stream runs on the host while the two MSMs above execute
     if (n) {
         if ((rc = pw->pin(128 * (size_t)n))) return rc;
-        for (uint32_t i = 0; i < 2 * n; i++) rng.fill_bytes(pw->h_pin + 64 * (size_t)i, 64);
+        rng.fill_many64(pw->h_pin, 2 * (size_t)n);  // 2n x fill_bytes(64); batched across proofs in flight
         CUDA_TRY(cudaMemcpyAsync(pw->wide.p, pw->h_pin, 128 * (size_t)n, cudaMemcpyHostToDevice, st));
         k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p, pw->sL.p, n);
         k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p + 64 * (size_t)n, pw->sR.p, n);

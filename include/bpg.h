@@ -95,6 +95,14 @@ void bpg_transcript_free(bpg_transcript* t);
 void bpg_transcript_append_message(bpg_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
 void bpg_transcript_challenge_bytes(bpg_transcript* t, const uint8_t* label, size_t label_len, uint8_t* out, size_t out_len);
 
+/* merlin TranscriptRng as Prover::prove uses it (bulletproofs r1cs/prover.rs): clone the transcript, rekey with k
+ * 32-byte witnesses under the label "v_blinding", finalize with 32 external bytes, discard `warm` 64-byte draws, then
+ * write n 64-byte draws.  Host only; concurrent callers' streams are run eight at a time (AVX-512). */
+int bpg_transcript_rng_fill64(const bpg_transcript* t, const uint8_t* witness32k, size_t k, const uint8_t seed32[32],
+                              size_t warm, uint8_t* out64n, size_t n);
+/* 0: streams served, 1: vector batches, 2: streams that ran alone */
+int64_t bpg_rng_batcher_stat(int which);
+
 /* ---- R1CS constraint system: prover --------------------------------------------------- */
 /* Variables are uint32 tags: kind<<29 | index, kind = 0 Committed, 1 MultiplierLeft,
  * 2 MultiplierRight, 3 MultiplierOutput, 4 One  (dalek r1cs::Variable). */

@@ -1,0 +1,69 @@
+"""Host logic: the Merlin TranscriptRng stream of Prover::prove (2n x fill_bytes(64)) through the cross-proof
+batcher (AVX-512 Keccak-f x8, csrc/keccak_x8_native.cpp + merlin.cpp) must produce exactly the bytes of the
+oracle's one-stream-at-a-time STROBE, whether a stream runs alone or in a batch of 2..8 with unequal lengths."""
+import ctypes
+import threading
+
+import pytest
+
+import bulletproof_gadgets_b200 as bpg
+from bulletproof_gadgets_b200 import build
+from oracle.pyref.merlin import Transcript as OTranscript
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_lib()
+    return bpg.lib()
+
+
+def oracle_stream(label, witnesses, seed, warm, n):
+    T = OTranscript(label)
+    T.append_message(b"dom-sep", b"r1cs v1")
+    b = T.build_rng()
+    for w in witnesses:
+        b.rekey_with_witness_bytes(b"v_blinding", w)
+    rng = b.finalize(seed)
+    for _ in range(warm):
+        rng.fill_bytes(64)
+    return b"".join(rng.fill_bytes(64) for _ in range(n))
+
+
+def product_stream(lib, label, witnesses, seed, warm, n):
+    T = bpg.Transcript(label)
+    T.append_message(b"dom-sep", b"r1cs v1")
+    out = ctypes.create_string_buffer(64 * max(n, 1))
+    rc = lib.bpg_transcript_rng_fill64(T._h, b"".join(witnesses) or None, len(witnesses), seed, warm, out, n)
+    assert rc == 0
+    return out.raw[: 64 * n]
+
+
+def test_single_stream_matches_oracle(lib):
+    for warm, n in ((3, 200), (0, 70), (1, 1), (3, 0), (3, 63), (3, 64)):
+        wit = [bytes([i + 1]) * 32 for i in range(3)]
+        assert product_stream(lib, b"solo", wit, b"\x05" * 32, warm, n) == oracle_stream(b"solo", wit, b"\x05" * 32, warm, n)
+
+
+@pytest.mark.parametrize("nthreads", [2, 5, 8, 11])
+def test_concurrent_streams_are_batched_and_exact(lib, nthreads):
+    counts = [64 + 37 * i for i in range(nthreads)]          # unequal lengths: streams leave the batch one by one
+    want = [oracle_stream(b"batch-%d" % i, [bytes([i]) * 32], bytes([0x40 + i]) * 32, 3, counts[i]) for i in range(nthreads)]
+    before = lib.bpg_rng_batcher_stat(1)
+    got = [None] * nthreads
+    gate = threading.Barrier(nthreads)
+
+    def work(i):
+        gate.wait()
+        got[i] = product_stream(lib, b"batch-%d" % i, [bytes([i]) * 32], bytes([0x40 + i]) * 32, 3, counts[i])
+
+    for rep in range(3):                                     # arrival-rate estimate warms up over the repetitions
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert got == want
+    import subprocess
+    has512 = "avx512f" in open("/proc/cpuinfo").read()
+    if has512:
+        assert lib.bpg_rng_batcher_stat(1) > before, "no vector batch was formed on an AVX-512 host"
