@@ -2,6 +2,8 @@
 // The R1CS prover/verifier entry points live in r1cs.cu, the statement front end in frontend.cpp.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "ctx.hpp"
 #include "host_sc.hpp"
 #include "merlin.hpp"
@@ -16,10 +18,40 @@ void bpg_set_error(const char* fmt, ...) {
 }
 
 void host_ristretto_compress(uint8_t out[32], const ge_ext& p) { ge_ristretto_compress(out, p); }
+// Few proofs in flight in this process: spin on the event (lowest latency).  Many: sleep in the driver
+// (cudaEventBlockingSync), because dozens of spinning host threads starve the few cores of a multi-GPU host.
+static std::atomic<int> g_waiters{0};
+cudaError_t ctx_sync(bpg_ctx* ctx) {
+    cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+    if (e != cudaSuccess) return e;
+    const int w = ++g_waiters;
+    int polls = 0;
+    for (;;) {
+        e = cudaEventQuery(ctx->ev_sync);
+        if (e != cudaErrorNotReady) break;
+        if (++polls >= 32 && (w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
+            e = cudaEventSynchronize(ctx->ev_sync);
+            break;
+        }
+    }
+    --g_waiters;
+    return e;
+}
+// Small device->host reads go through the context's pinned staging page: a copy into pageable memory would make the
+// driver spin-wait inside cudaMemcpyAsync, and spinning host threads are what starves a multi-GPU host of cores.
+// Layout of the 8 KiB page: [0, 4096) points of fetch_points, [4096, 8192) staged words (d2h_stage).
 int fetch_points(bpg_ctx* ctx, const ge_ext* d_pts, uint32_t n, ge_ext* h_out) {
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_pts, sizeof(ge_ext) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n > 32) return BPG_E_ARG;
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_result, d_pts, sizeof(ge_ext) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx_sync(ctx));
+    if (h_out != ctx->h_result) memcpy(h_out, ctx->h_result, sizeof(ge_ext) * n);
     return BPG_OK;
+}
+void* d2h_stage(bpg_ctx* ctx, size_t offset, const void* d_src, size_t bytes) {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(ctx->h_result) + 4096 + offset;
+    if (offset + bytes > 4096 || cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        return nullptr;
+    return dst;
 }
 bool host_is_ristretto_identity(const ge_ext& p) { return ge_is_ristretto_identity(p); }
 
@@ -34,6 +66,7 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ctx->ev_a));
     CUDA_TRY(cudaEventCreate(&ctx->ev_b));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
     *out = ctx;
     return BPG_OK;
@@ -84,7 +117,7 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
 void bpg_ctx_destroy(bpg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    ctx_sync(ctx);
     MsmWork& w = ctx->work;
     w.hist.release();
     w.bucket_off.release();
@@ -101,6 +134,7 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
+    cudaEventDestroy(ctx->ev_sync);
     cudaStreamDestroy(ctx->stream);
     gens_store_release(ctx->store);
     delete ctx;
@@ -295,6 +329,7 @@ int bpg_transcript_rng_fill64(const bpg_transcript* t, const uint8_t* witness32k
     for (size_t i = 0; i < k; i++) wit.push_back(witness32k + 32 * i);
     bpg::TranscriptRng rng = t->t.build_rng(wit, seed32);
     uint8_t tmp[64];
+    bpg::ProvingScope in_flight;
     for (size_t i = 0; i < warm; i++) rng.fill_bytes(tmp, 64);  // e.g. the three blinding draws that come first
     rng.fill_many64(out64n, n);
     return BPG_OK;

@@ -174,9 +174,9 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
         k_csc_long<<<(nt + 255) / 256, 256, 0, st>>>(c->d_col_start, nt, long_cap, c->d_long, d_flags + 1);
         ctx->launches += 2;
     }
-    uint32_t flags[2] = {0, 0};
-    TRY_CU(cudaMemcpyAsync(flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
-    TRY_CU(cudaStreamSynchronize(st));
+    const uint32_t* flags = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_flags, 8));
+    if (!flags) return fail(BPG_E_CUDA);
+    TRY_CU(ctx_sync(ctx));
     TRY_CU(cudaGetLastError());
     if (flags[0] & 1u) {
         bpg_set_error("constraint term references an unknown variable (n=%u, m=%u)", n, m);
@@ -214,9 +214,10 @@ int circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR3
         CUDA_TRY(cudaMemcpyAsync(c->d_aR, aR32n, 32 * n, cudaMemcpyHostToDevice, st));
         k_witness<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(c->d_aL, c->d_aR, c->d_aO, (uint32_t)n, d_err);
         ctx->launches++;
-        uint32_t err = 0;
-        CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint32_t* errp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_err, 4));
+        if (!errp) return BPG_E_CUDA;
+        CUDA_TRY(ctx_sync(ctx));
+        const uint32_t err = *errp;
         dfree(ctx, true, d_err);
         if (err) {
             bpg_set_error("multiplier assignment with bit 255 set (not a valid Scalar)");

@@ -118,6 +118,7 @@ struct bpg_ctx {
     uint64_t launches = 0;
     // timing of the dominant kernel (accumulate), CUDA events on ctx stream
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_sync = nullptr;  // blocking-sync event behind ctx_sync()
     float last_accum_ms = 0.f;
     uint64_t last_entries = 0;
     double sum_accum_ms = 0;  // accumulated over all MSMs since the last reset (time_accum mode)
@@ -125,11 +126,17 @@ struct bpg_ctx {
     bool time_accum = false;
 };
 
+// Waits for ctx->stream: a short poll (single proofs keep their latency) and then a BLOCKING wait, so that the many
+// host threads of a throughput run sleep instead of spinning on the few cores of a multi-GPU host.
+cudaError_t ctx_sync(bpg_ctx* ctx);
+
 // msm.cu
 // asynchronous on ctx->stream; writes nsets extended points to the DEVICE array d_out
 int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out);
-// copies n extended points from device to host and waits for the stream
+// copies n <= 32 extended points from device to host (through pinned staging) and waits for the stream
 int fetch_points(bpg_ctx* ctx, const ge_ext* d_pts, uint32_t n, ge_ext* h_out);
+// queues a small device->host copy into the pinned staging page (offset + bytes <= 4096); valid after ctx_sync()
+void* d2h_stage(bpg_ctx* ctx, size_t offset, const void* d_src, size_t bytes);
 // r1cs.cu
 void r1cs_release_work(bpg_ctx* ctx);
 // gens.cu

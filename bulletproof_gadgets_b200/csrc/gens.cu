@@ -137,7 +137,7 @@ int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     pk_pedersen_table(st, d_ext, (uint32_t)(2 * cap), d_ped);
     ctx->launches += 5;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(ctx_sync(ctx));
     cudaFree(d_uni);
     cudaFree(d_bp);
     cudaFree(d_fail);
@@ -190,7 +190,7 @@ int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count,
     k_compress<<<(uint32_t)((count + 127) / 128), 128, 0, ctx->stream>>>(ctx->gens_ext + base, d_out, (uint32_t)count);
     ctx->launches++;
     CUDA_TRY(cudaMemcpyAsync(out, d_out, 32 * count, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx_sync(ctx));
     cudaFree(d_out);
     return BPG_OK;
 }

@@ -363,7 +363,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     if (ctx->time_accum) {  // diagnostic mode: synchronous, reads back the entry count
-        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(ctx_sync(ctx));
         CUDA_TRY(cudaEventElapsedTime(&ctx->last_accum_ms, ctx->ev_a, ctx->ev_b));
         uint32_t ne = 0;
         CUDA_TRY(cudaMemcpy(&ne, w.bucket_off.p + G, 4, cudaMemcpyDeviceToHost));

@@ -154,7 +154,7 @@ struct Trace {
     void mark(const char* what) {
         if (!on) return;
         double a = now();
-        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(st);  // trace mode only
         double b = now();
         fprintf(stderr, "[bpg trace] %-28s host %8.3f ms  +gpu-drain %8.3f ms  (t=%.3f)\n", what, a - last, b - a, b - t0);
         last = b;
@@ -242,8 +242,10 @@ static int pedersen_batch(bpg_ctx* ctx, const sc* v, const sc* r, uint64_t k, ui
     } else {
         pk_compress(st, pw->dyn_pts.p, pw->dyn_enc.p, (uint32_t)k);
         ctx->launches++;
-        CUDA_TRY(cudaMemcpyAsync(out32k, pw->dyn_enc.p, 32 * k, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = pw->pin(32 * k))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(pw->h_pin, pw->dyn_enc.p, 32 * k, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx_sync(ctx));
+        memcpy(out32k, pw->h_pin, 32 * k);
     }
     return BPG_OK;
 }
@@ -290,6 +292,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     while ((1u << lg) < npad) lg++;
 
     Trace trace(st);
+    bpg::ProvingScope in_flight;
     T.append_u64("m", m);
     uint8_t seed[32];
     if (seed32) memcpy(seed, seed32, 32); else os_random(seed);
@@ -386,9 +389,9 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     sk_dot(st, wV, pw->vbl.p, m, small + 16);
     ctx->launches += 7;
     trace.mark("powers+flatten+lr_poly");
-    sc th[9];
-    CUDA_TRY(cudaMemcpyAsync(th, small + 8, 9 * 32, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const sc* th = static_cast<const sc*>(d2h_stage(ctx, 0, small + 8, 9 * 32));
+    if (!th) return BPG_E_CUDA;
+    CUDA_TRY(ctx_sync(ctx));
     const Scalar t1 = Scalar::from_sc(th[0]), t2 = Scalar::from_sc(th[1]), t3 = Scalar::from_sc(th[2]),
                  t4 = Scalar::from_sc(th[3]), t5 = Scalar::from_sc(th[4]), t6 = Scalar::from_sc(th[5]);
     const Scalar tb2 = Scalar::from_sc(th[8]);
@@ -449,10 +452,11 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         ctx->launches++;
     }
     trace.mark("ipp rounds");
-    sc ab[2];
-    CUDA_TRY(cudaMemcpyAsync(&ab[0], pw->lvec.p, 32, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(&ab[1], pw->rvec.p, 32, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const sc* ab0 = static_cast<const sc*>(d2h_stage(ctx, 0, pw->lvec.p, 32));
+    const sc* ab1 = static_cast<const sc*>(d2h_stage(ctx, 32, pw->rvec.p, 32));
+    if (!ab0 || !ab1) return BPG_E_CUDA;
+    CUDA_TRY(ctx_sync(ctx));
+    const sc ab[2] = {*ab0, *ab1};
     CUDA_TRY(cudaGetLastError());
 
     trace.mark("final a,b");
@@ -713,12 +717,12 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     pk_add2(st, slots + 8, slots + 9, slots + 10);
     ctx->launches++;
     trace.mark("v: fixed msm");
-    uint32_t fail = 0;
+    const uint32_t* failp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, pw->fail.p, 4));
     ge_ext res;
-    CUDA_TRY(cudaMemcpyAsync(&fail, pw->fail.p, 4, cudaMemcpyDeviceToHost, st));
+    if (!failp) return BPG_E_CUDA;
     if ((rc = fetch_points(ctx, slots + 10, 1, &res))) return rc;
     CUDA_TRY(cudaGetLastError());
-    if (fail) return BPG_E_VERIFY;  // a point did not decode
+    if (*failp) return BPG_E_VERIFY;  // a point did not decode
     return host_is_ristretto_identity(res) ? BPG_OK : BPG_E_VERIFY;
 }
 
@@ -779,10 +783,11 @@ int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars32n, const uint8_t* points32n, u
     pk_decompress(st, pw->dyn_enc.p, pw->dyn_pts.p, (uint32_t)n, pw->fail.p);
     pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, (uint32_t)n, pw->dyn_blk.p, ctx->d_points.p + 12);
     ctx->launches += 3;
-    uint32_t fail = 0;
+    const uint32_t* failp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, pw->fail.p, 4));
     ge_ext res;
-    CUDA_TRY(cudaMemcpyAsync(&fail, pw->fail.p, 4, cudaMemcpyDeviceToHost, st));
+    if (!failp) return BPG_E_CUDA;
     if ((rc = fetch_points(ctx, ctx->d_points.p + 12, 1, &res))) return rc;
+    const uint32_t fail = *failp;
     if (fail) {
         bpg_set_error("msm: %u point(s) failed to decompress", fail);
         return BPG_E_VERIFY;

@@ -44,20 +44,44 @@ def test_single_stream_matches_oracle(lib):
         assert product_stream(lib, b"solo", wit, b"\x05" * 32, warm, n) == oracle_stream(b"solo", wit, b"\x05" * 32, warm, n)
 
 
+def test_x8_kernel_on_short_unequal_streams(lib):
+    """Concurrent short streams of unequal length (the kernel hands each state back when its stream ends):
+    whatever batches happen to form, the bytes equal the oracle's."""
+    n = 8
+    counts = [64 + 37 * i for i in range(n)]
+    want = [oracle_stream(b"short-%d" % i, [bytes([i]) * 32], bytes([0x40 + i]) * 32, 3, counts[i]) for i in range(n)]
+    got = [None] * n
+
+    def work(i):
+        got[i] = product_stream(lib, b"short-%d" % i, [bytes([i]) * 32], bytes([0x40 + i]) * 32, 3, counts[i])
+
+    for rep in range(10):
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert got == want
+
+
 @pytest.mark.parametrize("nthreads", [2, 5, 8, 11])
-def test_concurrent_streams_are_batched_and_exact(lib, nthreads):
-    counts = [64 + 37 * i for i in range(nthreads)]          # unequal lengths: streams leave the batch one by one
-    want = [oracle_stream(b"batch-%d" % i, [bytes([i]) * 32], bytes([0x40 + i]) * 32, 3, counts[i]) for i in range(nthreads)]
+def test_concurrent_long_streams_are_batched_and_exact(lib, nthreads):
+    """Long streams (a proof's worth of draws overlaps in time): sequential calls take the one-stream path (checked
+    against the oracle on its first draws), concurrent calls must form vector batches and return the same bytes."""
+    counts = [20000 + 1500 * i for i in range(nthreads)]
+    args = [(b"long-%d" % i, [bytes([i]) * 32, bytes([i + 1]) * 32], bytes([0x60 + i]) * 32, 3, counts[i]) for i in range(nthreads)]
+    want = [product_stream(lib, *a) for a in args]                       # one at a time: scalar path
+    assert want[0][: 64 * 40] == oracle_stream(*args[0][:4], 40)
     before = lib.bpg_rng_batcher_stat(1)
     got = [None] * nthreads
     gate = threading.Barrier(nthreads)
 
     def work(i):
         gate.wait()
-        got[i] = product_stream(lib, b"batch-%d" % i, [bytes([i]) * 32], bytes([0x40 + i]) * 32, 3, counts[i])
+        got[i] = product_stream(lib, *args[i])
 
     formed = False
-    for rep in range(40):                                    # the arrival-rate window (16 requests) has to fill up first
+    for rep in range(12):
         ts = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
         for t in ts:
             t.start()
@@ -65,7 +89,7 @@ def test_concurrent_streams_are_batched_and_exact(lib, nthreads):
             t.join()
         assert got == want
         formed = lib.bpg_rng_batcher_stat(1) > before
-        if formed and rep >= 2:
+        if formed and rep >= 1:
             break
-    if "avx512f" in open("/proc/cpuinfo").read():
+    if nthreads >= 5 and "avx512f" in open("/proc/cpuinfo").read():      # pairs may legitimately run alone (low-latency policy)
         assert formed, "no vector batch was formed on an AVX-512 host"
