@@ -150,7 +150,7 @@ def main():
     from bulletproof_gadgets_b200 import build, workloads as W
     build.build_lib()
     warmup = max(args.warmup, 3)
-    inflight = args.inflight or 24   # host threads mostly block (GPU waits, rng batcher): not tied to the core count
+    inflight = args.inflight or 32   # host threads mostly block (GPU waits, rng batcher): not tied to the core count
     ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
     ctxs = [ctx0] + [ctx0.shared() for _ in range(inflight - 1)]
     st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank).pin(bpg)
@@ -236,9 +236,14 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = sum(c.get("launches") for c in ctxs)
+    stat0 = [bpg.lib().bpg_rng_batcher_stat(k) for k in range(3)]
+    cpu0 = time.process_time()
     ms_res = timed(step_resident, args.steps, warmup, ctxs)
+    cpu_res = time.process_time() - cpu0
     launches = sum(c.get("launches") for c in ctxs) - launches0
     ms_e2e = timed(step_e2e, args.steps, warmup, ctxs)
+    stat1 = [bpg.lib().bpg_rng_batcher_stat(k) for k in range(3)]
+    cpu_parts = {k: sum(c.get("cpu_%s_ns" % k) for c in ctxs) * 1e-9 for k in ("sync", "commit", "prove", "verify", "rng")}
     lat_steps = max(3, min(10, args.steps))
     ms_lat = timed(step_resident, lat_steps, warmup, ctxs[:1])
     sampler.stop_flag = True
@@ -300,6 +305,12 @@ def main():
                 "frac_of_imad_peak_whole_msm": 16 * npts * IMAD_PER_MADD / msm_s / (IMAD_WIDE_PEAK_TOPS * 1e12),
                 "note": "one GPU; sweep 2^10..2^22 in profiles/r01_configs_1gpu.jsonl (tools/bench_configs.py)"},
         "gpu_launches": launches,
+        "host": {"cores": os.cpu_count(), "cpu_s_per_step_rank0": cpu_res / (args.steps + max(warmup, inflight)),
+                 "rng_streams": stat1[0] - stat0[0], "rng_vector_batches": stat1[1] - stat0[1],
+                 "rng_streams_alone": stat1[2] - stat0[2],
+                 "thread_cpu_s_total_all_legs": cpu_parts,
+                 "note": "process CPU time of rank 0 over the resident leg (incl. its warm-up steps); the Merlin rng "
+                         "streams of proofs in flight run eight at a time (AVX-512) when batches form"},
         "roofline": {"kernel": "k_accumulate (MSM bucket accumulation, mixed Edwards adds)", "bound": "imad",
                      "achieved": achieved, "peak": IMAD_WIDE_PEAK_TOPS, "unit": "T IMAD.WIDE/s",
                      "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": 719.5e6,

@@ -1,6 +1,9 @@
 // extern "C" surface of libbpg.so: context, generators, MSM and transcript entry points.
 // The R1CS prover/verifier entry points live in r1cs.cu, the statement front end in frontend.cpp.
+#include <sched.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -21,15 +24,31 @@ void host_ristretto_compress(uint8_t out[32], const ge_ext& p) { ge_ristretto_co
 // Few proofs in flight in this process: spin on the event (lowest latency).  Many: sleep in the driver
 // (cudaEventBlockingSync), because dozens of spinning host threads starve the few cores of a multi-GPU host.
 static std::atomic<int> g_waiters{0};
+static int sync_mode() {  // BPG_SYNC = spin | yield | block | auto (default)
+    static const int mode = [] {
+        const char* e = getenv("BPG_SYNC");
+        if (!e) return 0;
+        return !strcmp(e, "spin") ? 1 : !strcmp(e, "yield") ? 2 : !strcmp(e, "block") ? 3 : 0;
+    }();
+    return mode;
+}
 cudaError_t ctx_sync(bpg_ctx* ctx) {
+    CpuTimer cpu(&ctx->cpu_sync_ns);
     cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
     if (e != cudaSuccess) return e;
+    const int mode = sync_mode();
     const int w = ++g_waiters;
     int polls = 0;
     for (;;) {
         e = cudaEventQuery(ctx->ev_sync);
         if (e != cudaErrorNotReady) break;
-        if (++polls >= 32 && (w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
+        ++polls;
+        if (mode == 1) continue;
+        if (mode == 2) {
+            if (polls >= 8) sched_yield();
+            continue;
+        }
+        if (polls >= 32 && (mode == 3 || w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
             e = cudaEventSynchronize(ctx->ev_sync);
             break;
         }
@@ -187,6 +206,12 @@ int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key) {
     if (k == "accum_entries") return (int64_t)ctx->last_entries;
     if (k == "sum_accum_ns") return (int64_t)(ctx->sum_accum_ms * 1e6);
     if (k == "sum_entries") return (int64_t)ctx->sum_entries;
+    if (k == "cpu_sync_ns") return (int64_t)ctx->cpu_sync_ns;
+    if (k == "cpu_commit_ns") return (int64_t)ctx->cpu_commit_ns;
+    if (k == "cpu_prove_ns") return (int64_t)ctx->cpu_prove_ns;
+    if (k == "cpu_verify_ns") return (int64_t)ctx->cpu_verify_ns;
+    if (k == "cpu_load_ns") return (int64_t)ctx->cpu_load_ns;
+    if (k == "cpu_rng_ns") return (int64_t)ctx->cpu_rng_ns;
     if (k == "capacity") return (int64_t)ctx->table.capacity;
     if (k == "window_bits") return ctx->table.c;
     if (k == "windows") return ctx->table.K;

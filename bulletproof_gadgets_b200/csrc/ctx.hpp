@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <time.h>
 
 #include <mutex>
 #include <string>
@@ -124,6 +125,19 @@ struct bpg_ctx {
     double sum_accum_ms = 0;  // accumulated over all MSMs since the last reset (time_accum mode)
     uint64_t sum_entries = 0;
     bool time_accum = false;
+    // host CPU accounting (thread CPU time, ns): inside ctx_sync, and inside the C-ABI calls commit / prove / verify / load
+    uint64_t cpu_sync_ns = 0, cpu_commit_ns = 0, cpu_prove_ns = 0, cpu_verify_ns = 0, cpu_load_ns = 0, cpu_rng_ns = 0;
+};
+struct CpuTimer {  // adds the calling thread's CPU time between construction and destruction to *acc
+    uint64_t* acc;
+    uint64_t t0;
+    static uint64_t now() {
+        timespec ts;
+        clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+        return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+    }
+    explicit CpuTimer(uint64_t* a) : acc(a), t0(now()) {}
+    ~CpuTimer() { *acc += now() - t0; }
 };
 
 // Waits for ctx->stream: a short poll (single proofs keep their latency) and then a BLOCKING wait, so that the many

@@ -342,7 +342,10 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     // the sequential STROBE stream runs on the host while the two MSMs above execute
     if (n) {
         if ((rc = pw->pin(128 * (size_t)n))) return rc;
-        rng.fill_many64(pw->h_pin, 2 * (size_t)n);  // 2n x fill_bytes(64); batched across proofs in flight
+        {
+            CpuTimer cpu_rng(&ctx->cpu_rng_ns);
+            rng.fill_many64(pw->h_pin, 2 * (size_t)n);  // 2n x fill_bytes(64); batched across proofs in flight
+        }
         CUDA_TRY(cudaMemcpyAsync(pw->wide.p, pw->h_pin, 128 * (size_t)n, cudaMemcpyHostToDevice, st));
         k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p, pw->sL.p, n);
         k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p + 64 * (size_t)n, pw->sR.p, n);
@@ -814,6 +817,7 @@ void bpg_prover_free(bpg_prover* p) {
 int bpg_prover_commit_batch(bpg_prover* p, const uint8_t* v32k, const uint8_t* vb32k, uint64_t k, uint8_t* V_out32k,
                             uint32_t* first_var_out) {
     if (!p || (k && (!v32k || !vb32k || !V_out32k))) return BPG_E_ARG;
+    CpuTimer cpu(&p->ctx->cpu_commit_ns);
     CUDA_TRY(cudaSetDevice(p->ctx->device));
     std::vector<sc> v(k), r(k);
     for (uint64_t i = 0; i < k; i++) {
@@ -926,6 +930,7 @@ uint64_t bpg_prover_num_multipliers(const bpg_prover* p) { return !p ? 0 : p->ci
 
 int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     if (!p || !proof_out || !proof_len) return BPG_E_ARG;
+    CpuTimer cpu(&p->ctx->cpu_prove_ns);
     CUDA_TRY(cudaSetDevice(p->ctx->device));
     std::vector<uint8_t> proof;
     int rc = prover_prove(p, rng_seed32, &proof);
@@ -1032,6 +1037,7 @@ int bpg_verifier_load_cs(bpg_verifier* v, uint64_t n, const uint32_t* row_start,
 uint64_t bpg_verifier_num_vars(const bpg_verifier* v) { return !v ? 0 : v->circ ? v->circ->n : v->num_vars; }
 int bpg_verifier_verify(bpg_verifier* v, const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32) {
     if (!v || !proof) return BPG_E_ARG;
+    CpuTimer cpu(&v->ctx->cpu_verify_ns);
     CUDA_TRY(cudaSetDevice(v->ctx->device));
     return verifier_verify(v, proof, proof_len, rng_seed32);
 }
