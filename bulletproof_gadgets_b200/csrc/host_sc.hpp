@@ -29,7 +29,7 @@ struct Scalar {
     // canonical representative of a 256-bit value
     static Scalar from_bytes_mod_order(const uint8_t b[32]) {
         Scalar r = from_bytes_raw(b);
-        r.s = sc_reduce(r.s);
+        if (!r.is_canonical()) r.s = sc_reduce(r.s);  // almost every input already is: skip the two Montgomery products
         return r;
     }
     // Scalar::from_bytes_mod_order_wide

@@ -18,7 +18,7 @@ void sk_powers(cudaStream_t st, sc* out, const PowTable& tbl, uint32_t n, uint32
 #define FLATTEN_LONG 128u  // columns with more terms than this get a whole CTA
 void sk_flatten(cudaStream_t st, const uint32_t* col_start, const uint32_t* col_row, const sc* col_coef,
                 const sc* zpow, sc* out, uint32_t nt, uint32_t neg_from, const uint32_t* long_targets,
-                uint32_t n_long);
+                uint32_t n_long, sc* part /* [n_long * 64] */, uint32_t* tickets /* [n_long], zero */);
 void sk_lr_poly(cudaStream_t st, const sc* aL, const sc* aR, const sc* aO, const sc* sL, const sc* sR, const sc* wL,
                 const sc* wR, const sc* wO, const sc* ypow, const sc* yinv, sc* l1, sc* r0, sc* r1, sc* r3,
                 sc* partial, sc* t_out, uint32_t n);

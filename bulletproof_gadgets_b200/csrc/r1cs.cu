@@ -36,7 +36,8 @@ static inline uint32_t var_idx(uint32_t v) { return v & ((1u << 29) - 1); }
 struct ProofWork {
     DevBuf<sc> aL, aR, aO, sL, sR, w, ypow, yinv, zpow, l1, r0, r1, r3, lvec, rvec, sG, sH, mG, mH, partial, small;
     DevBuf<sc> vbl, col_coef, dyn_s, ped_in;
-    DevBuf<uint32_t> col_start, col_row, fail, long_t;
+    DevBuf<uint32_t> col_start, col_row, fail, long_t, fl_tickets;
+    DevBuf<sc> fl_part;
     DevBuf<uint8_t> wide, dyn_enc;
     DevBuf<ge_ext> dyn_pts, dyn_blk;
     uint8_t* h_pin = nullptr;  // pinned staging
@@ -62,6 +63,8 @@ void r1cs_release_work(bpg_ctx* ctx) {
     p->col_row.release();
     p->fail.release();
     p->long_t.release();
+    p->fl_tickets.release();
+    p->fl_part.release();
     p->wide.release();
     p->dyn_enc.release();
     p->dyn_pts.release();
@@ -386,7 +389,10 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     sc* wR = wL + n;
     sc* wO = wR + n;
     sc* wV = wO + n;
-    sk_flatten(st, csc.col_start, csc.col_row, csc.col_coef, pw->zpow.p, pw->w.p, csc.nt - 1, 3 * n, csc.long_targets, csc.n_long);
+    if ((rc = pw->fl_part.ensure(64 * (size_t)csc.n_long + 1)) || (rc = pw->fl_tickets.ensure(csc.n_long + 1))) return rc;
+    CUDA_TRY(cudaMemsetAsync(pw->fl_tickets.p, 0, 4 * (size_t)(csc.n_long + 1), st));
+    sk_flatten(st, csc.col_start, csc.col_row, csc.col_coef, pw->zpow.p, pw->w.p, csc.nt - 1, 3 * n, csc.long_targets, csc.n_long,
+               pw->fl_part.p, pw->fl_tickets.p);
     sk_lr_poly(st, d_aL, d_aR, d_aO, pw->sL.p, pw->sR.p, wL, wR, wO, pw->ypow.p, pw->yinv.p, pw->l1.p,
                pw->r0.p, pw->r1.p, pw->r3.p, pw->partial.p, small + 8, n);
     sk_dot(st, wV, pw->vbl.p, m, small + 16);
@@ -656,7 +662,10 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     sc* wO = wR + n;
     sc* wV = wO + n;
     sc* wc = wV + m;
-    sk_flatten(st, csc.col_start, csc.col_row, csc.col_coef, pw->zpow.p, pw->w.p, csc.nt, 3 * n, csc.long_targets, csc.n_long);
+    if ((rc = pw->fl_part.ensure(64 * (size_t)csc.n_long + 1)) || (rc = pw->fl_tickets.ensure(csc.n_long + 1))) return rc;
+    CUDA_TRY(cudaMemsetAsync(pw->fl_tickets.p, 0, 4 * (size_t)(csc.n_long + 1), st));
+    sk_flatten(st, csc.col_start, csc.col_row, csc.col_coef, pw->zpow.p, pw->w.p, csc.nt, 3 * n, csc.long_targets, csc.n_long,
+               pw->fl_part.p, pw->fl_tickets.p);
     trace.mark("v: csc+powers+flatten");
     VerChallenges ch;
     memset(&ch, 0, sizeof ch);

@@ -38,11 +38,14 @@ __device__ sc block_sum(sc v, sc* sh /*[SK_THREADS]*/) {
     return r;
 }
 
-// out[i] = base^(start + i)
-__global__ void __launch_bounds__(SK_THREADS) k_powers(sc* out, PowTable tbl, uint32_t n, uint32_t start) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t e = start + i;
+// out[i] = base^(start + i).  Thread t computes base^(start + t) from the table of base^(2^k) (<= popcount muls) and then
+// walks out[t + j*T] = out[t + (j-1)*T] * base^T with T = 2^lgT threads: coalesced stores, ~3 multiplications per output
+// instead of one square-and-multiply ladder per output.
+__global__ void __launch_bounds__(SK_THREADS) k_powers(sc* out, PowTable tbl, uint32_t n, uint32_t start, uint32_t lgT) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t T = 1u << lgT;
+    if (t >= T || t >= n) return;
+    uint32_t e = start + t;
     sc acc = sc_one();
     bool first = true;
     for (int k = 0; k < 32 && (e >> k); k++) {
@@ -51,7 +54,11 @@ __global__ void __launch_bounds__(SK_THREADS) k_powers(sc* out, PowTable tbl, ui
             first = false;
         }
     }
-    st_sc(out + i, acc);
+    const sc step = tbl.p[lgT];
+    for (uint32_t i = t; i < n; i += T) {
+        st_sc(out + i, acc);
+        if (i + T < n) acc = sc_mul(acc, step);
+    }
 }
 
 __global__ void __launch_bounds__(SK_THREADS) k_flatten(const uint32_t* __restrict__ col_start,
@@ -68,25 +75,51 @@ __global__ void __launch_bounds__(SK_THREADS) k_flatten(const uint32_t* __restri
     st_sc(out + t, acc);
 }
 
-// columns with more than FLATTEN_LONG terms (e.g. the `One` column of a range-proof circuit: one term per bit)
-__global__ void __launch_bounds__(1024) k_flatten_long(const uint32_t* __restrict__ col_start,
-                                                       const uint32_t* __restrict__ col_row,
-                                                       const sc* __restrict__ col_coef, const sc* __restrict__ zpow,
-                                                       sc* __restrict__ out, const uint32_t* __restrict__ long_targets,
-                                                       uint32_t nt, uint32_t neg_from) {
-    __shared__ sc sh[1024];
-    const uint32_t t = long_targets[blockIdx.x];
+// Columns with more than FLATTEN_LONG terms (e.g. the `One` column of a range-proof circuit: one term per bit).
+// Each long column is split over FL_SPLIT CTAs; the last CTA to finish (ticket counter) adds the partial sums.
+#define FL_SPLIT 64
+#define FL_THREADS 256
+__global__ void __launch_bounds__(FL_THREADS) k_flatten_long(const uint32_t* __restrict__ col_start,
+                                                            const uint32_t* __restrict__ col_row,
+                                                            const sc* __restrict__ col_coef, const sc* __restrict__ zpow,
+                                                            sc* __restrict__ out, const uint32_t* __restrict__ long_targets,
+                                                            uint32_t nt, uint32_t neg_from, sc* __restrict__ part,
+                                                            uint32_t* __restrict__ tickets) {
+    __shared__ sc sh[FL_THREADS];
+    __shared__ bool last;
+    const uint32_t j = blockIdx.x, sidx = blockIdx.y;
+    const uint32_t t = long_targets[j];
     if (t >= nt) return;  // (uniform per block)
     const uint32_t e0 = col_start[t], e1 = col_start[t + 1], tid = threadIdx.x;
+    const uint32_t len = e1 - e0, per = (len + FL_SPLIT - 1) / FL_SPLIT;
+    const uint32_t a = e0 + sidx * per, b = min(a + per, e1);
     sc acc = sc_zero();
-    for (uint32_t e = e0 + tid; e < e1; e += 1024) acc = sc_add(acc, sc_mul(ld_sc(col_coef + e), ld_sc(zpow + col_row[e])));
+    for (uint32_t e = a + tid; e < b; e += FL_THREADS) acc = sc_add(acc, sc_mul(ld_sc(col_coef + e), ld_sc(zpow + col_row[e])));
     sh[tid] = acc;
     __syncthreads();
-    for (uint32_t s = 512; s > 0; s >>= 1) {
+    for (uint32_t s = FL_THREADS / 2; s > 0; s >>= 1) {
         if (tid < s) sh[tid] = sc_add(sh[tid], sh[tid + s]);
         __syncthreads();
     }
-    if (tid == 0) st_sc(out + t, t >= neg_from ? sc_neg(sh[0]) : sh[0]);
+    if (tid == 0) {
+        st_sc(part + j * FL_SPLIT + sidx, sh[0]);
+        __threadfence();
+        last = atomicAdd(&tickets[j], 1u) == FL_SPLIT - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    sc v = tid < FL_SPLIT ? ld_sc(part + j * FL_SPLIT + tid) : sc_zero();
+    sh[tid] = v;
+    __syncthreads();
+    for (uint32_t s = FL_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] = sc_add(sh[tid], sh[tid + s]);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        st_sc(out + t, t >= neg_from ? sc_neg(sh[0]) : sh[0]);
+        tickets[j] = 0;  // ready for the next launch
+    }
 }
 
 // l1 = aL + yinv^i wR ; r0 = wO - y^i ; r1 = y^i aR + wL ; r3 = y^i sR   (l2 = aO, l3 = sL)
@@ -265,14 +298,20 @@ static inline uint32_t nblk(uint64_t n) { return (uint32_t)((n + SK_THREADS - 1)
 #define SK_REDUCE_BLOCKS 296
 
 void sk_powers(cudaStream_t st, sc* out, const PowTable& tbl, uint32_t n, uint32_t start) {
-    if (n) k_powers<<<nblk(n), SK_THREADS, 0, st>>>(out, tbl, n, start);
+    if (!n) return;
+    uint32_t lgT = 0;
+    while ((1u << lgT) < n && lgT < 31) lgT++;      // T >= n: one output per thread ...
+    if (lgT > 14) lgT = lgT >= 17 ? lgT - 3 : 14;   // ... until there are enough threads: then 8 outputs (or more) each
+    const uint32_t T = 1u << lgT;
+    k_powers<<<nblk(T < n ? T : n), SK_THREADS, 0, st>>>(out, tbl, n, start, lgT);
 }
 void sk_flatten(cudaStream_t st, const uint32_t* col_start, const uint32_t* col_row, const sc* col_coef,
                 const sc* zpow, sc* out, uint32_t nt, uint32_t neg_from, const uint32_t* long_targets,
-                uint32_t n_long) {
+                uint32_t n_long, sc* part, uint32_t* tickets) {
     if (nt) k_flatten<<<nblk(nt), SK_THREADS, 0, st>>>(col_start, col_row, col_coef, zpow, out, nt, neg_from);
     if (nt && n_long)
-        k_flatten_long<<<n_long, 1024, 0, st>>>(col_start, col_row, col_coef, zpow, out, long_targets, nt, neg_from);
+        k_flatten_long<<<dim3(n_long, FL_SPLIT), FL_THREADS, 0, st>>>(col_start, col_row, col_coef, zpow, out, long_targets, nt,
+                                                                     neg_from, part, tickets);
 }
 void sk_lr_poly(cudaStream_t st, const sc* aL, const sc* aR, const sc* aO, const sc* sL, const sc* sR, const sc* wL,
                 const sc* wR, const sc* wO, const sc* ypow, const sc* yinv, sc* l1, sc* r0, sc* r1, sc* r3,
