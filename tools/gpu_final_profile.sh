@@ -10,3 +10,4 @@ ncu --set full --clock-control none --import-source on -k regex:k_accumulate --l
 ncu -i gpurun_out/f_accumulate.ncu-rep --page details --csv > gpurun_out/f_accumulate_details.csv 2>/dev/null
 ncu -i gpurun_out/f_accumulate.ncu-rep --page raw --csv > gpurun_out/f_accumulate_raw.csv 2>/dev/null
 cat gpurun_out/f_bench.json | cut -c1-600; cat gpurun_out/f_bench_ref.json | cut -c1-400
+python __graft_entry__.py smoke > gpurun_out/f_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/f_smoke.log
