@@ -355,6 +355,7 @@ int bpg_transcript_rng_fill64(const bpg_transcript* t, const uint8_t* witness32k
     bpg::TranscriptRng rng = t->t.build_rng(wit, seed32);
     uint8_t tmp[64];
     bpg::ProvingScope in_flight;
+    in_flight.enter();
     for (size_t i = 0; i < warm; i++) rng.fill_bytes(tmp, 64);  // e.g. the three blinding draws that come first
     rng.fill_many64(out64n, n);
     return BPG_OK;

@@ -55,11 +55,13 @@ struct TranscriptRng {
     // when several proofs are in flight in this process their streams are run eight at a time (keccak_x8_native.cpp).
     void fill_many64(uint8_t* out, size_t count);
 };
-// RAII marker of an executing Prover::prove (the batcher sizes its batches by how many are in flight)
+// Marker of a prover that exists and has not produced its proof yet (from Prover::new to the end of Prove::prove):
+// the batcher sizes its batches and its patience by how many of them this process has in flight.
 struct ProvingScope {
-    ProvingScope();
-    ~ProvingScope();
-    ProvingScope(const ProvingScope&) = delete;
+    bool active = false;
+    void enter();
+    void leave();
+    ~ProvingScope() { leave(); }
 };
 // statistics of the stream batcher: [0] streams served, [1] vector batches, [2] streams that ran alone (scalar)
 void rng_batcher_stats(uint64_t out[3]);

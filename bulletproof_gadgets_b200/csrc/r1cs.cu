@@ -129,6 +129,7 @@ struct bpg_prover {
     bpg::Transcript* T;
     const bpg_circuit* circ = nullptr;
     bpg_circuit* owned = nullptr;
+    bpg::ProvingScope in_flight;                       // from Prover::new until the proof is out
     ConstraintStore cs;
     std::vector<sc> aL, aR, aO, v, vbl;                // canonical
     std::vector<std::array<uint8_t, 32>> vbl_raw;     // as given (rekeys the transcript rng)
@@ -295,7 +296,11 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     while ((1u << lg) < npad) lg++;
 
     Trace trace(st);
-    bpg::ProvingScope in_flight;
+    P->in_flight.enter();
+    struct Leave {
+        bpg::ProvingScope& s;
+        ~Leave() { s.leave(); }
+    } leave_on_exit{P->in_flight};
     T.append_u64("m", m);
     uint8_t seed[32];
     if (seed32) memcpy(seed, seed32, 32); else os_random(seed);
@@ -814,6 +819,7 @@ int bpg_prover_new(bpg_ctx* ctx, bpg_transcript* t, bpg_prover** out) {
     p->ctx = ctx;
     p->T = &t->t;
     p->T->append_message("dom-sep", reinterpret_cast<const uint8_t*>("r1cs v1"), 7);
+    p->in_flight.enter();
     *out = p;
     return BPG_OK;
 }
