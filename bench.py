@@ -145,7 +145,15 @@ def main():
     import torch.distributed as dist
     if ws > 1:
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # The data path has no collective (independent proofs per rank): torch.distributed only provides the barrier
+        # and one max-reduce of the timing.  Measured on the 8-GPU box (32 vCPUs): with an NCCL process group alive
+        # every rank burns ~23 ms of host CPU per step in NCCL's service threads (479 vs 559 prove+verify/s,
+        # profiles/r01_bench_8gpu_{nccl,gloo}.json), and this workload is host-CPU bound there -- so gloo by default.
+        backend = os.environ.get("BPG_DIST_BACKEND", "gloo")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
     import bulletproof_gadgets_b200 as bpg
     from bulletproof_gadgets_b200 import build, workloads as W
     build.build_lib()
@@ -227,7 +235,7 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         if ws > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            t = torch.tensor([ms], device="cuda" if dist.get_backend() == "nccl" else "cpu", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
@@ -269,6 +277,7 @@ def main():
         ctx0.msm_gens_dev(d_sc.data_ptr(), st.n, d_sc.data_ptr() + 32 * st.n, st.n)
     msm_s = (time.perf_counter() - t0) / 10
 
+    dist_backend = dist.get_backend() if ws > 1 else None
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -292,7 +301,7 @@ def main():
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
-                   "inflight": inflight,
+                   "inflight": inflight, "dist_backend": (dist_backend if ws > 1 else None),
                    "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
                    "rng": "transcript rng seeded per step; proofs byte-identical to the CPU oracle",
                    "window_bits": ctx0.get("window_bits"), "task_len": 32},

@@ -48,7 +48,8 @@ cudaError_t ctx_sync(bpg_ctx* ctx) {
             if (polls >= 8) sched_yield();
             continue;
         }
-        if (polls >= 32 && (mode == 3 || w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
+        // under load every driver call contends with the other threads of the process: go to sleep almost at once
+        if (polls >= ((w > 4 || mode == 3) ? 2 : 32) && (mode == 3 || w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
             e = cudaEventSynchronize(ctx->ev_sync);
             break;
         }
