@@ -53,7 +53,10 @@ inline S s_u64(uint64_t x) {
 }
 inline bool s_eq(const S& a, const S& b) { return memcmp(a.v, b.v, 32) == 0; }  // raw bytes, like dalek's PartialEq
 inline bool s_is_zero(const S& a) { return sc_is_zero(a); }
-inline S s_red(const S& a) { return sc_reduce(a); }
+inline S s_red(const S& a) {  // canonical representative; almost every operand already is one
+    S t;
+    return sc_sub_raw(&t, a, sc_L()) != 0 ? a : sc_reduce(a);
+}
 inline S s_add(const S& a, const S& b) { return sc_add(s_red(a), s_red(b)); }
 inline S s_mul(const S& a, const S& b) { return sc_mul(a, b); }
 inline S s_neg(const S& a) { return sc_neg(s_red(a)); }
@@ -193,12 +196,12 @@ struct Buffer {
         const uint32_t i = n_mult++;
         return {mkvar(K_LEFT, i), mkvar(K_RIGHT, i), mkvar(K_OUT, i)};
     }
-    Vars3 multiply(const LC& l, const LC& r) {
-        Op o;
+    Vars3 multiply(LC l, LC r) {
+        ops.emplace_back();
+        Op& o = ops.back();
         o.kind = Op::MUL;
-        o.a = l;
-        o.b = r;
-        ops.push_back(std::move(o));
+        o.a = std::move(l);
+        o.b = std::move(r);
         return alloc();
     }
     Vars3 allocate_multiplier(bool has, const S& l, const S& r) {
@@ -610,7 +613,7 @@ struct Flat {
     std::vector<S> v, vbl;       // prover
     std::vector<Bytes> V;        // verifier
     std::vector<std::string> com_names;
-    std::vector<S> aL, aR;
+    std::vector<S> aL, aR, aO;  // aO: prover-side cache of a_L * a_R for LC evaluation
     uint32_t n = 0;
     std::vector<uint32_t> row_start{0}, term_var;
     std::vector<S> term_coef;
@@ -623,18 +626,25 @@ struct Flat {
             switch (k) {
                 case K_LEFT: if (i >= aL.size()) throw Panic("unallocated multiplier in a linear combination"); val = aL[i]; break;
                 case K_RIGHT: if (i >= aR.size()) throw Panic("unallocated multiplier in a linear combination"); val = aR[i]; break;
-                case K_OUT: if (i >= aL.size()) throw Panic("unallocated multiplier in a linear combination"); val = s_mul(aL[i], aR[i]); break;
+                case K_OUT: if (i >= aO.size()) throw Panic("unallocated multiplier in a linear combination"); val = aO[i]; break;
                 case K_COMMITTED: if (i >= v.size()) throw Panic("unknown committed variable"); val = v[i]; break;
                 default: val = s_one();
             }
-            acc = sc_add(acc, s_mul(e.second, val));
+            if (s_is_zero(e.second)) continue;                               // `Scalar::zero().into()` terms
+            const S term = s_eq(e.second, s_one()) ? s_red(val) : k == K_ONE ? s_red(e.second) : s_mul(e.second, val);
+            acc = sc_add(acc, term);
         }
         return acc;
     }
-    void constrain(const LC& lc) {
+    void constrain(const LC& lc, bool minus_var = false, Var var = 0) {  // lc, or lc - var
         for (auto& e : lc.t) {
             term_var.push_back(e.first);
             term_coef.push_back(e.second);
+        }
+        if (minus_var) {
+            static const S MINUS_ONE = s_neg(s_one());
+            term_var.push_back(var);
+            term_coef.push_back(MINUS_ONE);
         }
         row_start.push_back((uint32_t)term_var.size());
     }
@@ -646,14 +656,16 @@ struct Flat {
                     const S l = eval(o.a), r = eval(o.b);
                     aL.push_back(l);
                     aR.push_back(r);
+                    aO.push_back(s_mul(l, r));
                 }
                 n++;
-                constrain(o.a - LC::var(mkvar(K_LEFT, i)));
-                constrain(o.b - LC::var(mkvar(K_RIGHT, i)));
+                constrain(o.a, true, mkvar(K_LEFT, i));
+                constrain(o.b, true, mkvar(K_RIGHT, i));
             } else if (o.kind == Op::ALLOC) {
                 if (proving) {
                     aL.push_back(o.l);
                     aR.push_back(o.r);
+                    aO.push_back(s_mul(o.l, o.r));
                 }
                 n++;
             } else if (o.kind == Op::CON) {
