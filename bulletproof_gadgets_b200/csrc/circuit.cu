@@ -100,9 +100,13 @@ static void dfree(bpg_ctx* ctx, bool pooled, void* p) {
 
 void circuit_free(bpg_circuit* c) {
     if (!c) return;
-    cudaSetDevice(c->ctx->device);
+    cudaSetDevice(c->device);
     void* ps[] = {c->d_col_start, c->d_col_row, c->d_col_coef, c->d_long, c->d_aL, c->d_aR, c->d_aO};
-    for (void* p : ps) dfree(c->ctx, c->pooled, p);
+    for (void* p : ps) {
+        if (!p) continue;
+        if (c->pooled) cudaFreeAsync(p, c->ctx->stream);  // per-proof circuits die with their prover, before the context
+        else cudaFree(p);
+    }
     delete c;
 }
 
@@ -132,6 +136,7 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
     cudaStream_t st = ctx->stream;
     bpg_circuit* c = new bpg_circuit();
     c->ctx = ctx;
+    c->device = ctx->device;
     c->n = n, c->m = m, c->q = q, c->nt = nt, c->nnz = nnz, c->pooled = pooled;
     const uint32_t long_cap = nnz / FLATTEN_LONG + 1;
     uint32_t *d_row_start = nullptr, *d_term_var = nullptr, *d_cursor = nullptr, *d_scratch = nullptr, *d_flags = nullptr;

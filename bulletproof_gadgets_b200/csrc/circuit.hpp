@@ -6,7 +6,8 @@
 
 // targets (columns): [wL(n) | wR(n) | wO(n) | wV(m) | wc]; column t holds (constraint row, coefficient) pairs
 struct bpg_circuit {
-    bpg_ctx* ctx = nullptr;
+    bpg_ctx* ctx = nullptr;  // creating context (a resident circuit may outlive it: only `device` is used to free it)
+    int device = 0;
     uint32_t n = 0, m = 0, q = 0, nt = 0, nnz = 0, n_long = 0;
     uint32_t *d_col_start = nullptr, *d_col_row = nullptr, *d_long = nullptr;
     sc *d_col_coef = nullptr, *d_aL = nullptr, *d_aR = nullptr, *d_aO = nullptr;

@@ -961,12 +961,12 @@ int bpg_prover_prove(bpg_prover* p, const uint8_t* rng_seed32, uint8_t* proof_ou
 }
 
 int bpg_prover_attach(bpg_prover* p, const bpg_circuit* c) {
-    if (!p || !c || c->ctx->store != p->ctx->store || p->circ) return BPG_E_ARG;  // same GPU, nothing attached yet
+    if (!p || !c || c->device != p->ctx->device || p->circ) return BPG_E_ARG;  // same GPU, nothing attached yet
     p->circ = c;
     return BPG_OK;
 }
 int bpg_verifier_attach(bpg_verifier* v, const bpg_circuit* c) {
-    if (!v || !c || c->ctx->store != v->ctx->store || v->circ) return BPG_E_ARG;
+    if (!v || !c || c->device != v->ctx->device || v->circ) return BPG_E_ARG;
     v->circ = c;
     return BPG_OK;
 }
