@@ -81,6 +81,7 @@ struct FixedTable {
 struct GensStore {
     std::mutex mu;
     FixedTable table;
+    FixedTable small;  // 8-bit windows over the first `small.capacity` generators: MSMs of a few thousand points
     ge_ext* gens_ext = nullptr;
     ge_niels* ped = nullptr;
     int window_bits = 0;  // 0 = auto
@@ -105,6 +106,7 @@ struct bpg_ctx {
     GensStore* store = nullptr;  // shared per GPU
     // snapshots of the store taken by gens_build() at the start of every operation
     FixedTable table;
+    FixedTable small_table;
     ge_ext* gens_ext = nullptr;  // untabulated generators (extended), same order as the table
     MsmWork work;
     ge_ext* h_result = nullptr;  // pinned

@@ -10,6 +10,8 @@
 #include "kernels.hpp"
 #include "merlin.hpp"
 
+#define SMALL_TABLE_CAP 4096u
+
 __global__ void __launch_bounds__(128) k_uniform_to_ext(const uint8_t* __restrict__ uniform, ge_ext* __restrict__ out,
                                                         uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,6 +78,7 @@ static const uint8_t BASEPOINT_COMPRESSED[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0
 static void snapshot(bpg_ctx* ctx) {
     GensStore* g = ctx->store;
     ctx->table = g->table;
+    ctx->small_table = g->small;
     ctx->gens_ext = g->gens_ext;
     ctx->ped = g->ped;
 }
@@ -136,12 +139,36 @@ int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     k_to_niels<<<(uint32_t)((total + 127) / 128), 128, 0, st>>>(d_tmp, d_rows, total);
     pk_pedersen_table(st, d_ext, (uint32_t)(2 * cap), d_ped);
     ctx->launches += 5;
+    // Small-MSM table: 8-bit windows (32 rows per point, 128 signed buckets) over [G_0..G_sc-1 | H_0..H_sc-1 | B | B~].
+    // With 2^15 buckets a 1 000-point MSM spends its time walking empty buckets; with 128 it does not.
+    const uint64_t sc_cap = cap < SMALL_TABLE_CAP ? cap : SMALL_TABLE_CAP;
+    const uint32_t ns = (uint32_t)(2 * sc_cap + 2);
+    const int cs = 8, Ks = 32;
+    ge_ext *d_sub = nullptr, *d_stmp = nullptr;
+    ge_niels* d_srows = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_sub, ns * sizeof(ge_ext)));
+    CUDA_TRY(cudaMalloc((void**)&d_stmp, (size_t)Ks * ns * sizeof(ge_ext)));
+    CUDA_TRY(cudaMalloc((void**)&d_srows, (size_t)Ks * ns * sizeof(ge_niels)));
+    CUDA_TRY(cudaMemcpyAsync(d_sub, d_ext, sc_cap * sizeof(ge_ext), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_sub + sc_cap, d_ext + cap, sc_cap * sizeof(ge_ext), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_sub + 2 * sc_cap, d_ext + 2 * cap, 2 * sizeof(ge_ext), cudaMemcpyDeviceToDevice, st));
+    k_window_multiples<<<(ns + 127) / 128, 128, 0, st>>>(d_sub, d_stmp, ns, cs, Ks);
+    k_to_niels<<<(uint32_t)(((uint64_t)Ks * ns + 127) / 128), 128, 0, st>>>(d_stmp, d_srows, (uint64_t)Ks * ns);
+    ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(ctx_sync(ctx));
     cudaFree(d_uni);
     cudaFree(d_bp);
     cudaFree(d_fail);
     cudaFree(d_tmp);
+    cudaFree(d_sub);
+    cudaFree(d_stmp);
+    if (g->small.rows) g->garbage.push_back(g->small.rows);
+    g->small.rows = d_srows;
+    g->small.n_points = ns;
+    g->small.c = cs;
+    g->small.K = Ks;
+    g->small.capacity = sc_cap;
     // other contexts of this GPU may still be reading the superseded tables: keep them until the store dies
     if (g->table.rows) g->garbage.push_back(g->table.rows);
     if (g->gens_ext) g->garbage.push_back(g->gens_ext);
@@ -165,6 +192,7 @@ void gens_store_release(GensStore* g) {
     }
     if (!last) return;
     if (g->table.rows) cudaFree(g->table.rows);
+    if (g->small.rows) cudaFree(g->small.rows);
     if (g->gens_ext) cudaFree(g->gens_ext);
     if (g->ped) cudaFree(g->ped);
     for (void* p : g->garbage) cudaFree(p);

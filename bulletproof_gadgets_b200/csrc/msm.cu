@@ -28,6 +28,7 @@
 
 #define REDUCE_BLOCKS 128
 #define FINAL_THREADS 128
+#define SMALL_MSM_MAX_POINTS 4096u  // MSMs up to 2 x this many points use the 8-bit-window table
 #define REDUCE_THREADS 64
 #define ACC_THREADS 128
 
@@ -301,12 +302,38 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_reduce_final(const ge_ext* __
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
-int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out) {
-    const FixedTable& tb = ctx->table;
-    if (!tb.rows) {
+// Segments address points in the index space of the big table ([G | H | B | B~] with H at `capacity`).  MSMs whose points
+// all lie in the small table's prefix use it instead: 8-bit windows, 128 buckets per set.
+static bool to_small_table(const FixedTable& big, const FixedTable& sm, MsmSegments* segs) {
+    if (!sm.rows || segs->total > 2 * SMALL_MSM_MAX_POINTS + 2) return false;
+    const uint64_t cap = big.capacity, sc_cap = sm.capacity;
+    MsmSegments out = *segs;
+    for (uint32_t k = 0; k < segs->nseg; k++) {
+        const uint64_t base = segs->seg[k].point_base, cnt = segs->seg[k].count;
+        uint64_t nb;
+        if (base < cap) {
+            if (base + cnt > sc_cap) return false;
+            nb = base;
+        } else if (base < 2 * cap) {
+            if (base - cap + cnt > sc_cap) return false;
+            nb = sc_cap + (base - cap);
+        } else {
+            nb = 2 * sc_cap + (base - 2 * cap);
+        }
+        out.seg[k].point_base = (uint32_t)nb;
+    }
+    *segs = out;
+    return true;
+}
+
+int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_out) {
+    if (!ctx->table.rows) {
         bpg_set_error("msm_run: generator table not built");
         return BPG_E_ARG;
     }
+    MsmSegments segs = segs_in;
+    const bool use_small = to_small_table(ctx->table, ctx->small_table, &segs);
+    const FixedTable& tb = use_small ? ctx->small_table : ctx->table;
     if (nsets == 0 || segs.nseg > MSM_MAX_SEGMENTS) return BPG_E_ARG;
     cudaStream_t st = ctx->stream;
     const uint32_t nb = 1u << (tb.c - 1);
