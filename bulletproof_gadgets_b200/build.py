@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-march=x86-64-v3,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
     "-I", CSRC, "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("BPG_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -185,9 +185,153 @@ BPG_HD fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b))
 #endif
 
+#if defined(__CUDA_ARCH__) && defined(FE_KARATSUBA)
+// acc[0..4] += (a0, a1) * b laid out as lo,hi pairs on consecutive limbs; acc[4] takes the carry
+#define FE_MADROW5(acc, a0, a1, b)                                                                            \
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"                                                                  \
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"                                                                 \
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"                                                                 \
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"                                                                 \
+        "addc.u32 %4, %4, 0;"                                                                                 \
+        : "+r"((acc)[0]), "+r"((acc)[1]), "+r"((acc)[2]), "+r"((acc)[3]), "+r"((acc)[4])                      \
+        : "r"(a0), "r"(a1), "r"(b))
+#define FE_MADROW4(acc, a0, a1, b)                                                                            \
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"                                                                  \
+        "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"                                                                 \
+        "madc.lo.cc.u32 %2, %5, %6, %2;\n\t"                                                                 \
+        "madc.hi.u32 %3, %5, %6, %3;"                                                                         \
+        : "+r"((acc)[0]), "+r"((acc)[1]), "+r"((acc)[2]), "+r"((acc)[3])                                      \
+        : "r"(a0), "r"(a1), "r"(b))
+// r[0..8) = a[0..4) * b[0..4): 16 multiply-add pairs (IMAD.WIDE), even / odd column accumulators as in fe_mul_wide
+__device__ __forceinline__ void fe_mul4(uint32_t r[8], const uint32_t a[4], const uint32_t b[4]) {
+    uint32_t E[9], O[8];
+#pragma unroll
+    for (int k = 0; k < 9; k++) E[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t bi = b[i];
+        if ((i & 1) == 0) {
+            if (i + 4 < 8) {
+                FE_MADROW5(E + i, a[0], a[2], bi);
+                FE_MADROW5(O + i, a[1], a[3], bi);
+            } else {
+                FE_MADROW4(E + i, a[0], a[2], bi);
+                FE_MADROW4(O + i, a[1], a[3], bi);
+            }
+        } else {
+            if (i + 5 < 8) {
+                FE_MADROW5(E + i + 1, a[1], a[3], bi);
+            } else {
+                FE_MADROW4(E + i + 1, a[1], a[3], bi);
+            }
+            FE_MADROW5(O + i - 1, a[0], a[2], bi);
+        }
+    }
+    r[0] = E[0];
+    asm("add.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]), "r"(O[2]),
+          "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+}
+// One level of Karatsuba over 128-bit halves: 48 multiply-add pairs instead of 64 (the IMAD.WIDE pipe is the bound of the
+// bucket kernel); the extra additions ride the ALU pipe.  MEASURED AND NOT ENABLED (-DFE_KARATSUBA): correct (all GPU
+// parity tests pass) but k_accumulate gets slower on B200, 378 us vs 339 us at 2^18 points -- ~70 extra carry-chain
+// additions per product cost more issue slots than 16 IMAD.WIDE save, and the kernel goes from 108 to 126 registers.
+__device__ __forceinline__ void fe_mul_wide_karatsuba(uint32_t r[16], const fe& a, const fe& b) {
+    uint32_t z0[8], z2[8], zm[9], sa[4], sb[4], ca, cb;
+    fe_mul4(z0, a.v, b.v);
+    fe_mul4(z2, a.v + 4, b.v + 4);
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(sa[0]), "=r"(sa[1]), "=r"(sa[2]), "=r"(sa[3]), "=r"(ca)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(sb[0]), "=r"(sb[1]), "=r"(sb[2]), "=r"(sb[3]), "=r"(cb)
+        : "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    fe_mul4(zm, sa, sb);
+    // (sa + ca 2^128)(sb + cb 2^128) = sa sb + (ca sb + cb sa) 2^128 + ca cb 2^256
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %9, 0;"
+        : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "=r"(zm[8])
+        : "r"(sb[0] & ma), "r"(sb[1] & ma), "r"(sb[2] & ma), "r"(sb[3] & ma), "r"(ca & cb));
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "r"(sa[0] & mb), "r"(sa[1] & mb), "r"(sa[2] & mb), "r"(sa[3] & mb));
+    // z1 = zm - z0 - z2   (0 <= z1 < 2^258)
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, %11;\n\t"
+        "subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t"
+        "subc.cc.u32 %5, %5, %14;\n\t"
+        "subc.cc.u32 %6, %6, %15;\n\t"
+        "subc.cc.u32 %7, %7, %16;\n\t"
+        "subc.u32 %8, %8, 0;"
+        : "+r"(zm[0]), "+r"(zm[1]), "+r"(zm[2]), "+r"(zm[3]), "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]));
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, %11;\n\t"
+        "subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t"
+        "subc.cc.u32 %5, %5, %14;\n\t"
+        "subc.cc.u32 %6, %6, %15;\n\t"
+        "subc.cc.u32 %7, %7, %16;\n\t"
+        "subc.u32 %8, %8, 0;"
+        : "+r"(zm[0]), "+r"(zm[1]), "+r"(zm[2]), "+r"(zm[3]), "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+    // r = z0 + z1 2^128 + z2 2^256
+    r[0] = z0[0], r[1] = z0[1], r[2] = z0[2], r[3] = z0[3];
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, 0;\n\t"
+        "addc.cc.u32 %10, %22, 0;\n\t"
+        "addc.u32 %11, %23, 0;"
+        : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]),
+          "r"(z2[5]), "r"(z2[6]), "r"(z2[7]), "r"(zm[0]), "r"(zm[1]), "r"(zm[2]), "r"(zm[3]), "r"(zm[4]), "r"(zm[5]),
+          "r"(zm[6]), "r"(zm[7]), "r"(zm[8]));
+}
+#endif
+
 // r[0..16) = a*b (full 512-bit product)
 BPG_HD void fe_mul_wide(uint32_t r[16], const fe& a, const fe& b) {
 #ifdef __CUDA_ARCH__
+#ifdef FE_KARATSUBA
+    fe_mul_wide_karatsuba(r, a, b);
+    return;
+#endif
     // E holds products with (i+j) even at limb i+j; O holds (i+j) odd, stored one limb lower
     // (O[k] has weight 2^(32(k+1))) so that lo/hi pairs stay even-aligned in both arrays.
     uint32_t E[17], O[16];
