@@ -34,9 +34,9 @@ static inline uint32_t var_idx(uint32_t v) { return v & ((1u << 29) - 1); }
 // reusable device vectors
 // ------------------------------------------------------------------------------------------
 struct ProofWork {
-    DevBuf<sc> aL, aR, aO, sL, sR, w, ypow, yinv, zpow, l1, r0, r1, r3, lvec, rvec, sG, sH, mG, mH, partial, small;
-    DevBuf<sc> vbl, col_coef, dyn_s, ped_in;
-    DevBuf<uint32_t> col_start, col_row, fail, long_t, fl_tickets;
+    DevBuf<sc> sL, sR, w, ypow, yinv, zpow, l1, r0, r1, r3, lvec, rvec, sG, sH, mG, mH, partial, small;
+    DevBuf<sc> vbl, dyn_s, ped_in;
+    DevBuf<uint32_t> fail, fl_tickets;
     DevBuf<sc> fl_part;
     DevBuf<uint8_t> wide, dyn_enc;
     DevBuf<ge_ext> dyn_pts, dyn_blk;
@@ -55,14 +55,10 @@ struct ProofWork {
 void r1cs_release_work(bpg_ctx* ctx) {
     ProofWork* p = ctx->pw;
     if (!p) return;
-    DevBuf<sc>* bs[] = {&p->aL, &p->aR, &p->aO, &p->sL, &p->sR, &p->w, &p->ypow, &p->yinv, &p->zpow, &p->l1, &p->r0,
-                        &p->r1, &p->r3, &p->lvec, &p->rvec, &p->sG, &p->sH, &p->mG, &p->mH, &p->partial, &p->small,
-                        &p->vbl, &p->col_coef, &p->dyn_s, &p->ped_in};
+    DevBuf<sc>* bs[] = {&p->sL, &p->sR, &p->w, &p->ypow, &p->yinv, &p->zpow, &p->l1, &p->r0, &p->r1, &p->r3, &p->lvec,
+                        &p->rvec, &p->sG, &p->sH, &p->mG, &p->mH, &p->partial, &p->small, &p->vbl, &p->dyn_s, &p->ped_in};
     for (auto* b : bs) b->release();
-    p->col_start.release();
-    p->col_row.release();
     p->fail.release();
-    p->long_t.release();
     p->fl_tickets.release();
     p->fl_part.release();
     p->wide.release();
