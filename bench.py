@@ -37,6 +37,11 @@ WORKLOAD = "bounds_check 64-bit x1024 in one R1CS proof (n=2^17 multipliers, m=3
 # IMAD.WIDE.U32 issue rate, the instruction the field multiplication is built from
 IMAD_WIDE_PEAK_TOPS = 8.157
 IMAD_PER_MADD = 504  # 7 field muls x (64 + 8) 32x32->64 multiply-adds, SURVEY.md 8(d)
+try:
+    HBM_PEAK_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:  # noqa: BLE001
+    HBM_PEAK_GBS = 6537.6   # this pool's measured copy bandwidth (MEASURED_PEAKS.json of round 1)
+SORT_TRAFFIC_BYTES = 13.76e6   # dram read+write per launch of k_digits<1> (IPP-round MSM), profiles/r01_digits_ncu_details.csv
 
 
 def _dist():
@@ -260,6 +265,7 @@ def main():
     ctx0.set("time_accum", 1)
     step_resident(ctx0, 10 ** 6)
     acc_ns, acc_entries = ctx0.get("sum_accum_ns"), ctx0.get("sum_entries")
+    sct_ns, sct_points = ctx0.get("sum_scatter_ns"), ctx0.get("sum_points")
     ctx0.set("time_accum", 0)
 
     # second half of the BASELINE metric: raw fixed-base MSM (verifier mega-MSM shape), 2n' = 2^18 points, uniform
@@ -330,6 +336,15 @@ def main():
                      "work": "%d mixed adds x %d IMAD.WIDE" % (acc_entries, IMAD_PER_MADD),
                      "kernel_ms_per_step": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / (ms_lat / lat_steps),
                      "share_note": "share of the un-overlapped (latency) step"},
+        # the sort stage north_star asks to see against HBM: digit decomposition + scatter by bucket.  Algorithmic bytes
+        # per launch: 32 B per scalar read + 4 B per entry written + 4 B per entry of offset reads.
+        "roofline_sort": {"kernel": "k_digits<1> (signed-digit decomposition + counting-sort scatter)", "bound": "hbm",
+                          "achieved": (32 * sct_points + 8 * acc_entries) / (sct_ns * 1e-9) / 1e9 if sct_ns else None,
+                          "peak": HBM_PEAK_GBS, "unit": "GB/s",
+                          "frac": (32 * sct_points + 8 * acc_entries) / (sct_ns * 1e-9) / 1e9 / HBM_PEAK_GBS if sct_ns else None,
+                          "traffic": SORT_TRAFFIC_BYTES, "kernel_ms_per_step": sct_ns * 1e-6,
+                          "note": "bound in practice by L2 atomics (one atomicAdd per entry on 65 536 bucket cursors), not by "
+                                  "HBM bytes: profiles/r01_digits_ncu_details.csv"},
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:

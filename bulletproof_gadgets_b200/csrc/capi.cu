@@ -86,6 +86,8 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ctx->ev_a));
     CUDA_TRY(cudaEventCreate(&ctx->ev_b));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_c));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_d));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
     *out = ctx;
@@ -154,6 +156,8 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
+    cudaEventDestroy(ctx->ev_c);
+    cudaEventDestroy(ctx->ev_d);
     cudaEventDestroy(ctx->ev_sync);
     cudaStreamDestroy(ctx->stream);
     gens_store_release(ctx->store);
@@ -192,6 +196,8 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
         ctx->time_accum = value != 0;
         ctx->sum_accum_ms = 0;
         ctx->sum_entries = 0;
+        ctx->sum_scatter_ms = 0;
+        ctx->sum_points = 0;
     } else {
         return BPG_E_ARG;
     }
@@ -207,6 +213,8 @@ int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key) {
     if (k == "accum_entries") return (int64_t)ctx->last_entries;
     if (k == "sum_accum_ns") return (int64_t)(ctx->sum_accum_ms * 1e6);
     if (k == "sum_entries") return (int64_t)ctx->sum_entries;
+    if (k == "sum_scatter_ns") return (int64_t)(ctx->sum_scatter_ms * 1e6);
+    if (k == "sum_points") return (int64_t)ctx->sum_points;
     if (k == "cpu_sync_ns") return (int64_t)ctx->cpu_sync_ns;
     if (k == "cpu_commit_ns") return (int64_t)ctx->cpu_commit_ns;
     if (k == "cpu_prove_ns") return (int64_t)ctx->cpu_prove_ns;

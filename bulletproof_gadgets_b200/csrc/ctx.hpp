@@ -120,10 +120,12 @@ struct bpg_ctx {
     // counters for bench.py ("gpu_launches")
     uint64_t launches = 0;
     // timing of the dominant kernel (accumulate), CUDA events on ctx stream
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;  // accumulate / scatter brackets
     cudaEvent_t ev_sync = nullptr;  // blocking-sync event behind ctx_sync()
     float last_accum_ms = 0.f;
     uint64_t last_entries = 0;
+    double sum_scatter_ms = 0;  // digits + scatter kernel (the sort stage), same mode
+    uint64_t sum_points = 0;    // scalars decomposed
     double sum_accum_ms = 0;  // accumulated over all MSMs since the last reset (time_accum mode)
     uint64_t sum_entries = 0;
     bool time_accum = false;

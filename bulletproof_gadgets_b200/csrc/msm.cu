@@ -369,8 +369,10 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     ctx->launches += 3;
     if (total > 0) {
         const uint32_t blocks = (uint32_t)((total + 255) / 256);
+        if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_c, st));
         k_digits<true><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, w.bucket_off.p,
                                               w.entries.p);
+        if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_d, st));
         ctx->launches++;
     }
     k_chunks<<<(G + 255) / 256, 256, 0, st>>>(w.bucket_off.p, w.chunk_bucket.p, G, T);
@@ -397,6 +399,12 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
         ctx->last_entries = ne;
         ctx->sum_accum_ms += ctx->last_accum_ms;
         ctx->sum_entries += ne;
+        if (total > 0) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_c, ctx->ev_d));
+            ctx->sum_scatter_ms += ms;
+            ctx->sum_points += total;
+        }
         if (getenv("BPG_ACC_TRACE"))
             fprintf(stderr, "[bpg acc] sets %u points %llu entries %u accumulate %.1f us\n", nsets, (unsigned long long)total, ne,
                     ctx->last_accum_ms * 1e3);
