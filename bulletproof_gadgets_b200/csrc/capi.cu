@@ -84,6 +84,20 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
     ctx->device = device;
     ctx->store = store;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        // Per-proof device buffers (bulk-loaded circuits) come from a pool private to this context: with the device's
+        // default pool, memory freed on one stream and reused on another makes the driver chain the two streams, which
+        // serialises proofs that are otherwise independent.  Freed memory stays cached (release threshold = max).
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CUDA_TRY(cudaMemPoolCreate(&ctx->pool, &props));
+        uint64_t keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_TRY(cudaEventCreate(&ctx->ev_a));
     CUDA_TRY(cudaEventCreate(&ctx->ev_b));
     CUDA_TRY(cudaEventCreate(&ctx->ev_c));
@@ -115,11 +129,6 @@ int bpg_ctx_create(int device, bpg_ctx** out) {
         bpg_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return BPG_E_CUDA;
     }
-    // per-proof device buffers come from the stream-ordered pool: keep freed memory cached
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = ~0ull;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     return ctx_new(device, new GensStore(), out);
 }
 
@@ -160,6 +169,7 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     cudaEventDestroy(ctx->ev_d);
     cudaEventDestroy(ctx->ev_sync);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     gens_store_release(ctx->store);
     delete ctx;
 }

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_witness(sc* __restrict__ aL, sc* __rest
 }
 
 static int dalloc(bpg_ctx* ctx, bool pooled, void** p, size_t bytes) {
-    if (pooled) CUDA_TRY(cudaMallocAsync(p, bytes, ctx->stream));
+    if (pooled) CUDA_TRY(cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream));
     else CUDA_TRY(cudaMalloc(p, bytes));
     return BPG_OK;
 }

@@ -103,6 +103,7 @@ struct MsmWork {
 struct bpg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;  // private stream-ordered pool: per-proof circuits never create cross-stream dependencies
     GensStore* store = nullptr;  // shared per GPU
     // snapshots of the store taken by gens_build() at the start of every operation
     FixedTable table;
