@@ -9,6 +9,7 @@
 // (build.py); selected at run time when the CPU has AVX-512F.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define X8_TARGET __attribute__((target("avx512f")))
@@ -23,7 +24,9 @@ static const uint64_t RC[24] = {
     0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
 
-bool keccak_x8_supported() {
+bool keccak_x8_supported() {  // BPG_KECCAK=scalar forces the portable code (tests cover both paths on AVX-512 hosts)
+    const char* e = getenv("BPG_KECCAK");
+    if (e && !strcmp(e, "scalar")) return false;
     __builtin_cpu_init();
     return __builtin_cpu_supports("avx512f");
 }

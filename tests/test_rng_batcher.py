@@ -93,3 +93,29 @@ def test_concurrent_long_streams_are_batched_and_exact(lib, nthreads):
             break
     if nthreads >= 5 and "avx512f" in open("/proc/cpuinfo").read():      # pairs may legitimately run alone (low-latency policy)
         assert formed, "no vector batch was formed on an AVX-512 host"
+
+
+def test_scalar_keccak_path_in_a_subprocess():
+    """BPG_KECCAK=scalar disables both AVX-512 paths (single-state permutation and the x8 batcher): the portable code
+    must give the same transcript / rng bytes (this is what a host without AVX-512 runs)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import ctypes, sys; sys.path.insert(0, %r)\n"
+        "import bulletproof_gadgets_b200 as bpg\n"
+        "T = bpg.Transcript(b'test protocol'); T.append_message(b'some label', b'some data')\n"
+        "print(T.challenge_bytes(b'challenge', 32).hex())\n"
+        "T = bpg.Transcript(b'solo'); T.append_message(b'dom-sep', b'r1cs v1')\n"
+        "out = ctypes.create_string_buffer(64 * 300)\n"
+        "assert bpg.lib().bpg_transcript_rng_fill64(T._h, b'\\x01' * 32, 1, b'\\x05' * 32, 3, out, 300) == 0\n"
+        "print(out.raw.hex())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for mode in ("scalar", "auto"):
+        env = dict(os.environ, BPG_KECCAK=mode)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.split())
+    assert outs[0] == outs[1]
+    assert outs[0][0] == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    assert bytes.fromhex(outs[0][1]) == oracle_stream(b"solo", [b"\x01" * 32], b"\x05" * 32, 3, 300)
