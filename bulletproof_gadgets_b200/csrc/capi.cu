@@ -162,7 +162,6 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     ctx->d_points.release();
     r1cs_release_work(ctx);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
     cudaEventDestroy(ctx->ev_c);

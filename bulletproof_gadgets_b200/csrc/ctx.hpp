@@ -111,8 +111,6 @@ struct bpg_ctx {
     ge_ext* gens_ext = nullptr;  // untabulated generators (extended), same order as the table
     MsmWork work;
     ge_ext* h_result = nullptr;  // pinned
-    uint8_t* h_stage = nullptr;  // pinned staging
-    size_t h_stage_cap = 0;
     DevBuf<uint32_t> d_scalars;  // staging for host-provided scalars
     DevBuf<ge_ext> d_points;     // result slots of asynchronous MSMs
     ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu); snapshot
