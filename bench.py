@@ -2,8 +2,9 @@
 """bench.py -- BASELINE.json headline: R1CS prove & verify per second on B200 (config 2:
 `BOUND` 64-bit range statements x1024 in ONE R1CS proof, n = 2^17 multipliers, m = 3072 commitments).
 
-One "step" = one pass of the hot path over one statement: m Pedersen commitments + Prover::prove
-+ Verifier::verify (accepting).  Legs:
+One "step" = one pass of the hot path over one BATCH of PROOFS_PER_STEP = 8 independent statements (eight is the
+width at which the library runs the provers' Merlin rng streams in lockstep); each statement costs m Pedersen
+commitments + Prover::prove + Verifier::verify (accepting).  value = steps x 8 / time, in proofs per second.  Legs:
   value  constraint system and witness already resident in HBM (bpg_circuit); proofs verified inside
          the timed region.  `inflight` host threads (one bpg context = one stream each, generator
          tables shared) keep several independent steps in flight on the GPU, because the prover's
@@ -37,6 +38,7 @@ WORKLOAD = "bounds_check 64-bit x1024 in one R1CS proof (n=2^17 multipliers, m=3
 # IMAD.WIDE.U32 issue rate, the instruction the field multiplication is built from
 IMAD_WIDE_PEAK_TOPS = 8.157
 IMAD_PER_MADD = 504  # 7 field muls x (64 + 8) 32x32->64 multiply-adds, SURVEY.md 8(d)
+PROOFS_PER_STEP = 8  # statements per step (one batch); every statement is proven and verified
 try:
     HBM_PEAK_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:  # noqa: BLE001
@@ -135,7 +137,7 @@ def run_reference(args, ws, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=8, help="batches of %d statements" % PROOFS_PER_STEP)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--count", type=int, default=1024, help="BOUND statements per proof (1024 = BASELINE config 2)")
@@ -227,7 +229,7 @@ def main():
         if errs:
             raise errs[0]
 
-    def timed(fn, steps, warm, use_ctxs):
+    def timed(fn, steps, warm, use_ctxs):   # `steps` here = number of statements
         run_steps(fn, 0, max(warm, len(use_ctxs)), use_ctxs)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,13 +253,14 @@ def main():
     launches0 = sum(c.get("launches") for c in ctxs)
     stat0 = [bpg.lib().bpg_rng_batcher_stat(k) for k in range(3)]
     cpu0 = time.process_time()
-    ms_res = timed(step_resident, args.steps, warmup, ctxs)
+    nproofs = args.steps * PROOFS_PER_STEP
+    ms_res = timed(step_resident, nproofs, warmup, ctxs)
     cpu_res = time.process_time() - cpu0
     launches = sum(c.get("launches") for c in ctxs) - launches0
-    ms_e2e = timed(step_e2e, args.steps, warmup, ctxs)
+    ms_e2e = timed(step_e2e, nproofs, warmup, ctxs)
     stat1 = [bpg.lib().bpg_rng_batcher_stat(k) for k in range(3)]
     cpu_parts = {k: sum(c.get("cpu_%s_ns" % k) for c in ctxs) * 1e-9 for k in ("sync", "commit", "prove", "verify", "rng")}
-    lat_steps = max(3, min(10, args.steps))
+    lat_steps = 10
     ms_lat = timed(step_resident, lat_steps, warmup, ctxs[:1])
     sampler.stop_flag = True
 
@@ -290,8 +293,8 @@ def main():
     if rank != 0:
         return
     per_step_ms = ms_res / args.steps
-    value = ws * args.steps / (ms_res * 1e-3)
-    e2e_value = ws * args.steps / (ms_e2e * 1e-3)
+    value = ws * nproofs / (ms_res * 1e-3)
+    e2e_value = ws * nproofs / (ms_e2e * 1e-3)
     achieved = acc_entries * IMAD_PER_MADD / (acc_ns * 1e-9) / 1e12 if acc_ns else None
     lg = max(st.n - 1, 0).bit_length()
     # bytes crossing PCIe per e2e step, counted from the buffers handed to the C ABI plus the library's own uploads
@@ -307,20 +310,20 @@ def main():
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
-                   "inflight": inflight, "dist_backend": (dist_backend if ws > 1 else None),
+                   "proofs_per_step": PROOFS_PER_STEP, "inflight": inflight, "dist_backend": (dist_backend if ws > 1 else None),
                    "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
                    "rng": "transcript rng seeded per step; proofs byte-identical to the CPU oracle",
                    "window_bits": ctx0.get("window_bits"), "task_len": 32},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h},
-        "latency": {"ms_per_step": ms_lat / lat_steps, "steps": lat_steps,
-                    "note": "one step at a time on one context; the prover waits on the host for the sequential "
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d * PROOFS_PER_STEP, "d2h_bytes_per_step": d2h * PROOFS_PER_STEP},
+        "latency": {"ms_per_proof": ms_lat / lat_steps, "proofs": lat_steps,
+                    "note": "one proof+verify at a time on one context; the prover waits on the host for the sequential "
                             "Merlin TranscriptRng stream (2n Keccak-f permutations)"},
         "msm": {"points": npts, "mpoints_per_s": npts / msm_s / 1e6, "ms": msm_s * 1e3, "scalars": "uniform mod l",
                 "frac_of_imad_peak_whole_msm": 16 * npts * IMAD_PER_MADD / msm_s / (IMAD_WIDE_PEAK_TOPS * 1e12),
                 "note": "one GPU; sweep 2^10..2^22 in profiles/r01_configs_1gpu.jsonl (tools/bench_configs.py)"},
         "gpu_launches": launches,
-        "host": {"cores": os.cpu_count(), "cpu_s_per_step_rank0": cpu_res / (args.steps + max(warmup, inflight)),
+        "host": {"cores": os.cpu_count(), "cpu_s_per_proof_rank0": cpu_res / (nproofs + max(warmup, inflight)),
                  "rng_streams": stat1[0] - stat0[0], "rng_vector_batches": stat1[1] - stat0[1],
                  "rng_streams_alone": stat1[2] - stat0[2],
                  "thread_cpu_s_total_all_legs": cpu_parts,
@@ -334,15 +337,15 @@ def main():
                      "peak_source": "tools/imad_peak.cu on this pool (profiles/r01_imad_peak.jsonl); IMAD.WIDE.U32 issues at "
                                     "28/clk/SM vs 64 for 32-bit IMAD; not in MEASURED_PEAKS.json",
                      "work": "%d mixed adds x %d IMAD.WIDE" % (acc_entries, IMAD_PER_MADD),
-                     "kernel_ms_per_step": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / (ms_lat / lat_steps),
-                     "share_note": "share of the un-overlapped (latency) step"},
+                     "kernel_ms_per_proof": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / (ms_lat / lat_steps),
+                     "share_note": "share of one un-overlapped proof+verify (the latency leg)"},
         # the sort stage north_star asks to see against HBM: digit decomposition + scatter by bucket.  Algorithmic bytes
         # per launch: 32 B per scalar read + 4 B per entry written + 4 B per entry of offset reads.
         "roofline_sort": {"kernel": "k_digits<1> (signed-digit decomposition + counting-sort scatter)", "bound": "hbm",
                           "achieved": (32 * sct_points + 8 * acc_entries) / (sct_ns * 1e-9) / 1e9 if sct_ns else None,
                           "peak": HBM_PEAK_GBS, "unit": "GB/s",
                           "frac": (32 * sct_points + 8 * acc_entries) / (sct_ns * 1e-9) / 1e9 / HBM_PEAK_GBS if sct_ns else None,
-                          "traffic": SORT_TRAFFIC_BYTES, "kernel_ms_per_step": sct_ns * 1e-6,
+                          "traffic": SORT_TRAFFIC_BYTES, "kernel_ms_per_proof": sct_ns * 1e-6,
                           "note": "bound in practice by L2 atomics (one atomicAdd per entry on 65 536 bucket cursors), not by "
                                   "HBM bytes: profiles/r01_digits_ncu_details.csv"},
         "clocks": sampler.summary(),
