@@ -21,6 +21,7 @@
 // raw bytes; + - * invert return canonical values.
 #include <stdlib.h>
 
+#include <chrono>
 #include <functional>
 #include <map>
 #include <random>
@@ -145,8 +146,95 @@ typedef uint32_t Var;
 inline Var mkvar(uint32_t kind, uint32_t idx) { return (kind << 29) | idx; }
 const Var ONE_VAR = 4u << 29;
 
+struct Term {
+    Var first;
+    S second;
+};
+// Term list with room for four terms in place: almost every linear combination a gadget builds has one to three terms
+// (a variable, a constant, `p + k + c_i`), so the common case never touches the heap.
+class TermVec {
+    static const uint32_t INLINE = 4;
+    Term inl_[INLINE];
+    Term* p_ = inl_;
+    uint32_t n_ = 0, cap_ = INLINE;
+    void grow(uint32_t want) {
+        uint32_t cap = cap_ * 2;
+        while (cap < want) cap *= 2;
+        Term* q = (Term*)malloc(sizeof(Term) * cap);
+        if (!q) throw std::bad_alloc();
+        memcpy(q, p_, sizeof(Term) * n_);
+        if (p_ != inl_) free(p_);
+        p_ = q;
+        cap_ = cap;
+    }
+    void steal(TermVec& o) {
+        n_ = o.n_;
+        if (o.p_ == o.inl_) {
+            memcpy(inl_, o.inl_, sizeof(Term) * o.n_);
+            p_ = inl_;
+            cap_ = INLINE;
+        } else {
+            p_ = o.p_;
+            cap_ = o.cap_;
+            o.p_ = o.inl_;
+            o.cap_ = INLINE;
+        }
+        o.n_ = 0;
+    }
+
+   public:
+    TermVec() {}
+    TermVec(const TermVec& o) { append(o.p_, o.n_); }
+    TermVec(TermVec&& o) noexcept { steal(o); }
+    TermVec& operator=(const TermVec& o) {
+        if (this != &o) {
+            n_ = 0;
+            append(o.p_, o.n_);
+        }
+        return *this;
+    }
+    TermVec& operator=(TermVec&& o) noexcept {
+        if (this != &o) {
+            if (p_ != inl_) free(p_);
+            steal(o);
+        }
+        return *this;
+    }
+    ~TermVec() {
+        if (p_ != inl_) free(p_);
+    }
+    void reserve(uint32_t want) {
+        if (want > cap_) grow(want);
+    }
+    void push_back(const Term& t) {
+        if (n_ == cap_) grow(n_ + 1);
+        p_[n_++] = t;
+    }
+    void append(const Term* q, uint32_t n) {
+        reserve(n_ + n);
+        memcpy(p_ + n_, q, sizeof(Term) * n);
+        n_ += n;
+    }
+    const Term* begin() const { return p_; }
+    const Term* end() const { return p_ + n_; }
+    Term* begin() { return p_; }
+    Term* end() { return p_ + n_; }
+    uint32_t size() const { return n_; }
+};
+
+// read-only window on a term list (an LC, or a recorded operation's slice of a buffer's arena)
+struct LCView {
+    const Term* p;
+    uint32_t n;
+    const Term* begin() const { return p; }
+    const Term* end() const { return p + n; }
+};
+
 struct LC {
-    std::vector<std::pair<Var, S>> t;
+    TermVec t;
+    LC() {}
+    LC(const LCView& v) { t.append(v.p, v.n); }
+    operator LCView() const { return {t.begin(), t.size()}; }
     static LC var(Var v) {
         LC r;
         r.t.push_back({v, s_one()});
@@ -157,15 +245,16 @@ struct LC {
         r.t.push_back({ONE_VAR, s});
         return r;
     }
-    LC operator+(const LC& o) const {
-        LC r = *this;
-        r.t.insert(r.t.end(), o.t.begin(), o.t.end());
-        return r;
+    // the left operand is taken by value: temporaries (and std::move'd accumulators) are extended in place, the way
+    // the reference's `LinearCombination + / -` consume their left side
+    friend LC operator+(LC a, const LC& o) {
+        a.t.append(o.t.begin(), o.t.size());
+        return a;
     }
-    LC operator-(const LC& o) const {
-        LC r = *this;
-        for (auto& e : o.t) r.t.push_back({e.first, s_neg(e.second)});
-        return r;
+    friend LC operator-(LC a, const LC& o) {
+        a.t.reserve(a.t.size() + o.t.size());
+        for (auto& e : o.t) a.t.push_back({e.first, s_neg(e.second)});
+        return a;
     }
     LC scale(const S& s) const {
         LC r;
@@ -175,11 +264,13 @@ struct LC {
 };
 
 // ---------------------------------------------------------------------------------------- cs_buffer.rs
+// A recorded operation.  Its linear combinations live in the owning buffer's term arena (offset, length) and the
+// assignment of an allocate_multiplier in the buffer's `vals`, so an Op is 24 bytes and recording one is two appends.
 struct Op {
-    enum Kind { MUL, ALLOC, CON, COMMIT } kind;
-    LC a, b;          // MUL: left, right ; CON: a
-    bool has = false; // ALLOC: assignment present
-    S l = sc_zero(), r = sc_zero();
+    enum Kind : uint8_t { MUL, ALLOC, CON, COMMIT } kind;
+    bool has = false;          // ALLOC: assignment present
+    uint32_t a_off = 0, a_len = 0, b_off = 0, b_len = 0;  // MUL: left, right ; CON: a
+    uint32_t val = 0;          // ALLOC: vals[val], vals[val + 1] = left, right
 };
 struct Vars3 {
     Var l, r, o;
@@ -190,18 +281,30 @@ struct Buffer {
     bool proving;
     std::vector<Op> ops;
     std::vector<std::vector<Op>> cache;
+    std::vector<Term> arena;  // shared by `ops` and every rewound clause in `cache`
+    std::vector<S> vals;
     uint32_t n_mult = 0;
     explicit Buffer(bool p) : proving(p) {}
+    LCView a_of(const Op& o) const { return {arena.data() + o.a_off, o.a_len}; }
+    LCView b_of(const Op& o) const { return {arena.data() + o.b_off, o.b_len}; }
     Vars3 alloc() {
         const uint32_t i = n_mult++;
         return {mkvar(K_LEFT, i), mkvar(K_RIGHT, i), mkvar(K_OUT, i)};
     }
-    Vars3 multiply(LC l, LC r) {
-        ops.emplace_back();
-        Op& o = ops.back();
+    uint32_t stash(const LCView& lc) {
+        if ((uint64_t)arena.size() + lc.n >= (1ull << 32)) throw Panic("constraint system too large");
+        const uint32_t off = (uint32_t)arena.size();
+        arena.insert(arena.end(), lc.p, lc.p + lc.n);
+        return off;
+    }
+    Vars3 multiply(const LCView& l, const LCView& r) {
+        Op o;
         o.kind = Op::MUL;
-        o.a = std::move(l);
-        o.b = std::move(r);
+        o.a_off = stash(l);
+        o.a_len = l.n;
+        o.b_off = stash(r);
+        o.b_len = r.n;
+        ops.push_back(o);
         return alloc();
     }
     Vars3 allocate_multiplier(bool has, const S& l, const S& r) {
@@ -209,21 +312,23 @@ struct Buffer {
         Op o;
         o.kind = Op::ALLOC;
         o.has = proving;
-        o.l = l;
-        o.r = r;
-        ops.push_back(std::move(o));
+        o.val = (uint32_t)vals.size();
+        vals.push_back(l);
+        vals.push_back(r);
+        ops.push_back(o);
         return alloc();
     }
-    void constrain(const LC& lc) {
+    void constrain(const LCView& lc) {
         Op o;
         o.kind = Op::CON;
-        o.a = lc;
-        ops.push_back(std::move(o));
+        o.a_off = stash(lc);
+        o.a_len = lc.n;
+        ops.push_back(o);
     }
     void commit_drvd() {
         Op o;
         o.kind = Op::COMMIT;
-        ops.push_back(std::move(o));
+        ops.push_back(o);
     }
     void initialize_from(const std::vector<const std::vector<Op>*>& init) {
         for (auto* v : init)
@@ -253,7 +358,7 @@ void range_proof(Buffer& cs, LC x, unsigned n, bool has, const S& x_assignment) 
         Vars3 v = cs.allocate_multiplier(has, s_u64(1 - bit), s_u64(bit));
         cs.constrain(LC::var(v.o));
         cs.constrain(LC::var(v.l) + (LC::var(v.r) - LC::cst(s_one())));
-        x = x - LC::var(v.r).scale(exp2);
+        x = std::move(x) - LC::var(v.r).scale(exp2);
         exp2 = s_add(exp2, exp2);
     }
     cs.constrain(x);
@@ -426,21 +531,21 @@ void set_membership_assemble(Buffer& cs, const LC& value, const std::vector<LC>&
 }
 
 void or_combine(Buffer& main, const Buffer& inner) {  // or_conjunction.rs:4-38
-    std::vector<std::vector<LC>> per_clause;
+    std::vector<std::vector<LCView>> per_clause;  // windows on inner's arena, which no longer changes
     for (auto& ops : inner.cache) {
-        std::vector<LC> cons;
+        std::vector<LCView> cons;
         for (auto& o : ops) {
-            if (o.kind == Op::MUL) main.multiply(o.a, o.b);
-            else if (o.kind == Op::ALLOC) main.allocate_multiplier(o.has, o.l, o.r);
-            else if (o.kind == Op::CON) cons.push_back(o.a);
+            if (o.kind == Op::MUL) main.multiply(inner.a_of(o), inner.b_of(o));
+            else if (o.kind == Op::ALLOC) main.allocate_multiplier(o.has, inner.vals[o.val], inner.vals[o.val + 1]);
+            else if (o.kind == Op::CON) cons.push_back(inner.a_of(o));
         }
         per_clause.push_back(std::move(cons));
     }
     if (per_clause.empty()) return;
-    std::vector<std::vector<const LC*>> combos;
+    std::vector<std::vector<const LCView*>> combos;
     for (auto& c : per_clause[0]) combos.push_back({&c});
     for (size_t k = 1; k < per_clause.size(); k++) {
-        std::vector<std::vector<const LC*>> nxt;
+        std::vector<std::vector<const LCView*>> nxt;
         for (auto& xs : combos)
             for (auto& y : per_clause[k]) {
                 auto v = xs;
@@ -450,7 +555,7 @@ void or_combine(Buffer& main, const Buffer& inner) {  // or_conjunction.rs:4-38
         combos.swap(nxt);
     }
     for (auto& combo : combos) {
-        LC prod = *combo[0];
+        LC prod(*combo[0]);
         for (size_t i = 1; i < combo.size(); i++) {
             Vars3 p = main.multiply(prod, *combo[i]);
             prod = LC::var(p.o);
@@ -618,9 +723,9 @@ struct Flat {
     std::vector<uint32_t> row_start{0}, term_var;
     std::vector<S> term_coef;
 
-    S eval(const LC& lc) const {
+    S eval(const LCView& lc) const {
         S acc = s_zero();
-        for (auto& e : lc.t) {
+        for (auto& e : lc) {
             const uint32_t k = e.first >> 29, i = e.first & ((1u << 29) - 1);
             S val;
             switch (k) {
@@ -636,8 +741,8 @@ struct Flat {
         }
         return acc;
     }
-    void constrain(const LC& lc, bool minus_var = false, Var var = 0) {  // lc, or lc - var
-        for (auto& e : lc.t) {
+    void constrain(const LCView& lc, bool minus_var = false, Var var = 0) {  // lc, or lc - var
+        for (auto& e : lc) {
             term_var.push_back(e.first);
             term_coef.push_back(e.second);
         }
@@ -648,28 +753,30 @@ struct Flat {
         }
         row_start.push_back((uint32_t)term_var.size());
     }
-    void replay(const std::vector<Op>& ops, bool proving) {  // assign_buffer (prove.rs:84-99 / verify.rs:75-90)
-        for (auto& o : ops) {
+    void replay(const Buffer& buf, bool proving) {  // assign_buffer (prove.rs:84-99 / verify.rs:75-90)
+        for (auto& o : buf.ops) {
             if (o.kind == Op::MUL) {
                 const uint32_t i = n;
+                const LCView oa = buf.a_of(o), ob = buf.b_of(o);
                 if (proving) {
-                    const S l = eval(o.a), r = eval(o.b);
+                    const S l = eval(oa), r = eval(ob);
                     aL.push_back(l);
                     aR.push_back(r);
                     aO.push_back(s_mul(l, r));
                 }
                 n++;
-                constrain(o.a, true, mkvar(K_LEFT, i));
-                constrain(o.b, true, mkvar(K_RIGHT, i));
+                constrain(oa, true, mkvar(K_LEFT, i));
+                constrain(ob, true, mkvar(K_RIGHT, i));
             } else if (o.kind == Op::ALLOC) {
                 if (proving) {
-                    aL.push_back(o.l);
-                    aR.push_back(o.r);
-                    aO.push_back(s_mul(o.l, o.r));
+                    const S &l = buf.vals[o.val], &r = buf.vals[o.val + 1];
+                    aL.push_back(l);
+                    aR.push_back(r);
+                    aO.push_back(s_mul(l, r));
                 }
                 n++;
             } else if (o.kind == Op::CON) {
-                constrain(o.a);
+                constrain(buf.a_of(o));
             }
         }
     }
@@ -1047,8 +1154,12 @@ void compile_prover(const char* instance, const char* witness, const char* gadge
     }
     Buffer top(true);
     Walker wk{*side, split_lines(gadgets)};
+    auto T0 = std::chrono::steady_clock::now();
     wk.run(top);
-    side->st.replay(top.ops, true);
+    auto T1 = std::chrono::steady_clock::now();
+    side->st.replay(top, true);
+    auto T2 = std::chrono::steady_clock::now();
+    if (getenv("BPG_FE_TRACE")) fprintf(stderr, "[fe] walk %.1f ms replay %.1f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count());
 }
 
 void compile_verifier(const char* instance, const char* commitments, const char* gadgets, Side* side) {
@@ -1067,7 +1178,7 @@ void compile_verifier(const char* instance, const char* commitments, const char*
     Buffer top(false);
     Walker wk{*side, split_lines(gadgets)};
     wk.run(top);
-    side->st.replay(top.ops, false);
+    side->st.replay(top, false);
 }
 
 template <typename T>
