@@ -59,7 +59,13 @@ inline S s_red(const S& a) {  // canonical representative; almost every operand 
     return sc_sub_raw(&t, a, sc_L()) != 0 ? a : sc_reduce(a);
 }
 inline S s_add(const S& a, const S& b) { return sc_add(s_red(a), s_red(b)); }
-inline S s_mul(const S& a, const S& b) { return sc_mul(a, b); }
+inline S s_mul(const S& a, const S& b) {  // 0 and 1 operands (bits, unit coefficients) skip the two Montgomery products
+    const uint32_t ta = a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7];
+    const uint32_t tb = b.v[1] | b.v[2] | b.v[3] | b.v[4] | b.v[5] | b.v[6] | b.v[7];
+    if (ta == 0 && a.v[0] <= 1) return a.v[0] ? s_red(b) : sc_zero();
+    if (tb == 0 && b.v[0] <= 1) return b.v[0] ? s_red(a) : sc_zero();
+    return sc_mul(a, b);
+}
 inline S s_neg(const S& a) { return sc_neg(s_red(a)); }
 // dalek 3.2 `&Scalar - &Scalar`: Scalar52::sub adds l ONCE on underflow and then reduces; for unreduced operands whose
 // difference is below -l the 260-bit wrap shows through (+2^260 mod l).
@@ -350,15 +356,23 @@ struct Derived {
 
 // ---------------------------------------------------------------------------------------- gadgets
 void range_proof(Buffer& cs, LC x, unsigned n, bool has, const S& x_assignment) {  // utils.rs:5-35
+    // Term lists are written out directly; they are the ones the operator forms would build:
+    //   o                          LC::var(o)
+    //   l + (r - 1)                (l, 1) (r, 1) (One, -1)
+    //   x - r * 2^i                x ... (r, -(1 * 2^i))
+    static const S ONE = s_one(), MINUS_ONE = s_neg(s_one());
     S exp2 = s_one();
     uint8_t xb[32] = {0};
     if (has) s_bytes(x_assignment, xb);
+    x.t.reserve(x.t.size() + n);
     for (unsigned i = 0; i < n; i++) {
         const uint32_t bit = has ? (xb[i / 8] >> (i % 8)) & 1u : 0u;
         Vars3 v = cs.allocate_multiplier(has, s_u64(1 - bit), s_u64(bit));
-        cs.constrain(LC::var(v.o));
-        cs.constrain(LC::var(v.l) + (LC::var(v.r) - LC::cst(s_one())));
-        x = std::move(x) - LC::var(v.r).scale(exp2);
+        const Term is_zero[1] = {{v.o, ONE}};
+        cs.constrain(LCView{is_zero, 1});
+        const Term is_bit[3] = {{v.l, ONE}, {v.r, ONE}, {ONE_VAR, MINUS_ONE}};
+        cs.constrain(LCView{is_bit, 3});
+        x.t.push_back({v.r, s_neg(s_mul(ONE, exp2))});
         exp2 = s_add(exp2, exp2);
     }
     cs.constrain(x);
@@ -714,66 +728,103 @@ MerkleLine parse_tree(const std::string& line) {
 }
 
 // ---------------------------------------------------------------------------------------- flat statement
+// malloc'd array whose ownership can be handed to the C ABI (bpg_flat_statement) without a copy
+template <typename T>
+struct Owned {
+    T* p = nullptr;
+    Owned() {}
+    Owned(const Owned&) = delete;
+    Owned& operator=(const Owned&) = delete;
+    ~Owned() { free(p); }
+    void alloc(size_t k) {
+        free(p);
+        p = (T*)malloc(sizeof(T) * (k ? k : 1));
+        if (!p) throw std::bad_alloc();
+    }
+    T* release() {
+        T* q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
 struct Flat {
     std::vector<S> v, vbl;       // prover
     std::vector<Bytes> V;        // verifier
     std::vector<std::string> com_names;
-    std::vector<S> aL, aR, aO;  // aO: prover-side cache of a_L * a_R for LC evaluation
-    uint32_t n = 0;
-    std::vector<uint32_t> row_start{0}, term_var;
-    std::vector<S> term_coef;
+    // Sized exactly from the recorded operations before the replay, written once: no growth copies, and the arrays
+    // go to the caller as they are.  (S is eight little-endian 32-bit limbs = the ABI's 32-byte scalar.)
+    Owned<S> aL, aR, aO;  // aO: prover-side cache of a_L * a_R for LC evaluation
+    uint32_t n = 0;       // multipliers assigned so far
+    Owned<uint32_t> row_start, term_var;
+    Owned<S> term_coef;
+    size_t rows = 0, nnz = 0;
 
     S eval(const LCView& lc) const {
         S acc = s_zero();
         for (auto& e : lc) {
             const uint32_t k = e.first >> 29, i = e.first & ((1u << 29) - 1);
-            S val;
+            const S* val;
+            static const S ONE = s_one();
             switch (k) {
-                case K_LEFT: if (i >= aL.size()) throw Panic("unallocated multiplier in a linear combination"); val = aL[i]; break;
-                case K_RIGHT: if (i >= aR.size()) throw Panic("unallocated multiplier in a linear combination"); val = aR[i]; break;
-                case K_OUT: if (i >= aO.size()) throw Panic("unallocated multiplier in a linear combination"); val = aO[i]; break;
-                case K_COMMITTED: if (i >= v.size()) throw Panic("unknown committed variable"); val = v[i]; break;
-                default: val = s_one();
+                case K_LEFT: if (i >= n) throw Panic("unallocated multiplier in a linear combination"); val = &aL.p[i]; break;
+                case K_RIGHT: if (i >= n) throw Panic("unallocated multiplier in a linear combination"); val = &aR.p[i]; break;
+                case K_OUT: if (i >= n) throw Panic("unallocated multiplier in a linear combination"); val = &aO.p[i]; break;
+                case K_COMMITTED: if (i >= v.size()) throw Panic("unknown committed variable"); val = &v[i]; break;
+                default: val = &ONE;
             }
             if (s_is_zero(e.second)) continue;                               // `Scalar::zero().into()` terms
-            const S term = s_eq(e.second, s_one()) ? s_red(val) : k == K_ONE ? s_red(e.second) : s_mul(e.second, val);
+            const S term = s_eq(e.second, ONE) ? s_red(*val) : k == K_ONE ? s_red(e.second) : s_mul(e.second, *val);
             acc = sc_add(acc, term);
         }
         return acc;
     }
     void constrain(const LCView& lc, bool minus_var = false, Var var = 0) {  // lc, or lc - var
-        for (auto& e : lc) {
-            term_var.push_back(e.first);
-            term_coef.push_back(e.second);
+        for (uint32_t k = 0; k < lc.n; k++) {
+            term_var.p[nnz + k] = lc.p[k].first;
+            term_coef.p[nnz + k] = lc.p[k].second;
         }
+        nnz += lc.n;
         if (minus_var) {
             static const S MINUS_ONE = s_neg(s_one());
-            term_var.push_back(var);
-            term_coef.push_back(MINUS_ONE);
+            term_var.p[nnz] = var;
+            term_coef.p[nnz] = MINUS_ONE;
+            nnz++;
         }
-        row_start.push_back((uint32_t)term_var.size());
+        row_start.p[++rows] = (uint32_t)nnz;
+    }
+    void assign(const S& l, const S& r) {
+        aL.p[n] = l;
+        aR.p[n] = r;
+        aO.p[n] = s_mul(l, r);
     }
     void replay(const Buffer& buf, bool proving) {  // assign_buffer (prove.rs:84-99 / verify.rs:75-90)
+        size_t n_total = 0, q_total = 0, nnz_total = 0;
+        for (auto& o : buf.ops) {
+            if (o.kind == Op::MUL) n_total++, q_total += 2, nnz_total += (size_t)o.a_len + o.b_len + 2;
+            else if (o.kind == Op::ALLOC) n_total++;
+            else if (o.kind == Op::CON) q_total++, nnz_total += o.a_len;
+        }
+        if (nnz_total >= (1ull << 32) || n_total >= (1u << 29)) throw Panic("constraint system too large");
+        row_start.alloc(q_total + 1);
+        term_var.alloc(nnz_total);
+        term_coef.alloc(nnz_total);
+        row_start.p[0] = 0;
+        if (proving) {
+            aL.alloc(n_total);
+            aR.alloc(n_total);
+            aO.alloc(n_total);
+        }
         for (auto& o : buf.ops) {
             if (o.kind == Op::MUL) {
                 const uint32_t i = n;
                 const LCView oa = buf.a_of(o), ob = buf.b_of(o);
-                if (proving) {
-                    const S l = eval(oa), r = eval(ob);
-                    aL.push_back(l);
-                    aR.push_back(r);
-                    aO.push_back(s_mul(l, r));
-                }
+                if (proving) assign(eval(oa), eval(ob));
                 n++;
                 constrain(oa, true, mkvar(K_LEFT, i));
                 constrain(ob, true, mkvar(K_RIGHT, i));
             } else if (o.kind == Op::ALLOC) {
-                if (proving) {
-                    const S &l = buf.vals[o.val], &r = buf.vals[o.val + 1];
-                    aL.push_back(l);
-                    aR.push_back(r);
-                    aO.push_back(s_mul(l, r));
-                }
+                if (proving) assign(buf.vals[o.val], buf.vals[o.val + 1]);
                 n++;
             } else if (o.kind == Op::CON) {
                 constrain(buf.a_of(o));
@@ -1113,6 +1164,38 @@ struct Walker {
     }
 };
 
+// The top-level buffer's arrays are kept per thread between statements (up to SCRATCH_KEEP bytes): a 2^17-multiplier
+// statement records ~45 MB of operations, and first-touch page faults on fresh allocations cost more than filling them.
+struct Scratch {
+    std::vector<Term> arena;
+    std::vector<Op> ops;
+    std::vector<S> vals;
+};
+const size_t SCRATCH_KEEP = 256u << 20;
+struct ScratchLease {
+    Buffer& b;
+    static Scratch& tls() {
+        static thread_local Scratch s;
+        return s;
+    }
+    explicit ScratchLease(Buffer& buf) : b(buf) {
+        Scratch& s = tls();
+        b.arena.swap(s.arena);
+        b.ops.swap(s.ops);
+        b.vals.swap(s.vals);
+    }
+    ~ScratchLease() {
+        Scratch& s = tls();
+        b.arena.clear();
+        b.ops.clear();
+        b.vals.clear();
+        if (b.arena.capacity() * sizeof(Term) + b.ops.capacity() * sizeof(Op) + b.vals.capacity() * sizeof(S) > SCRATCH_KEEP) return;
+        b.arena.swap(s.arena);
+        b.ops.swap(s.ops);
+        b.vals.swap(s.vals);
+    }
+};
+
 std::function<S(uint64_t)> blinding_stream(const uint8_t seed[32]) {
     Bytes s(seed, seed + 32);
     return [s](uint64_t k) {
@@ -1153,6 +1236,7 @@ void compile_prover(const char* instance, const char* witness, const char* gadge
         side->witness[kv.first] = w;
     }
     Buffer top(true);
+    ScratchLease lease(top);
     Walker wk{*side, split_lines(gadgets)};
     auto T0 = std::chrono::steady_clock::now();
     wk.run(top);
@@ -1176,6 +1260,7 @@ void compile_verifier(const char* instance, const char* commitments, const char*
         side->st.com_names.push_back(kv.first);
     }
     Buffer top(false);
+    ScratchLease lease(top);
     Walker wk{*side, split_lines(gadgets)};
     wk.run(top);
     side->st.replay(top, false);
@@ -1193,24 +1278,24 @@ uint8_t* dup_scalars(const std::vector<S>& v) {
     return p;
 }
 
-bpg_flat_statement* export_flat(const Flat& st, bool proving) {
+bpg_flat_statement* export_flat(Flat& st, bool proving) {  // hands the statement's arrays over
     bpg_flat_statement* f = (bpg_flat_statement*)calloc(1, sizeof(bpg_flat_statement));
     f->n = st.n;
     f->m = proving ? st.v.size() : st.V.size();
-    f->q = st.row_start.size() - 1;
-    f->nnz = st.term_var.size();
+    f->q = st.rows;
+    f->nnz = st.nnz;
     if (proving) {
         f->v32m = dup_scalars(st.v);
         f->vbl32m = dup_scalars(st.vbl);
-        f->aL32n = dup_scalars(st.aL);
-        f->aR32n = dup_scalars(st.aR);
+        f->aL32n = reinterpret_cast<uint8_t*>(st.aL.release());
+        f->aR32n = reinterpret_cast<uint8_t*>(st.aR.release());
     } else {
         f->V32m = (uint8_t*)malloc(32 * (st.V.size() ? st.V.size() : 1));
         for (size_t i = 0; i < st.V.size(); i++) memcpy(f->V32m + 32 * i, st.V[i].data(), 32);
     }
-    f->row_start = dup(st.row_start);
-    f->term_var = dup(st.term_var);
-    f->term_coef32 = dup_scalars(st.term_coef);
+    f->row_start = st.row_start.release();
+    f->term_var = st.term_var.release();
+    f->term_coef32 = reinterpret_cast<uint8_t*>(st.term_coef.release());
     std::string names;
     for (auto& n : st.com_names) names += n + "\n";
     f->com_names = strdup(names.c_str());
@@ -1303,13 +1388,14 @@ int bpg_prove(bpg_ctx* ctx, const char* name, const char* instance, const char* 
         std::vector<uint8_t> V(32 * (st.v.size() ? st.v.size() : 1)), proof(1 + 14 * 32 + 66 * 32);
         size_t proof_len = 0;
         if (!rc) {
-            uint8_t *v = dup_scalars(st.v), *vb = dup_scalars(st.vbl), *aL = dup_scalars(st.aL), *aR = dup_scalars(st.aR),
-                    *coef = dup_scalars(st.term_coef);
+            uint8_t *v = dup_scalars(st.v), *vb = dup_scalars(st.vbl);
+            const uint8_t *aL = reinterpret_cast<const uint8_t*>(st.aL.p), *aR = reinterpret_cast<const uint8_t*>(st.aR.p),
+                          *coef = reinterpret_cast<const uint8_t*>(st.term_coef.p);
             // every commitment precedes every challenge, so one batched launch keeps the transcript order
             rc = bpg_prover_commit_batch(p, v, vb, st.v.size(), V.data(), nullptr);
-            if (!rc) rc = bpg_prover_load_cs(p, aL, aR, st.n, st.row_start.data(), st.term_var.data(), coef, st.row_start.size() - 1);
+            if (!rc) rc = bpg_prover_load_cs(p, aL, aR, st.n, st.row_start.p, st.term_var.p, coef, st.rows);
             if (!rc) rc = bpg_prover_prove(p, rng_seed32, proof.data(), proof.size(), &proof_len);
-            free(v), free(vb), free(aL), free(aR), free(coef);
+            free(v), free(vb);
         }
         if (p) bpg_prover_free(p);
         bpg_transcript_free(t);
@@ -1329,7 +1415,7 @@ int bpg_prove(bpg_ctx* ctx, const char* name, const char* instance, const char* 
         a->proof = (uint8_t*)malloc(proof_len ? proof_len : 1);
         memcpy(a->proof, proof.data(), proof_len);
         a->proof_len = proof_len;
-        a->num_constraints = st.row_start.size() - 1;
+        a->num_constraints = st.rows;
         *out = a;
         return BPG_OK;
     });
@@ -1349,11 +1435,10 @@ int bpg_verify(bpg_ctx* ctx, const char* name, const char* instance, const char*
         if (!rc) {
             std::vector<uint8_t> V(32 * (st.V.size() ? st.V.size() : 1));
             for (size_t i = 0; i < st.V.size(); i++) memcpy(&V[32 * i], st.V[i].data(), 32);
-            uint8_t* coef = dup_scalars(st.term_coef);
+            const uint8_t* coef = reinterpret_cast<const uint8_t*>(st.term_coef.p);
             rc = bpg_verifier_commit_batch(v, V.data(), st.V.size(), nullptr);
-            if (!rc) rc = bpg_verifier_load_cs(v, st.n, st.row_start.data(), st.term_var.data(), coef, st.row_start.size() - 1);
+            if (!rc) rc = bpg_verifier_load_cs(v, st.n, st.row_start.p, st.term_var.p, coef, st.rows);
             if (!rc) rc = bpg_verifier_verify(v, proof, proof_len, rng_seed32);
-            free(coef);
         }
         if (v) bpg_verifier_free(v);
         bpg_transcript_free(t);

@@ -41,6 +41,17 @@ BPG_HD sc sc_RR() {
 
 // r = a - b, returns borrow (0/1)
 BPG_HD uint32_t sc_sub_raw(sc* r, const sc& a, const sc& b) {
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__) && !defined(BPG_SC_PORTABLE)
+    unsigned __int128 bw = 0;  // host: four 64-bit limbs
+    for (int i = 0; i < 4; i++) {
+        const uint64_t x = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32), y = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+        const unsigned __int128 d = (unsigned __int128)x - y - bw;
+        r->v[2 * i] = (uint32_t)d;
+        r->v[2 * i + 1] = (uint32_t)((uint64_t)d >> 32);
+        bw = (d >> 64) & 1;
+    }
+    return (uint32_t)bw;
+#else
     int64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -49,8 +60,20 @@ BPG_HD uint32_t sc_sub_raw(sc* r, const sc& a, const sc& b) {
         c >>= 32;
     }
     return (uint32_t)(c & 1);
+#endif
 }
 BPG_HD uint32_t sc_add_raw(sc* r, const sc& a, const sc& b) {
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__) && !defined(BPG_SC_PORTABLE)
+    unsigned __int128 cy = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint64_t x = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32), y = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+        cy += (unsigned __int128)x + y;
+        r->v[2 * i] = (uint32_t)cy;
+        r->v[2 * i + 1] = (uint32_t)((uint64_t)cy >> 32);
+        cy >>= 64;
+    }
+    return (uint32_t)cy;
+#else
     uint64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -59,6 +82,7 @@ BPG_HD uint32_t sc_add_raw(sc* r, const sc& a, const sc& b) {
         c >>= 32;
     }
     return (uint32_t)c;
+#endif
 }
 BPG_HD sc sc_select(bool c, const sc& a, const sc& b) {
     sc r;
