@@ -319,8 +319,10 @@ struct Buffer {
         o.kind = Op::ALLOC;
         o.has = proving;
         o.val = (uint32_t)vals.size();
-        vals.push_back(l);
-        vals.push_back(r);
+        if (proving) {  // a verifier's buffer never reads assignments
+            vals.push_back(l);
+            vals.push_back(r);
+        }
         ops.push_back(o);
         return alloc();
     }
@@ -361,7 +363,16 @@ void range_proof(Buffer& cs, LC x, unsigned n, bool has, const S& x_assignment) 
     //   l + (r - 1)                (l, 1) (r, 1) (One, -1)
     //   x - r * 2^i                x ... (r, -(1 * 2^i))
     static const S ONE = s_one(), MINUS_ONE = s_neg(s_one());
-    S exp2 = s_one();
+    static const std::vector<S> NEG_POW2 = [] {  // -(1 * 2^i) along the reference's doubling chain exp2 = exp2 + exp2
+        std::vector<S> t;
+        S exp2 = s_one();
+        for (int i = 0; i < 256; i++) {
+            t.push_back(s_neg(s_mul(s_one(), exp2)));
+            exp2 = s_add(exp2, exp2);
+        }
+        return t;
+    }();
+    if (n > NEG_POW2.size()) throw Panic("range proof wider than 256 bits");
     uint8_t xb[32] = {0};
     if (has) s_bytes(x_assignment, xb);
     x.t.reserve(x.t.size() + n);
@@ -372,8 +383,7 @@ void range_proof(Buffer& cs, LC x, unsigned n, bool has, const S& x_assignment) 
         cs.constrain(LCView{is_zero, 1});
         const Term is_bit[3] = {{v.l, ONE}, {v.r, ONE}, {ONE_VAR, MINUS_ONE}};
         cs.constrain(LCView{is_bit, 3});
-        x.t.push_back({v.r, s_neg(s_mul(ONE, exp2))});
-        exp2 = s_add(exp2, exp2);
+        x.t.push_back({v.r, NEG_POW2[i]});
     }
     cs.constrain(x);
 }
@@ -550,7 +560,10 @@ void or_combine(Buffer& main, const Buffer& inner) {  // or_conjunction.rs:4-38
         std::vector<LCView> cons;
         for (auto& o : ops) {
             if (o.kind == Op::MUL) main.multiply(inner.a_of(o), inner.b_of(o));
-            else if (o.kind == Op::ALLOC) main.allocate_multiplier(o.has, inner.vals[o.val], inner.vals[o.val + 1]);
+            else if (o.kind == Op::ALLOC) {
+                if (inner.proving) main.allocate_multiplier(o.has, inner.vals[o.val], inner.vals[o.val + 1]);
+                else main.allocate_multiplier(o.has, s_zero(), s_zero());
+            }
             else if (o.kind == Op::CON) cons.push_back(inner.a_of(o));
         }
         per_clause.push_back(std::move(cons));
@@ -1262,8 +1275,12 @@ void compile_verifier(const char* instance, const char* commitments, const char*
     Buffer top(false);
     ScratchLease lease(top);
     Walker wk{*side, split_lines(gadgets)};
+    auto T0 = std::chrono::steady_clock::now();
     wk.run(top);
+    auto T1 = std::chrono::steady_clock::now();
     side->st.replay(top, false);
+    auto T2 = std::chrono::steady_clock::now();
+    if (getenv("BPG_FE_TRACE")) fprintf(stderr, "[fe] verifier walk %.1f ms replay %.1f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count());
 }
 
 template <typename T>

@@ -104,6 +104,17 @@ def _hex(b):
     return "0x" + bytes(b).hex()
 
 
+def bounds_check_text(count=1024, max_bytes=8, seed=20261018):
+    """The same workload as bounds_check_statement in the reference's text formats: `count` lines  BOUND W<i> I0 I1
+    (/root/reference/src/bounds_check/bounds_check_gadget.rs:13-64).  Returns (gadgets, inst, wtns)."""
+    rng = np.random.default_rng(seed)
+    vals = [rng.integers(0, 256, size=max_bytes, dtype=np.uint8).tobytes() for _ in range(count)]
+    inst = "I0 = 0x00\nI1 = 0x%s\n" % ("ff" * max_bytes)
+    wtns = "".join("W%d = %s\n" % (i, _hex(v)) for i, v in enumerate(vals))
+    gadgets = "".join("BOUND W%d I0 I1\n" % i for i in range(count))
+    return gadgets, inst, wtns
+
+
 def merkle_text(depth=32, seed=20261018, witness_siblings=False):
     """BASELINE config 3: `MERKLE I0 (((..(W0 I1) I2)..) I<depth>)` -- membership of leaf W0 under root I0 with MiMC
     (/root/reference/src/merkle_tree/merkle_tree_gadget.rs:39-114, /root/reference/src/prove.rs:289-321).
