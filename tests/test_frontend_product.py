@@ -122,3 +122,87 @@ def test_front_end_errors_match_oracle_panics(lib, case):
     assert (rc == 0) == oracle_ok, (rc, msg)
     if not oracle_ok:
         assert rc == _capi.E_GADGET and msg.startswith("front end:")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# random statements: every gadget kind, nested OR blocks, variables of 1..40 bytes (multi-limb variables take the hashing
+# and panic paths).  The C++ front end must agree with the oracle's on the flat circuit, or both must reject the input.
+def _random_statement(seed):
+    rng = np.random.default_rng(seed)
+    n_i, n_w = int(rng.integers(2, 6)), int(rng.integers(2, 6))
+
+    def val():
+        k = int(rng.choice([1, 2, 8, 15, 31, 32, 33, 40], p=[.2, .15, .2, .1, .1, .1, .1, .05]))
+        b = rng.integers(0, 256, size=k, dtype=np.uint8).tobytes()
+        return b if b.strip(b"\0") else b"\x01" + b[1:]
+
+    pool = [val() for _ in range(3)]           # repeated values make EQUALS / SET_MEMBER hit
+    pick = lambda: pool[int(rng.integers(0, len(pool)))] if rng.random() < 0.4 else val()
+    inst = "".join("I%d = 0x%s\n" % (i, pick().hex()) for i in range(n_i))
+    wtns = "".join("W%d = 0x%s\n" % (i, pick().hex()) for i in range(n_w))
+    I = lambda: "I%d" % int(rng.integers(0, n_i))
+    Wv = lambda: "W%d" % int(rng.integers(0, n_w))
+    any_v = lambda: I() if rng.random() < 0.5 else Wv()
+
+    def tree(depth):
+        kids = []
+        for _ in range(2):
+            kids.append(tree(depth - 1) if depth > 0 and rng.random() < 0.4 else any_v())
+        return "(%s %s)" % (kids[0], kids[1])
+
+    def line(in_or):
+        # range proofs inside OR clauses multiply into 10^5+ product constraints (or_conjunction.rs:20-37): top level only
+        k = int(rng.choice([1, 2, 3, 5, 6])) if in_or else int(rng.integers(0, 7))
+        if k == 0:
+            return "BOUND %s %s %s" % (Wv(), I(), I())
+        if k == 1:
+            return "HASH %s %s" % (any_v(), Wv())
+        if k == 2:
+            a, b = (Wv(), any_v()) if rng.random() < 0.7 else (I(), Wv())
+            return "EQUALS %s %s" % (a, b)
+        if k == 3:
+            a, b = (Wv(), any_v()) if rng.random() < 0.7 else (I(), Wv())
+            return "UNEQUAL %s %s" % (a, b)
+        if k == 4:
+            return "LESS_THAN %s %s" % (Wv(), Wv())
+        if k == 5:
+            return "SET_MEMBER %s %s" % (any_v(), " ".join(any_v() for _ in range(int(rng.integers(1, 4)))))
+        return "MERKLE %s %s" % (any_v(), tree(1))
+
+    def block(depth):
+        out = []
+        for _ in range(int(rng.integers(1, 3))):
+            if depth < 2 and rng.random() < 0.3:
+                out += ["OR", "["]
+                for _ in range(int(rng.integers(1, 4))):
+                    out += ["{"] + block(depth + 1) + ["}"]
+                out += ["]"]
+            else:
+                out.append(line(depth > 0))
+        return out
+
+    return "\n".join(block(0)) + "\n", inst, wtns
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_random_statements_agree_with_oracle(lib, seed):
+    gad, inst, wtns = _random_statement(1000 + seed)
+    bseed = bytes([seed % 255 + 1]) * 32
+    try:
+        st = F.compile_prover("rnd", inst, wtns, gad, _c_blinding(bseed))
+    except F.FrontendPanic:
+        st = None
+    rc, d = _c_flat(lib, "prover", "rnd", inst, wtns, gad, bseed)
+    assert (rc == 0) == (st is not None), (gad, inst, wtns, rc, d if rc else "")
+    if st is None:
+        assert rc == _capi.E_GADGET
+        return
+    _assert_same_prover(d, st)
+    text = st.coms_text([bytes([(7 * i + seed) % 251]) * 32 for i in range(st.m)])
+    vs = F.compile_verifier("rnd", inst, text, gad)
+    rc, dv = _c_flat(lib, "verifier", "rnd", inst, text, gad)
+    assert rc == 0, dv
+    assert (dv["n"], dv["m"], dv["q"], dv["nnz"]) == (vs.n, vs.m, vs.q, vs.nnz)
+    assert dv["V"] == b"".join(vs.V) and dv["names"] == vs.com_names
+    assert (dv["row_start"] == vs.row_start).all() and (dv["term_var"][: vs.nnz] == vs.term_var[: vs.nnz]).all()
+    assert _canon(dv["term_coef"]) == _canon(vs.term_coef[: 32 * vs.nnz])
