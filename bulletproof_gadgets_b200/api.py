@@ -462,8 +462,8 @@ def _take_flat(out, proving, label):
     st.vbl = [int.from_bytes(st.vbl_bytes[32 * i: 32 * i + 32], "little") for i in range(m)] if proving else []
     st.V = [get(f.V32m, 32 * m)[32 * i: 32 * i + 32] for i in range(m)] if not proving else []
     st.aL, st.aR = (get(f.aL32n, 32 * n), get(f.aR32n, 32 * n)) if proving else (b"", b"")
-    st.row_start = np.frombuffer(get(f.row_start, 4 * (q + 1)), dtype=np.uint32).copy()
-    st.term_var = np.frombuffer(get(f.term_var, 4 * nnz), dtype=np.uint32).copy() if nnz else np.zeros(1, dtype=np.uint32)
+    st.row_start = np.ctypeslib.as_array(f.row_start, shape=(q + 1,)).copy()      # one copy out of the C arrays
+    st.term_var = np.ctypeslib.as_array(f.term_var, shape=(nnz,)).copy() if nnz else np.zeros(1, dtype=np.uint32)
     st.term_coef = get(f.term_coef32, 32 * nnz) or bytes(32)
     st.com_names = f.com_names.decode().split("\n")[:-1]
     lib().bpg_flat_statement_free(out)
