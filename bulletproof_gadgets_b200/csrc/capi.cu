@@ -104,6 +104,13 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
     CUDA_TRY(cudaEventCreate(&ctx->ev_d));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
+    if (const char* e = getenv("BPG_REDUCE")) {  // "threads,blocks" of k_reduce_chunks, for A/B measurements
+        int t = 0, b = 0;
+        if (sscanf(e, "%d,%d", &t, &b) == 2 && (t == 32 || t == 64) && b >= 1 && b <= REDUCE_BLOCKS_MAX) {
+            ctx->reduce_threads = t;
+            ctx->reduce_blocks = b;
+        }
+    }
     *out = ctx;
     return BPG_OK;
 }
@@ -141,7 +148,11 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
         parent->store->refs++;
     }
     int rc = ctx_new(parent->device, parent->store, out);
-    if (rc == BPG_OK) (*out)->task_len = parent->task_len;
+    if (rc == BPG_OK) {
+        (*out)->task_len = parent->task_len;
+        (*out)->reduce_threads = parent->reduce_threads;
+        (*out)->reduce_blocks = parent->reduce_blocks;
+    }
     return rc;
 }
 
@@ -191,6 +202,12 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
     if (k == "task_len") {
         if (value < 1 || value > 255) return BPG_E_ARG;
         ctx->task_len = (int)value;
+    } else if (k == "reduce_threads") {
+        if (value != 32 && value != 64) return BPG_E_ARG;
+        ctx->reduce_threads = (int)value;
+    } else if (k == "reduce_blocks") {
+        if (value < 1 || value > REDUCE_BLOCKS_MAX) return BPG_E_ARG;
+        ctx->reduce_blocks = (int)value;
     } else if (k == "window_bits") {
         if (value != 0 && (value < 4 || value > 16)) return BPG_E_ARG;
         GensStore* g = ctx->store;

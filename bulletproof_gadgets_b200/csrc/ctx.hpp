@@ -89,6 +89,7 @@ struct GensStore {
     int refs = 1;
 };
 
+#define REDUCE_BLOCKS_MAX 1024
 struct MsmWork {
     DevBuf<uint32_t> hist;          // [nsets*nb] counts, then reused as scatter cursors
     DevBuf<uint32_t> bucket_off;    // [nsets*nb + 1] exclusive scan of the counts
@@ -96,7 +97,7 @@ struct MsmWork {
     DevBuf<uint32_t> entries;       // [K*N] (row | sign << 31), sorted by bucket
     DevBuf<ge_ext> partials;        // slot (chunk t, bucket b) = t + b
     DevBuf<uint32_t> slot_bucket;   // bucket of each used partial slot (0xffffffff = unused)
-    DevBuf<ge_ext> blockres;        // [nsets][REDUCE_BLOCKS]
+    DevBuf<ge_ext> blockres;        // [nsets][reduce_blocks <= REDUCE_BLOCKS_MAX]
     DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan
 };
 
@@ -116,6 +117,7 @@ struct bpg_ctx {
     ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu); snapshot
     struct ProofWork* pw = nullptr;  // reusable device vectors of the R1CS driver (r1cs.cu)
     int task_len = 32;
+    int reduce_threads = 64, reduce_blocks = 128;  // k_reduce_chunks geometry (msm.cu); 32 x 256 = one-warp CTAs
     // counters for bench.py ("gpu_launches")
     uint64_t launches = 0;
     // timing of the dominant kernel (accumulate), CUDA events on ctx stream

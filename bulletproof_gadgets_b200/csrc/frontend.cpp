@@ -1184,7 +1184,7 @@ struct Scratch {
     std::vector<Op> ops;
     std::vector<S> vals;
 };
-const size_t SCRATCH_KEEP = 256u << 20;
+const size_t SCRATCH_KEEP = 128u << 20;
 struct ScratchLease {
     Buffer& b;
     static Scratch& tls() {

@@ -26,10 +26,8 @@
 #include "circuit.hpp"
 #include "ctx.hpp"
 
-#define REDUCE_BLOCKS 128
 #define FINAL_THREADS 128
 #define SMALL_MSM_MAX_POINTS 4096u  // MSMs up to 2 x this many points use the 8-bit-window table
-#define REDUCE_THREADS 64
 #define ACC_THREADS 128
 
 // ------------------------------------------------------------------------------------------
@@ -245,19 +243,20 @@ __device__ __forceinline__ void block_tree_reduce(ge_ext* sh, ge_ext& mine, uint
 // digit-1 bucket of a 0/1-valued a_L vector -- spreads over many threads).  Walking down from the top slot with
 // running sums:  invariant  S + w_prev * R = sum of weight * partial over the slots seen so far.
 #define SLOT_EMPTY 0xffffffffu
-__global__ void __launch_bounds__(REDUCE_THREADS)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
     k_reduce_chunks(const ge_ext* __restrict__ partials, const uint32_t* __restrict__ slot_bucket,
                     const uint32_t* __restrict__ bucket_off, uint32_t nb, uint32_t nsets, uint32_t CL,
                     ge_ext* __restrict__ blockres) {
-    __shared__ ge_ext sh[REDUCE_THREADS];
+    __shared__ ge_ext sh[THREADS];
     const uint32_t s = blockIdx.y;
     const uint32_t G = nb * nsets, base = s * nb;
     const uint32_t E = bucket_off[G];
     const uint32_t p0 = bucket_off[base] / CL + base;
     const uint32_t p1 = s + 1 < nsets ? bucket_off[base + nb] / CL + base + nb : (E + CL - 1) / CL + G;
-    const uint32_t nthreads = REDUCE_BLOCKS * REDUCE_THREADS;
+    const uint32_t nthreads = gridDim.x * THREADS;
     const uint32_t per = (p1 - p0 + nthreads - 1) / nthreads;
-    const uint32_t cidx = blockIdx.x * REDUCE_THREADS + threadIdx.x;
+    const uint32_t cidx = blockIdx.x * THREADS + threadIdx.x;
     const uint64_t lo64 = (uint64_t)p0 + (uint64_t)cidx * per;
     ge_ext total = ge_identity();
     if (per > 0 && lo64 < p1) {
@@ -283,18 +282,18 @@ __global__ void __launch_bounds__(REDUCE_THREADS)
         }
         if (wprev) total = ge_add(S, ge_mul_small(R, wprev));
     }
-    block_tree_reduce(sh, total, threadIdx.x, REDUCE_THREADS);
-    if (threadIdx.x == 0) store_ext(blockres + s * REDUCE_BLOCKS + blockIdx.x, load_ext(sh));
+    block_tree_reduce(sh, total, threadIdx.x, THREADS);
+    if (threadIdx.x == 0) store_ext(blockres + s * gridDim.x + blockIdx.x, load_ext(sh));
 }
 
-__global__ void __launch_bounds__(FINAL_THREADS) k_reduce_final(const ge_ext* __restrict__ blockres,
+__global__ void __launch_bounds__(FINAL_THREADS) k_reduce_final(const ge_ext* __restrict__ blockres, uint32_t nblocks,
                                                                  ge_ext* __restrict__ result) {
     __shared__ ge_ext sh[FINAL_THREADS];
     const uint32_t s = blockIdx.x;
-    ge_ext mine = load_ext(blockres + s * REDUCE_BLOCKS + threadIdx.x);
+    ge_ext mine = threadIdx.x < nblocks ? load_ext(blockres + s * nblocks + threadIdx.x) : ge_identity();
 #pragma unroll 1
-    for (uint32_t k = threadIdx.x + FINAL_THREADS; k < REDUCE_BLOCKS; k += FINAL_THREADS)
-        mine = ge_add(mine, load_ext(blockres + s * REDUCE_BLOCKS + k));
+    for (uint32_t k = threadIdx.x + FINAL_THREADS; k < nblocks; k += FINAL_THREADS)
+        mine = ge_add(mine, load_ext(blockres + s * nblocks + k));
     block_tree_reduce(sh, mine, threadIdx.x, FINAL_THREADS);
     if (threadIdx.x == 0) store_ext(result + s, load_ext(sh));
 }
@@ -355,7 +354,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     int rc;
     if ((rc = w.hist.ensure(G + 1)) || (rc = w.bucket_off.ensure(G + 2)) || (rc = w.chunk_bucket.ensure(max_chunks + 1)) ||
         (rc = w.entries.ensure(max_entries + 1)) || (rc = w.partials.ensure(max_partials)) || (rc = w.slot_bucket.ensure(max_partials)) ||
-        (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS)) || (rc = w.scan_tmp.ensure(G / 2048 + 4)))
+        (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS_MAX)) || (rc = w.scan_tmp.ensure(G / 2048 + 4)))
         return rc;
 
     CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));
@@ -386,9 +385,12 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_b, st));
         ctx->launches++;
     }
-    k_reduce_chunks<<<dim3(REDUCE_BLOCKS, nsets), REDUCE_THREADS, 0, st>>>(w.partials.p, w.slot_bucket.p, w.bucket_off.p, nb, nsets,
-                                                                          T, w.blockres.p);
-    k_reduce_final<<<nsets, FINAL_THREADS, 0, st>>>(w.blockres.p, d_out);
+    const uint32_t rblocks = (uint32_t)ctx->reduce_blocks;
+    if (ctx->reduce_threads == 32)
+        k_reduce_chunks<32><<<dim3(rblocks, nsets), 32, 0, st>>>(w.partials.p, w.slot_bucket.p, w.bucket_off.p, nb, nsets, T, w.blockres.p);
+    else
+        k_reduce_chunks<64><<<dim3(rblocks, nsets), 64, 0, st>>>(w.partials.p, w.slot_bucket.p, w.bucket_off.p, nb, nsets, T, w.blockres.p);
+    k_reduce_final<<<nsets, FINAL_THREADS, 0, st>>>(w.blockres.p, rblocks, d_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     if (ctx->time_accum) {  // diagnostic mode: synchronous, reads back the entry count
