@@ -165,7 +165,10 @@ def main():
     from bulletproof_gadgets_b200 import build, workloads as W
     build.build_lib()
     warmup = max(args.warmup, 3)
-    inflight = args.inflight or 32   # host threads mostly block (GPU waits, rng batcher): not tied to the core count
+    # Host threads mostly block (GPU waits, rng batcher).  Measured on one B200 with 16 vCPUs: 24 / 32 / 48 / 64 in flight
+    # = 72 / 79 / 92 / 92 prove+verify/s (profiles/r01_summary.md); the 8-GPU box has 4 vCPUs per rank and was measured
+    # at 32, so the larger default is used only where a rank has the cores for it.
+    inflight = args.inflight or (48 if (os.cpu_count() or 1) // ws >= 12 else 32)
     ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
     ctxs = [ctx0] + [ctx0.shared() for _ in range(inflight - 1)]
     st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank).pin(bpg)
