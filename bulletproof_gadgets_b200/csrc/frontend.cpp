@@ -832,7 +832,11 @@ struct Flat {
             if (o.kind == Op::MUL) {
                 const uint32_t i = n;
                 const LCView oa = buf.a_of(o), ob = buf.b_of(o);
-                if (proving) assign(eval(oa), eval(ob));
+                if (proving) {
+                    const S l = eval(oa);  // `multiply(t, t)` (every MiMC round's square) records the same terms twice
+                    const bool same = oa.n == ob.n && memcmp(oa.p, ob.p, sizeof(Term) * oa.n) == 0;
+                    assign(l, same ? l : eval(ob));
+                }
                 n++;
                 constrain(oa, true, mkvar(K_LEFT, i));
                 constrain(ob, true, mkvar(K_RIGHT, i));
