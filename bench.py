@@ -2,9 +2,10 @@
 """bench.py -- BASELINE.json headline: R1CS prove & verify per second on B200 (config 2:
 `BOUND` 64-bit range statements x1024 in ONE R1CS proof, n = 2^17 multipliers, m = 3072 commitments).
 
-One "step" = one pass of the hot path over one BATCH of PROOFS_PER_STEP = 8 independent statements (eight is the
-width at which the library runs the provers' Merlin rng streams in lockstep); each statement costs m Pedersen
-commitments + Prover::prove + Verifier::verify (accepting).  value = steps x 8 / time, in proofs per second.  Legs:
+One "step" = one pass of the hot path over one BATCH of PROOFS_PER_STEP = 16 independent statements (two rounds of the
+eight-wide lockstep in which the library runs the provers' Merlin rng streams); each statement costs m Pedersen
+commitments + Prover::prove + Verifier::verify (accepting).  value = steps x 16 / time, in proofs per second.  With
+the default 8 steps the timed region holds 128 statements, so the drain of the last <= 48 in flight weighs little.  Legs:
   value  constraint system and witness already resident in HBM (bpg_circuit); proofs verified inside
          the timed region.  `inflight` host threads (one bpg context = one stream each, generator
          tables shared) keep several independent steps in flight on the GPU, because the prover's
@@ -38,7 +39,7 @@ WORKLOAD = "bounds_check 64-bit x1024 in one R1CS proof (n=2^17 multipliers, m=3
 # IMAD.WIDE.U32 issue rate, the instruction the field multiplication is built from
 IMAD_WIDE_PEAK_TOPS = 8.157
 IMAD_PER_MADD = 504  # 7 field muls x (64 + 8) 32x32->64 multiply-adds, SURVEY.md 8(d)
-PROOFS_PER_STEP = 8  # statements per step (one batch); every statement is proven and verified
+PROOFS_PER_STEP = 16  # statements per step (one batch); every statement is proven and verified
 try:
     HBM_PEAK_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:  # noqa: BLE001
@@ -244,7 +245,7 @@ def main():
             raise errs[0]
 
     def timed(fn, steps, warm, use_ctxs):   # `steps` here = number of statements
-        run_steps(fn, 0, max(warm, len(use_ctxs)), use_ctxs)
+        run_steps(fn, 0, max(warm * PROOFS_PER_STEP, len(use_ctxs)) if len(use_ctxs) > 1 else warm, use_ctxs)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(streams[0])
@@ -342,7 +343,7 @@ def main():
                 "frac_of_imad_peak_whole_msm": 16 * npts * IMAD_PER_MADD / msm_s / (IMAD_WIDE_PEAK_TOPS * 1e12),
                 "note": "one GPU; sweep 2^10..2^22 in profiles/r01_configs_1gpu.jsonl (tools/bench_configs.py)"},
         "gpu_launches": launches,
-        "host": {"cores": os.cpu_count(), "cpu_s_per_proof_rank0": cpu_res / (nproofs + max(warmup, inflight)),
+        "host": {"cores": os.cpu_count(), "cpu_s_per_proof_rank0": cpu_res / (nproofs + max(warmup * PROOFS_PER_STEP, inflight)),
                  "rng_streams": stat1[0] - stat0[0], "rng_vector_batches": stat1[1] - stat0[1],
                  "rng_streams_alone": stat1[2] - stat0[2],
                  "thread_cpu_s_total_all_legs": cpu_parts,
