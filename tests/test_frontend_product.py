@@ -206,3 +206,38 @@ def test_random_statements_agree_with_oracle(lib, seed):
     assert dv["V"] == b"".join(vs.V) and dv["names"] == vs.com_names
     assert (dv["row_start"] == vs.row_start).all() and (dv["term_var"][: vs.nnz] == vs.term_var[: vs.nnz]).all()
     assert _canon(dv["term_coef"]) == _canon(vs.term_coef[: 32 * vs.nnz])
+
+
+def test_front_end_is_thread_safe(lib):
+    """The front end keeps per-thread scratch between statements; concurrent callers must get what a lone caller gets."""
+    import threading
+    cases = [_random_statement(1000 + s) for s in (0, 1, 2, 3, 5, 6, 7, 8)]
+    seeds = [bytes([k + 1]) * 32 for k in range(len(cases))]
+
+    def flat(k):
+        gad, inst, wtns = cases[k]
+        rc, d = _c_flat(lib, "prover", "rnd", inst, wtns, gad, seeds[k])
+        return rc, (d if rc else (d["n"], d["q"], d["aL"], d["aR"], d["term_coef"], d["term_var"].tobytes(), d["v"], d["vbl"]))
+
+    alone = [flat(k) for k in range(len(cases))]
+    got, errs = {}, []
+
+    def work(t):
+        try:
+            for rep in range(6):
+                k = (t + rep) % len(cases)
+                got[(t, rep)] = (k, flat(k))
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs
+    for (t, rep), (k, res) in got.items():
+        if alone[k][0]:
+            assert res[0] == alone[k][0]
+        else:
+            assert res == alone[k], (t, rep, k)
