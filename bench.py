@@ -80,6 +80,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def _thread_cpu_by_name():
+    """CPU seconds of the threads still alive at the end of the run, grouped by thread name (driver / runtime threads;
+    the per-statement host threads have exited and are accounted by cpu_s_per_proof_worker_threads)."""
+    out, tick = {}, os.sysconf("SC_CLK_TCK")
+    try:
+        for tid in os.listdir("/proc/self/task"):
+            with open("/proc/self/task/%s/stat" % tid) as f:
+                raw = f.read()
+            name = raw[raw.index("(") + 1: raw.rindex(")")]
+            rest = raw[raw.rindex(")") + 2:].split()
+            out[name] = out.get(name, 0.0) + (int(rest[11]) + int(rest[12])) / tick
+    except OSError:
+        pass
+    return {k: round(v, 3) for k, v in sorted(out.items(), key=lambda kv: -kv[1])[:8]}
+
+
 def run_reference(args, ws, rank):
     """CPU restatement (oracle/c) on all host cores; bounded sample: BOUND x128 per worker per step."""
     if rank != 0:
@@ -216,6 +232,8 @@ def main():
         if ws > 1:
             dist.barrier()
 
+    worker_cpu = [0.0]
+
     def run_steps(fn, first, count, use_ctxs):
         """`count` steps spread over the contexts: each host thread pulls the next step index."""
         if len(use_ctxs) == 1:
@@ -235,6 +253,9 @@ def main():
                     fn(c, i)
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
+            finally:
+                with lock:
+                    worker_cpu[0] += time.thread_time()   # CPU of this host thread (python + C ABI inside it)
 
         ts = [threading.Thread(target=work, args=(c,)) for c in use_ctxs]
         for t in ts:
@@ -271,6 +292,7 @@ def main():
     nproofs = args.steps * PROOFS_PER_STEP
     ms_res = timed(step_resident, nproofs, warmup, ctxs)
     cpu_res = time.process_time() - cpu0
+    cpu_res_workers = worker_cpu[0]
     launches = sum(c.get("launches") for c in ctxs) - launches0
     ms_e2e = timed(step_e2e, nproofs, warmup, ctxs)
     ms_stmt = timed(step_statement, nproofs, warmup, ctxs)
@@ -347,6 +369,8 @@ def main():
                 "note": "one GPU; sweep 2^10..2^22 in profiles/r01_configs_1gpu.jsonl (tools/bench_configs.py)"},
         "gpu_launches": launches,
         "host": {"cores": os.cpu_count(), "cpu_s_per_proof_rank0": cpu_res / (nproofs + max(warmup * PROOFS_PER_STEP, inflight)),
+                 "cpu_s_per_proof_worker_threads": cpu_res_workers / (nproofs + max(warmup * PROOFS_PER_STEP, inflight)),
+                 "live_threads_cpu_s": _thread_cpu_by_name(),
                  "rng_streams": stat1[0] - stat0[0], "rng_vector_batches": stat1[1] - stat0[1],
                  "rng_streams_alone": stat1[2] - stat0[2],
                  "thread_cpu_s_total_all_legs": cpu_parts,
