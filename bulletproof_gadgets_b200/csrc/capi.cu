@@ -111,6 +111,7 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
             ctx->reduce_blocks = b;
         }
     }
+    if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
     *out = ctx;
     return BPG_OK;
 }
@@ -152,6 +153,7 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
         (*out)->task_len = parent->task_len;
         (*out)->reduce_threads = parent->reduce_threads;
         (*out)->reduce_blocks = parent->reduce_blocks;
+        (*out)->use_tickets = parent->use_tickets;
     }
     return rc;
 }
@@ -169,6 +171,7 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     w.slot_bucket.release();
     w.blockres.release();
     w.scan_tmp.release();
+    w.tickets.release();
     ctx->d_scalars.release();
     ctx->d_points.release();
     r1cs_release_work(ctx);
@@ -202,6 +205,8 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
     if (k == "task_len") {
         if (value < 1 || value > 255) return BPG_E_ARG;
         ctx->task_len = (int)value;
+    } else if (k == "tickets") {
+        ctx->use_tickets = value != 0;
     } else if (k == "reduce_threads") {
         if (value != 32 && value != 64) return BPG_E_ARG;
         ctx->reduce_threads = (int)value;

@@ -99,6 +99,7 @@ struct MsmWork {
     DevBuf<uint32_t> slot_bucket;   // bucket of each used partial slot (0xffffffff = unused)
     DevBuf<ge_ext> blockres;        // [nsets][reduce_blocks <= REDUCE_BLOCKS_MAX]
     DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan
+    DevBuf<uint32_t> tickets;       // [16][points] rank of each entry inside its bucket (histogram pass -> scatter pass)
 };
 
 struct bpg_ctx {
@@ -117,6 +118,7 @@ struct bpg_ctx {
     ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu); snapshot
     struct ProofWork* pw = nullptr;  // reusable device vectors of the R1CS driver (r1cs.cu)
     int task_len = 32;
+    int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
     int reduce_threads = 64, reduce_blocks = 128;  // k_reduce_chunks geometry (msm.cu); 32 x 256 = one-warp CTAs
     // counters for bench.py ("gpu_launches")
     uint64_t launches = 0;

@@ -36,7 +36,7 @@
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, uint32_t nb, uint32_t n_points,
                                                 uint32_t* __restrict__ hist, const uint32_t* __restrict__ bucket_off,
-                                                uint32_t* __restrict__ entries) {
+                                                uint32_t* __restrict__ entries, uint32_t* __restrict__ tickets) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= segs.total) return;
     // locate the segment
@@ -85,15 +85,33 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
                 }
             }
         }
+        // With `tickets` the histogram pass keeps what its atomicAdd returns -- the rank of the entry inside its bucket
+        // -- at [w][g] (coalesced), and the scatter pass is bucket_off + rank: no second round of atomics.
         if (!SCATTER) {
+            if (tickets) {
+                uint32_t tk[16];
 #pragma unroll
-            for (int w = 0; w < 16; w++)
-                if (gbv[w] != 0xffffffffu) atomicAdd(&hist[gbv[w]], 1u);
+                for (int w = 0; w < 16; w++)
+                    if (gbv[w] != 0xffffffffu) tk[w] = atomicAdd(&hist[gbv[w]], 1u);
+#pragma unroll
+                for (int w = 0; w < 16; w++)
+                    if (gbv[w] != 0xffffffffu) tickets[(size_t)w * segs.total + g] = tk[w];
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; w++)
+                    if (gbv[w] != 0xffffffffu) atomicAdd(&hist[gbv[w]], 1u);
+            }
         } else {
             uint32_t pos[16];
+            if (tickets) {
 #pragma unroll
-            for (int w = 0; w < 16; w++)
-                if (gbv[w] != 0xffffffffu) pos[w] = bucket_off[gbv[w]] + atomicAdd(&hist[gbv[w]], 1u);
+                for (int w = 0; w < 16; w++)
+                    if (gbv[w] != 0xffffffffu) pos[w] = bucket_off[gbv[w]] + tickets[(size_t)w * segs.total + g];
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; w++)
+                    if (gbv[w] != 0xffffffffu) pos[w] = bucket_off[gbv[w]] + atomicAdd(&hist[gbv[w]], 1u);
+            }
 #pragma unroll
             for (int w = 0; w < 16; w++)
                 if (gbv[w] != 0xffffffffu) entries[pos[w]] = entv[w];
@@ -357,20 +375,25 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
         (rc = w.blockres.ensure((size_t)nsets * REDUCE_BLOCKS_MAX)) || (rc = w.scan_tmp.ensure(G / 2048 + 4)))
         return rc;
 
+    uint32_t* tickets = nullptr;  // rank of every entry inside its bucket (unrolled K <= 16 path of k_digits only)
+    if (ctx->use_tickets && tb.K <= 16 && total > 0) {
+        if ((rc = w.tickets.ensure((size_t)16 * total))) return rc;
+        tickets = w.tickets.p;
+    }
     CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));
     if (total > 0) {
         const uint32_t blocks = (uint32_t)((total + 255) / 256);
-        k_digits<false><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, nullptr, nullptr);
+        k_digits<false><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, nullptr, nullptr, tickets);
         ctx->launches++;
     }
     dev_exclusive_scan_u32(st, w.hist.p, w.bucket_off.p, G, w.scan_tmp.p);
-    CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));  // becomes the scatter cursor
-    ctx->launches += 3;
+    if (!tickets) CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, (size_t)G * 4, st));  // becomes the scatter cursor
+    ctx->launches += tickets ? 2 : 3;
     if (total > 0) {
         const uint32_t blocks = (uint32_t)((total + 255) / 256);
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_c, st));
         k_digits<true><<<blocks, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, w.hist.p, w.bucket_off.p,
-                                              w.entries.p);
+                                              w.entries.p, tickets);
         if (ctx->time_accum) CUDA_TRY(cudaEventRecord(ctx->ev_d, st));
         ctx->launches++;
     }
