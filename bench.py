@@ -393,8 +393,10 @@ def main():
                           "peak": HBM_PEAK_GBS, "unit": "GB/s",
                           "frac": (32 * sct_points + 8 * acc_entries) / (sct_ns * 1e-9) / 1e9 / HBM_PEAK_GBS if sct_ns else None,
                           "traffic": SORT_TRAFFIC_BYTES, "kernel_ms_per_proof": sct_ns * 1e-6,
-                          "note": "bound in practice by L2 atomics (one atomicAdd per entry on 65 536 bucket cursors), not by "
-                                  "HBM bytes: profiles/r01_digits_ncu_details.csv"},
+                          "note": "the scatter pass places entries at bucket offset + the rank the histogram pass's atomicAdd "
+                                  "returned (no atomics of its own); bound by 4-byte scattered stores through L2, not by HBM bytes. "
+                                  "`traffic` is the ncu capture of the earlier atomic version (profiles/r01_digits_ncu_details.csv); "
+                                  "the rank array adds 4 B per entry each way, L2-resident"},
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
