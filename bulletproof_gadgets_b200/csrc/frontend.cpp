@@ -223,8 +223,6 @@ class TermVec {
     }
     const Term* begin() const { return p_; }
     const Term* end() const { return p_ + n_; }
-    Term* begin() { return p_; }
-    Term* end() { return p_ + n_; }
     uint32_t size() const { return n_; }
 };
 
@@ -261,11 +259,6 @@ struct LC {
         a.t.reserve(a.t.size() + o.t.size());
         for (auto& e : o.t) a.t.push_back({e.first, s_neg(e.second)});
         return a;
-    }
-    LC scale(const S& s) const {
-        LC r;
-        for (auto& e : t) r.t.push_back({e.first, s_mul(e.second, s)});
-        return r;
     }
 };
 
