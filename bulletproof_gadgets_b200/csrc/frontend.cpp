@@ -24,6 +24,7 @@
 #include <chrono>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -1174,35 +1175,49 @@ struct Walker {
     }
 };
 
-// The top-level buffer's arrays are kept per thread between statements (up to SCRATCH_KEEP bytes): a 2^17-multiplier
-// statement records ~45 MB of operations, and first-touch page faults on fresh allocations cost more than filling them.
+// The top-level buffer's arrays are recycled between statements through a small process-wide pool (at most SCRATCH_SLOTS
+// sets of at most SCRATCH_KEEP bytes each): a 2^17-multiplier statement records ~45 MB of operations, and first-touch
+// page faults on fresh allocations cost more than filling them.  A pool rather than thread-local storage, so that
+// short-lived caller threads (one per statement is common) still find warm memory.
 struct Scratch {
     std::vector<Term> arena;
     std::vector<Op> ops;
     std::vector<S> vals;
 };
 const size_t SCRATCH_KEEP = 128u << 20;
+const size_t SCRATCH_SLOTS = 64;
+struct ScratchPool {
+    std::mutex mu;
+    std::vector<Scratch> free_list;
+};
+ScratchPool& scratch_pool() {
+    static ScratchPool* p = new ScratchPool();  // never destroyed: callers may still run during process exit
+    return *p;
+}
 struct ScratchLease {
     Buffer& b;
-    static Scratch& tls() {
-        static thread_local Scratch s;
-        return s;
-    }
     explicit ScratchLease(Buffer& buf) : b(buf) {
-        Scratch& s = tls();
+        ScratchPool& pool = scratch_pool();
+        std::lock_guard<std::mutex> lock(pool.mu);
+        if (pool.free_list.empty()) return;
+        Scratch s = std::move(pool.free_list.back());
+        pool.free_list.pop_back();
         b.arena.swap(s.arena);
         b.ops.swap(s.ops);
         b.vals.swap(s.vals);
     }
     ~ScratchLease() {
-        Scratch& s = tls();
         b.arena.clear();
         b.ops.clear();
         b.vals.clear();
         if (b.arena.capacity() * sizeof(Term) + b.ops.capacity() * sizeof(Op) + b.vals.capacity() * sizeof(S) > SCRATCH_KEEP) return;
-        b.arena.swap(s.arena);
-        b.ops.swap(s.ops);
-        b.vals.swap(s.vals);
+        Scratch s;
+        s.arena.swap(b.arena);
+        s.ops.swap(b.ops);
+        s.vals.swap(b.vals);
+        ScratchPool& pool = scratch_pool();
+        std::lock_guard<std::mutex> lock(pool.mu);
+        if (pool.free_list.size() < SCRATCH_SLOTS) pool.free_list.push_back(std::move(s));
     }
 };
 
