@@ -1,7 +1,16 @@
 // Host-compiled view of the device math headers (portable branch), for CPU-side unit tests.
 #include "ge25519.cuh"
+#include "sc25519.cuh"
 #include <string.h>
 extern "C" {
+// scalar field: built twice by the test (4 x 64-bit host limbs, and -DBPG_SC_PORTABLE = the 8 x 32-bit code the device runs)
+void hm_sc_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { sc x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); sc z = sc_mul(x, y); memcpy(r, &z, 32); }
+void hm_sc_montmul(const uint32_t* a, const uint32_t* b, uint32_t* r) { sc x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); sc z = sc_montmul(x, y); memcpy(r, &z, 32); }
+void hm_sc_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { sc x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); sc z = sc_add(x, y); memcpy(r, &z, 32); }
+void hm_sc_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { sc x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); sc z = sc_sub(x, y); memcpy(r, &z, 32); }
+void hm_sc_reduce(const uint32_t* a, uint32_t* r) { sc x; memcpy(&x, a, 32); sc z = sc_reduce(x); memcpy(r, &z, 32); }
+uint32_t hm_sc_add_raw(const uint32_t* a, const uint32_t* b, uint32_t* r) { sc x, y, z; memcpy(&x, a, 32); memcpy(&y, b, 32); uint32_t c = sc_add_raw(&z, x, y); memcpy(r, &z, 32); return c; }
+uint32_t hm_sc_sub_raw(const uint32_t* a, const uint32_t* b, uint32_t* r) { sc x, y, z; memcpy(&x, a, 32); memcpy(&y, b, 32); uint32_t c = sc_sub_raw(&z, x, y); memcpy(r, &z, 32); return c; }
 void hm_fe_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { fe x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); fe z = fe_mul(x, y); memcpy(r, &z, 32); }
 void hm_fe_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { fe x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); fe z = fe_add(x, y); memcpy(r, &z, 32); }
 void hm_fe_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { fe x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); fe z = fe_sub(x, y); memcpy(r, &z, 32); }

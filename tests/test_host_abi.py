@@ -149,3 +149,51 @@ def test_group_and_codec_portable_branch(hm):
         assert o1.raw == ed.from_uniform_bytes(u).compress()
     a, b = bytes.fromhex(RFC9496_MULTIPLES[5]), bytes.fromhex(RFC9496_MULTIPLES[9])
     assert hm.hm_add(a, b, o1) == 1 and o1.raw.hex() == RFC9496_MULTIPLES[14]
+
+
+@pytest.fixture(scope="module", params=["host64", "portable"])
+def hm_sc(request):
+    """tests/host_math built with the host's 4 x 64-bit scalar routines, and with -DBPG_SC_PORTABLE (the limb code the
+    device compiles)."""
+    out = os.path.join(ROOT, "build", "libhost_math_sc_%s.so" % request.param)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "host_math", "host_math.cpp")
+    inc = os.path.join(ROOT, "bulletproof_gadgets_b200", "csrc")
+    deps = [src] + [os.path.join(inc, f) for f in ("fe25519.cuh", "ge25519.cuh", "sc25519.cuh", "consts.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        flags = ["-DBPG_SC_PORTABLE=1"] if request.param == "portable" else []
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", inc] + flags + [src, "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+def test_scalar_field_host_routines(hm_sc):
+    """mod-l arithmetic of sc25519.cuh as the host runs it (statement front end, challenge arithmetic) against python
+    integers: canonical operands, Scalar::from_bits style operands up to 2^255, and the edges around l and 2^256."""
+    L = 2**252 + 27742317777372353535851937790883648493
+    R = 1 << 256
+    rnd = random.Random(252)
+    edge = [0, 1, 2, L - 2, L - 1, L, L + 1, 2 * L - 1, 2 * L, (1 << 252) - 1, 1 << 252, (1 << 255) - 1, (1 << 255), R - 1]
+    vals = edge + [rnd.randrange(L) for _ in range(150)] + [rnd.randrange(1 << 255) for _ in range(100)] + [rnd.randrange(R) for _ in range(50)]
+    out = (ctypes.c_uint32 * 8)()
+    rinv = pow(R, -1, L)
+    for i, a in enumerate(vals):
+        b = vals[(i * 11 + 5) % len(vals)]
+        # raw add / sub with carry / borrow: any 256-bit operands
+        c = hm_sc.hm_sc_add_raw(_fe(a), _fe(b), out)
+        assert (_int(out), c) == ((a + b) % R, (a + b) >> 256)
+        c = hm_sc.hm_sc_sub_raw(_fe(a), _fe(b), out)
+        assert (_int(out), c) == ((a - b) % R, 1 if a < b else 0)
+        # modular add / sub: canonical operands
+        ac, bc = a % L, b % L
+        hm_sc.hm_sc_add(_fe(ac), _fe(bc), out)
+        assert _int(out) == (ac + bc) % L
+        hm_sc.hm_sc_sub(_fe(ac), _fe(bc), out)
+        assert _int(out) == (ac - bc) % L
+        # products: one operand below 2^255 and one canonical keep a*b < R*l (the contract of sc_montmul)
+        a255 = a % (1 << 255)
+        hm_sc.hm_sc_montmul(_fe(a255), _fe(bc), out)
+        assert _int(out) == a255 * bc * rinv % L
+        hm_sc.hm_sc_mul(_fe(a255), _fe(bc), out)
+        assert _int(out) == a255 * bc % L
+        hm_sc.hm_sc_reduce(_fe(a), out)
+        assert _int(out) == a % L
