@@ -2,10 +2,11 @@
 """bench.py -- BASELINE.json headline: R1CS prove & verify per second on B200 (config 2:
 `BOUND` 64-bit range statements x1024 in ONE R1CS proof, n = 2^17 multipliers, m = 3072 commitments).
 
-One "step" = one pass of the hot path over one BATCH of PROOFS_PER_STEP = 16 independent statements (two rounds of the
+One "step" = one pass of the hot path over one BATCH of PROOFS_PER_STEP = 32 independent statements (four rounds of the
 eight-wide lockstep in which the library runs the provers' Merlin rng streams); each statement costs m Pedersen
-commitments + Prover::prove + Verifier::verify (accepting).  value = steps x 16 / time, in proofs per second.  With
-the default 8 steps the timed region holds 128 statements, so the drain of the last <= 48 in flight weighs little.  Legs:
+commitments + Prover::prove + Verifier::verify (accepting).  value = steps x 32 / time, in proofs per second.  With
+the default 8 steps the timed region holds 256 statements, so the drain of the last <= 48 in flight weighs little
+(measured: 64 statements in the timed region read 71/s where 128 read 94/s).  Legs:
   value  constraint system and witness already resident in HBM (bpg_circuit); proofs verified inside
          the timed region.  `inflight` host threads (one bpg context = one stream each, generator
          tables shared) keep several independent steps in flight on the GPU, because the prover's
@@ -39,7 +40,7 @@ WORKLOAD = "bounds_check 64-bit x1024 in one R1CS proof (n=2^17 multipliers, m=3
 # IMAD.WIDE.U32 issue rate, the instruction the field multiplication is built from
 IMAD_WIDE_PEAK_TOPS = 8.157
 IMAD_PER_MADD = 504  # 7 field muls x (64 + 8) 32x32->64 multiply-adds, SURVEY.md 8(d)
-PROOFS_PER_STEP = 16  # statements per step (one batch); every statement is proven and verified
+PROOFS_PER_STEP = 32  # statements per step (one batch); every statement is proven and verified
 try:
     HBM_PEAK_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:  # noqa: BLE001
