@@ -1236,6 +1236,7 @@ std::function<S(uint64_t)> blinding_stream(const uint8_t seed[32]) {
 }
 
 void compile_prover(const char* instance, const char* witness, const char* gadgets, const uint8_t* blinding_seed32, Side* side) {
+    auto Tp = std::chrono::steady_clock::now();
     side->proving = true;
     uint8_t seed[32];
     if (blinding_seed32) memcpy(seed, blinding_seed32, 32);
@@ -1268,10 +1269,11 @@ void compile_prover(const char* instance, const char* witness, const char* gadge
     auto T1 = std::chrono::steady_clock::now();
     side->st.replay(top, true);
     auto T2 = std::chrono::steady_clock::now();
-    if (getenv("BPG_FE_TRACE")) fprintf(stderr, "[fe] walk %.1f ms replay %.1f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count());
+    if (getenv("BPG_FE_TRACE")) fprintf(stderr, "[fe] prover parse+commit %.1f ms walk %.1f ms replay %.1f ms\n", std::chrono::duration<double, std::milli>(T0 - Tp).count(), std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count());
 }
 
 void compile_verifier(const char* instance, const char* commitments, const char* gadgets, Side* side) {
+    auto Tp = std::chrono::steady_clock::now();
     side->proving = false;
     for (auto& line : split_lines(instance)) {
         auto kv = parse_var_line('I', line);
@@ -1292,7 +1294,7 @@ void compile_verifier(const char* instance, const char* commitments, const char*
     auto T1 = std::chrono::steady_clock::now();
     side->st.replay(top, false);
     auto T2 = std::chrono::steady_clock::now();
-    if (getenv("BPG_FE_TRACE")) fprintf(stderr, "[fe] verifier walk %.1f ms replay %.1f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count());
+    if (getenv("BPG_FE_TRACE")) fprintf(stderr, "[fe] verifier parse %.1f ms walk %.1f ms replay %.1f ms\n", std::chrono::duration<double, std::milli>(T0 - Tp).count(), std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count());
 }
 
 template <typename T>
