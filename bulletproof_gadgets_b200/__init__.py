@@ -19,6 +19,8 @@ from .api import (  # noqa: F401
     Transcript,
     Variable,
     Verifier,
+    c_prove,
+    c_verify,
     flatten_prover,
     flatten_verifier,
     mimc_hash,
@@ -26,7 +28,11 @@ from .api import (  # noqa: F401
     pinned_copy,
     pinned_empty,
     prove,
+    prove_batch,
+    prove_text_batch,
     verify,
+    verify_batch,
+    verify_text_batch,
 )
 
 __all__ = ["Context", "Transcript", "Prover", "Verifier", "LinearCombination", "Variable", "BpgError", "prove",

@@ -23,6 +23,35 @@ class ProofArtifacts(ctypes.Structure):
                 ("num_constraints", c_uint64)]
 
 
+class RefProofArtifacts(ctypes.Structure):
+    """struct ProofArtifacts of include/bulletproofs_gadgets.h (/root/reference/interfaces/ios/src/lib.rs:11-19)."""
+    _fields_ = [("commitments", c_char_p), ("proof", POINTER(c_uint8)), ("proof_len", c_size_t), ("proof_cap", c_size_t)]
+
+
+class ProveJob(ctypes.Structure):
+    _fields_ = [("label", c_void_p), ("label_len", c_size_t), ("v32m", c_void_p), ("vbl32m", c_void_p), ("m", c_uint64),
+                ("circuit", c_void_p), ("aL32n", c_void_p), ("aR32n", c_void_p), ("n", c_uint64), ("row_start", c_void_p),
+                ("term_var", c_void_p), ("term_coef32", c_void_p), ("q", c_uint64), ("rng_seed32", c_void_p),
+                ("verify_seed32", c_void_p), ("flags", c_uint32), ("V_out32m", c_void_p), ("proof_out", c_void_p),
+                ("proof_cap", c_size_t), ("proof_len", c_size_t), ("status", c_int)]
+
+
+class VerifyJob(ctypes.Structure):
+    _fields_ = [("label", c_void_p), ("label_len", c_size_t), ("V32m", c_void_p), ("m", c_uint64), ("circuit", c_void_p),
+                ("n", c_uint64), ("row_start", c_void_p), ("term_var", c_void_p), ("term_coef32", c_void_p), ("q", c_uint64),
+                ("proof", c_void_p), ("proof_len", c_size_t), ("rng_seed32", c_void_p), ("status", c_int)]
+
+
+class TextJob(ctypes.Structure):
+    _fields_ = [("name", c_char_p), ("instance", c_char_p), ("witness", c_char_p), ("gadgets", c_char_p),
+                ("commitments", c_char_p), ("proof", c_void_p), ("proof_len", c_size_t), ("blinding_seed32", c_void_p),
+                ("rng_seed32", c_void_p), ("verify_seed32", c_void_p), ("flags", c_uint32),
+                ("artifacts", POINTER(ProofArtifacts)), ("accepted", c_int), ("status", c_int)]
+
+
+JOB_VERIFY = 1
+
+
 class FlatStatementC(ctypes.Structure):
     _fields_ = [("n", c_uint64), ("m", c_uint64), ("q", c_uint64), ("nnz", c_uint64), ("v32m", POINTER(c_uint8)),
                 ("vbl32m", POINTER(c_uint8)), ("V32m", POINTER(c_uint8)), ("aL32n", POINTER(c_uint8)),
@@ -98,6 +127,16 @@ PROTOTYPES = {
     "bpg_flat_statement_free": (None, [POINTER(FlatStatementC)]),
     "bpg_mimc_hash": (c_int, [c_char_p, c_size_t, c_char_p]),
     "bpg_mimc_sponge": (c_int, [c_char_p, c_size_t, c_char_p]),
+    "bpg_r1cs_prove_batch": (c_int, [POINTER(c_void_p), c_size_t, POINTER(ProveJob), c_size_t]),
+    "bpg_r1cs_verify_batch": (c_int, [POINTER(c_void_p), c_size_t, POINTER(VerifyJob), c_size_t]),
+    "bpg_prove_batch": (c_int, [POINTER(c_void_p), c_size_t, POINTER(TextJob), c_size_t]),
+    "bpg_verify_batch": (c_int, [POINTER(c_void_p), c_size_t, POINTER(TextJob), c_size_t]),
+}
+# include/bulletproofs_gadgets.h: the reference's own C ABI (same names as /root/reference/interfaces/ios/src/lib.rs)
+REF_PROTOTYPES = {
+    "c_prove": (POINTER(RefProofArtifacts), [c_char_p, c_char_p, c_char_p, c_char_p]),
+    "c_verify": (ctypes.c_bool, [c_char_p, c_char_p, c_char_p, c_char_p, c_char_p, c_size_t]),
+    "free_proof": (None, [POINTER(RefProofArtifacts)]),
 }
 
 
@@ -109,7 +148,7 @@ def lib():
             raise BpgError(E_CUDA, "libbpg.so is not built (run `python -m bulletproof_gadgets_b200.build`); "
                                    "there is no CPU fallback")
         L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in PROTOTYPES.items():
+        for name, (res, args) in list(PROTOTYPES.items()) + list(REF_PROTOTYPES.items()):
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

@@ -484,3 +484,147 @@ def flatten_verifier(name, instance, commitments, gadgets):
     check(lib().bpg_frontend_flatten_verifier(name.encode(), instance.encode(), commitments.encode(), gadgets.encode(),
                                               byref(out)))
     return _take_flat(out, False, name.encode())
+
+
+# ------------------------------------------------------------------------------------------------
+# batches (bpg_r1cs_prove_batch / bpg_r1cs_verify_batch / bpg_prove_batch / bpg_verify_batch): the library owns the
+# host threads, one per context
+# ------------------------------------------------------------------------------------------------
+def _ctx_array(ctxs):
+    arr = (c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    return ctypes.cast(arr, ctypes.POINTER(c_void_p)), arr
+
+
+def _ptr(x, keep):
+    """address of bytes / numpy data, keeping the object alive in `keep`."""
+    if x is None:
+        return None
+    if isinstance(x, (bytes, bytearray)):
+        if not x:
+            return None
+        b = ctypes.create_string_buffer(bytes(x), len(x)) if isinstance(x, bytearray) else x
+        keep.append(b)
+        return ctypes.cast(ctypes.c_char_p(b) if isinstance(b, bytes) else b, c_void_p).value
+    keep.append(x)
+    return x.ctypes.data if x.size else None
+
+
+def prove_batch(ctxs, statements, seeds, circuits=None, verify=False, verify_seeds=None):
+    """N independent flat statements (workloads.FlatStatement-like: label, v_bytes, vbl_bytes, m, aL, aR, n, row_start,
+    term_var, term_coef, q) through bpg_r1cs_prove_batch.  `circuits`: one resident Circuit (with witness) for all, or a
+    list.  Returns a list of (status, proof bytes, commitments bytes m*32)."""
+    n = len(statements)
+    jobs = (_capi.ProveJob * n)()
+    keep, outs = [], []
+    for k, st in enumerate(statements):
+        j = jobs[k]
+        j.label, j.label_len = _ptr(st.label, keep), len(st.label)
+        j.v32m, j.vbl32m, j.m = _ptr(st.v_bytes, keep), _ptr(st.vbl_bytes, keep), st.m
+        circ = circuits[k] if isinstance(circuits, (list, tuple)) else circuits
+        if circ is not None:
+            j.circuit = circ._h
+            keep.append(circ)
+        else:
+            j.aL32n, j.aR32n = _ptr(st.aL, keep), _ptr(st.aR, keep)
+        j.n, j.q = st.n, st.q
+        j.row_start, j.term_var, j.term_coef32 = _ptr(st.row_start, keep), _ptr(st.term_var, keep), _ptr(st.term_coef, keep)
+        j.rng_seed32 = _ptr(seeds[k] if seeds else None, keep)
+        j.verify_seed32 = _ptr(verify_seeds[k] if verify_seeds else None, keep)
+        j.flags = _capi.JOB_VERIFY if verify else 0
+        V = ctypes.create_string_buffer(32 * max(st.m, 1))
+        P = ctypes.create_string_buffer(1 + 14 * 32 + 66 * 32)
+        outs.append((V, P))
+        j.V_out32m, j.proof_out, j.proof_cap = ctypes.addressof(V), ctypes.addressof(P), len(P)
+    cp, arr = _ctx_array(ctxs)
+    rc = lib().bpg_r1cs_prove_batch(cp, len(ctxs), jobs, n)
+    if rc < 0:
+        check(rc)
+    return [(jobs[k].status, outs[k][1].raw[:jobs[k].proof_len], outs[k][0].raw[:32 * statements[k].m]) for k in range(n)]
+
+
+def verify_batch(ctxs, statements, coms, proofs, seeds=None, circuits=None):
+    """bpg_r1cs_verify_batch: coms[k] = m*32 bytes.  Returns the list of statuses (0 accepted, -2 rejected, -1 malformed)."""
+    n = len(statements)
+    jobs = (_capi.VerifyJob * n)()
+    keep = []
+    for k, st in enumerate(statements):
+        j = jobs[k]
+        j.label, j.label_len = _ptr(st.label, keep), len(st.label)
+        c = coms[k] if isinstance(coms[k], (bytes, bytearray)) else b"".join(coms[k])
+        j.V32m, j.m = _ptr(c, keep), len(c) // 32
+        circ = circuits[k] if isinstance(circuits, (list, tuple)) else circuits
+        if circ is not None:
+            j.circuit = circ._h
+            keep.append(circ)
+        j.n, j.q = st.n, st.q
+        j.row_start, j.term_var, j.term_coef32 = _ptr(st.row_start, keep), _ptr(st.term_var, keep), _ptr(st.term_coef, keep)
+        j.proof, j.proof_len = _ptr(proofs[k], keep), len(proofs[k])
+        j.rng_seed32 = _ptr(seeds[k] if seeds else None, keep)
+    cp, arr = _ctx_array(ctxs)
+    rc = lib().bpg_r1cs_verify_batch(cp, len(ctxs), jobs, n)
+    if rc < 0:
+        check(rc)
+    return [jobs[k].status for k in range(n)]
+
+
+def prove_text_batch(ctxs, texts, blinding_seeds=None, rng_seeds=None, verify=False):
+    """bpg_prove_batch over (name, instance, witness, gadgets) tuples.  Returns [(status, proof, commitments text,
+    accepted)]; `accepted` is meaningful with verify=True."""
+    n = len(texts)
+    jobs = (_capi.TextJob * n)()
+    keep = []
+    for k, (name, inst, wtns, gad) in enumerate(texts):
+        j = jobs[k]
+        j.name, j.instance, j.witness, j.gadgets = name.encode(), inst.encode(), wtns.encode(), gad.encode()
+        j.blinding_seed32 = _ptr(blinding_seeds[k] if blinding_seeds else None, keep)
+        j.rng_seed32 = _ptr(rng_seeds[k] if rng_seeds else None, keep)
+        j.verify_seed32 = j.rng_seed32
+        j.flags = _capi.JOB_VERIFY if verify else 0
+    cp, arr = _ctx_array(ctxs)
+    rc = lib().bpg_prove_batch(cp, len(ctxs), jobs, n)
+    if rc < 0:
+        check(rc)
+    out = []
+    for k in range(n):
+        j = jobs[k]
+        if j.artifacts:
+            a = j.artifacts.contents
+            out.append((j.status, ctypes.string_at(a.proof, a.proof_len), a.commitments.decode(), bool(j.accepted)))
+            lib().bpg_free_proof(j.artifacts)
+        else:
+            out.append((j.status, b"", "", False))
+    return out
+
+
+def verify_text_batch(ctxs, texts, seeds=None):
+    """bpg_verify_batch over (name, instance, gadgets, commitments text, proof) tuples -> [(status, accepted)]."""
+    n = len(texts)
+    jobs = (_capi.TextJob * n)()
+    keep = []
+    for k, (name, inst, gad, coms, proof) in enumerate(texts):
+        j = jobs[k]
+        j.name, j.instance, j.gadgets, j.commitments = name.encode(), inst.encode(), gad.encode(), coms.encode()
+        j.proof, j.proof_len = _ptr(proof, keep), len(proof)
+        j.verify_seed32 = _ptr(seeds[k] if seeds else None, keep)
+    cp, arr = _ctx_array(ctxs)
+    rc = lib().bpg_verify_batch(cp, len(ctxs), jobs, n)
+    if rc < 0:
+        check(rc)
+    return [(jobs[k].status, bool(jobs[k].accepted)) for k in range(n)]
+
+
+def c_prove(name, instance, witness, gadgets):
+    """The reference's own C entry point (include/bulletproofs_gadgets.h): -> (proof bytes, commitments text) or None."""
+    a = lib().c_prove(name.encode(), instance.encode(), witness.encode(), gadgets.encode())
+    if not a:
+        return None
+    try:
+        c = a.contents
+        assert c.proof_cap >= c.proof_len
+        return ctypes.string_at(c.proof, c.proof_len), c.commitments.decode()
+    finally:
+        lib().free_proof(a)
+
+
+def c_verify(name, instance, gadgets, commitments, proof):
+    return bool(lib().c_verify(name.encode(), instance.encode(), gadgets.encode(), commitments.encode(), proof, len(proof)))

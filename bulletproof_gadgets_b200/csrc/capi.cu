@@ -98,19 +98,16 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
         uint64_t keep = ~0ull;
         CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    CUDA_TRY(cudaEventCreate(&ctx->ev_a));
-    CUDA_TRY(cudaEventCreate(&ctx->ev_b));
-    CUDA_TRY(cudaEventCreate(&ctx->ev_c));
-    CUDA_TRY(cudaEventCreate(&ctx->ev_d));
+    for (int k = 0; k <= MSM_STAGES; k++) CUDA_TRY(cudaEventCreate(&ctx->ev_stage[k]));
+    {
+        int sms = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        if (sms > 0) ctx->sm_count = sms;
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
-    if (const char* e = getenv("BPG_REDUCE")) {  // "threads,blocks" of k_reduce_chunks, for A/B measurements
-        int t = 0, b = 0;
-        if (sscanf(e, "%d,%d", &t, &b) == 2 && (t == 32 || t == 64) && b >= 1 && b <= REDUCE_BLOCKS_MAX) {
-            ctx->reduce_threads = t;
-            ctx->reduce_blocks = b;
-        }
-    }
+    if (const char* e = getenv("BPG_TASK_LEN")) ctx->task_len = atoi(e) > 0 && atoi(e) < (1 << 20) ? atoi(e) : 0;
+    if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
     *out = ctx;
     return BPG_OK;
@@ -151,8 +148,8 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
     int rc = ctx_new(parent->device, parent->store, out);
     if (rc == BPG_OK) {
         (*out)->task_len = parent->task_len;
-        (*out)->reduce_threads = parent->reduce_threads;
-        (*out)->reduce_blocks = parent->reduce_blocks;
+        (*out)->target_chunks = parent->target_chunks;
+        (*out)->cl_min = parent->cl_min;
         (*out)->use_tickets = parent->use_tickets;
     }
     return rc;
@@ -165,10 +162,9 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     MsmWork& w = ctx->work;
     w.hist.release();
     w.bucket_off.release();
-    w.chunk_bucket.release();
+    w.meta.release();
     w.entries.release();
     w.partials.release();
-    w.slot_bucket.release();
     w.blockres.release();
     w.scan_tmp.release();
     w.tickets.release();
@@ -176,10 +172,7 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     ctx->d_points.release();
     r1cs_release_work(ctx);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
-    cudaEventDestroy(ctx->ev_a);
-    cudaEventDestroy(ctx->ev_b);
-    cudaEventDestroy(ctx->ev_c);
-    cudaEventDestroy(ctx->ev_d);
+    for (int k = 0; k <= MSM_STAGES; k++) cudaEventDestroy(ctx->ev_stage[k]);
     cudaEventDestroy(ctx->ev_sync);
     cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -203,16 +196,16 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return BPG_E_ARG;
     std::string k(key);
     if (k == "task_len") {
-        if (value < 1 || value > 255) return BPG_E_ARG;
+        if (value < 0 || value >= (1 << 20)) return BPG_E_ARG;  // 0 = derived on the device from the entry count
         ctx->task_len = (int)value;
+    } else if (k == "target_chunks") {
+        if (value < 0 || value > (1 << 24)) return BPG_E_ARG;
+        ctx->target_chunks = (int)value;
+    } else if (k == "cl_min") {
+        if (value < 1 || value > 4096) return BPG_E_ARG;
+        ctx->cl_min = (int)value;
     } else if (k == "tickets") {
         ctx->use_tickets = value != 0;
-    } else if (k == "reduce_threads") {
-        if (value != 32 && value != 64) return BPG_E_ARG;
-        ctx->reduce_threads = (int)value;
-    } else if (k == "reduce_blocks") {
-        if (value < 1 || value > REDUCE_BLOCKS_MAX) return BPG_E_ARG;
-        ctx->reduce_blocks = (int)value;
     } else if (k == "window_bits") {
         if (value != 0 && (value < 4 || value > 16)) return BPG_E_ARG;
         GensStore* g = ctx->store;
@@ -229,6 +222,8 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
         ctx->sum_entries = 0;
         ctx->sum_scatter_ms = 0;
         ctx->sum_points = 0;
+        ctx->timed_msms = 0;
+        for (int i = 0; i < MSM_STAGES; i++) ctx->sum_stage_ms[i] = 0;
     } else {
         return BPG_E_ARG;
     }
@@ -246,6 +241,13 @@ int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key) {
     if (k == "sum_entries") return (int64_t)ctx->sum_entries;
     if (k == "sum_scatter_ns") return (int64_t)(ctx->sum_scatter_ms * 1e6);
     if (k == "sum_points") return (int64_t)ctx->sum_points;
+    if (k == "timed_msms") return (int64_t)ctx->timed_msms;
+    if (k.rfind("stage_ns_", 0) == 0) {  // stage_ns_0 .. stage_ns_6: see MSM_STAGES (ctx.hpp)
+        const int i = atoi(k.c_str() + 9);
+        return i >= 0 && i < MSM_STAGES ? (int64_t)(ctx->sum_stage_ms[i] * 1e6) : -1;
+    }
+    if (k == "task_len") return ctx->task_len;
+    if (k == "last_chunk_len") return (int64_t)ctx->last_chunk_len;
     if (k == "cpu_sync_ns") return (int64_t)ctx->cpu_sync_ns;
     if (k == "cpu_commit_ns") return (int64_t)ctx->cpu_commit_ns;
     if (k == "cpu_prove_ns") return (int64_t)ctx->cpu_prove_ns;

@@ -26,3 +26,7 @@ void circuit_free(bpg_circuit* c);
 
 // scan.cu: out[i] = sum_{j<i} in[i] for i in [0, n]  (n+1 outputs; in and out may alias); scratch >= n/2048 + 2 words
 void dev_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch);
+// MSM form: off[0..G] = exclusive scan of hist[0..G), hist re-zeroed, *meta = {E, CL, nchunks} with the chunk length
+// CL = cl_fixed, or max(cl_min, ceil(E / target_chunks)) when cl_fixed == 0.  One launch (a single CTA).
+void dev_scan_meta(cudaStream_t st, uint32_t* hist, uint32_t* off, uint32_t G, uint32_t target_chunks, uint32_t cl_min,
+                   uint32_t cl_fixed, MsmMeta* meta);

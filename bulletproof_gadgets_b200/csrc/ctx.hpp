@@ -29,6 +29,7 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;  // elements
+    bool fresh = false;  // (re)allocated since the owner last cleared the flag: contents undefined
     int ensure(size_t n) {
         if (n <= cap) return BPG_OK;
         if (p) cudaFree(p);
@@ -37,6 +38,7 @@ struct DevBuf {
         size_t want = n + n / 8 + 64;
         CUDA_TRY(cudaMalloc((void**)&p, want * sizeof(T)));
         cap = want;
+        fresh = true;
         return BPG_OK;
     }
     void release() {
@@ -89,16 +91,24 @@ struct GensStore {
     int refs = 1;
 };
 
-#define REDUCE_BLOCKS_MAX 1024
+// Geometry of one MSM's bucket accumulation, derived ON THE DEVICE from the entry count (scan.cu: k_scan_meta)
+struct MsmMeta {
+    uint32_t E;        // entries (non-zero digits)
+    uint32_t CL;       // entries per chunk (= per thread of k_accumulate)
+    uint32_t nchunks;  // ceil(E / CL)
+    uint32_t pad;
+};
+#define MSM_STAGES 7  // digits+histogram, scan, digits+scatter, accumulate, bucket reduce, final, whole
+#define REDUCE_MAXV 16  // values per segment of the bucket-reduction butterfly (R, M_0 .. M_14)
 struct MsmWork {
-    DevBuf<uint32_t> hist;          // [nsets*nb] counts, then reused as scatter cursors
+    DevBuf<uint32_t> hist;          // [nsets*nb] counts (zero between MSMs: the scan re-zeroes it)
+    bool hist_dirty = true;         // needs a memset before the next histogram pass
     DevBuf<uint32_t> bucket_off;    // [nsets*nb + 1] exclusive scan of the counts
-    DevBuf<uint32_t> chunk_bucket;  // bucket of the first entry of each fixed-length chunk
+    DevBuf<MsmMeta> meta;
     DevBuf<uint32_t> entries;       // [K*N] (row | sign << 31), sorted by bucket
     DevBuf<ge_ext> partials;        // slot (chunk t, bucket b) = t + b
-    DevBuf<uint32_t> slot_bucket;   // bucket of each used partial slot (0xffffffff = unused)
-    DevBuf<ge_ext> blockres;        // [nsets][reduce_blocks <= REDUCE_BLOCKS_MAX]
-    DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan
+    DevBuf<ge_ext> blockres;        // [2][G / buckets-per-CTA][REDUCE_MAXV] ping-pong of the reduction butterfly
+    DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan (multi-CTA fallback)
     DevBuf<uint32_t> tickets;       // [16][points] rank of each entry inside its bucket (histogram pass -> scatter pass)
 };
 
@@ -117,13 +127,18 @@ struct bpg_ctx {
     DevBuf<ge_ext> d_points;     // result slots of asynchronous MSMs
     ge_niels* ped = nullptr;     // radix-16 tables of B and B_blinding (points.cu); snapshot
     struct ProofWork* pw = nullptr;  // reusable device vectors of the R1CS driver (r1cs.cu)
-    int task_len = 32;
+    int task_len = 0;         // entries per k_accumulate thread; 0 = derived on the device: one full wave of equal chunks
+    int target_chunks = 0;    // chunks aimed at when task_len == 0 (0 = SMs x resident CTAs x threads), at least cl_min entries each
+    int cl_min = 8;
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
-    int reduce_threads = 64, reduce_blocks = 128;  // k_reduce_chunks geometry (msm.cu); 32 x 256 = one-warp CTAs
+    int sm_count = 148;
     // counters for bench.py ("gpu_launches")
     uint64_t launches = 0;
     // timing of the dominant kernel (accumulate), CUDA events on ctx stream
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;  // accumulate / scatter brackets
+    cudaEvent_t ev_stage[MSM_STAGES + 1] = {nullptr};  // time_accum mode: one event after every MSM stage
+    double sum_stage_ms[MSM_STAGES] = {0};             // accumulated since the last reset
+    uint64_t timed_msms = 0;
+    uint32_t last_chunk_len = 0;
     cudaEvent_t ev_sync = nullptr;  // blocking-sync event behind ctx_sync()
     float last_accum_ms = 0.f;
     uint64_t last_entries = 0;

@@ -226,7 +226,10 @@ static uint32_t next_pow2(uint64_t n) {
 static int pedersen_batch(bpg_ctx* ctx, const sc* v, const sc* r, uint64_t k, uint8_t* out32k) {
     if (k == 0) return BPG_OK;
     int rc;
-    if ((rc = gens_build(ctx, 1))) return rc;
+    // Keep the snapshot the caller is working with: prover_prove calls this between MSMs that index the generator table
+    // by the capacity it read at its start, and another context of the same GPU may grow the shared store meanwhile
+    // (superseded tables stay alive, and the B / B_blinding table does not depend on the capacity).
+    if (!ctx->ped && (rc = gens_build(ctx, 1))) return rc;
     ProofWork* pw = work(ctx);
     cudaStream_t st = ctx->stream;
     if ((rc = pw->ped_in.ensure(2 * k)) || (rc = pw->dyn_pts.ensure(k)) || (rc = pw->dyn_enc.ensure(32 * k)))

@@ -52,7 +52,10 @@ def _scalar_bytes(x):
 
 def bounds_check_statement(count=1024, max_bytes=8, seed=20261018, label=b"bench-bound"):
     """`count` x  BOUND W_i I_min I_max  with I_min = 0, I_max = 2^(8*max_bytes)-1.
-    Committed variables per statement: [v, a = v - min, b = max - v]  (witness + 2 derived)."""
+    Committed variables in the reference's order: the `count` witnesses W_i first (.wtns replay,
+    /root/reference/src/lalrpop/assignment_parser.rs), then per statement the derived a = v - min, b = max - v
+    (/root/reference/src/gadget.rs:28-36).  Equal, array for array, to the library front end's flattening of
+    bounds_check_text(count) -- tests/test_host_abi.py::test_bench_statement_is_the_reference_gadget."""
     n_bits = 8 * max_bytes
     vmin, vmax = 0, (1 << n_bits) - 1
     rng = np.random.default_rng(seed)
@@ -67,12 +70,18 @@ def bounds_check_statement(count=1024, max_bytes=8, seed=20261018, label=b"bench
     one_b, minus_one_b = _scalar_bytes(1), _scalar_bytes(-1)
     pow2_neg = [_scalar_bytes(-(1 << i)) for i in range(n_bits)]
     mult = 0
+    def blind():
+        return int.from_bytes(brng.integers(0, 256, size=32, dtype=np.uint8).tobytes(), "little") % L_ORDER
+
+    for val in vals:
+        v.append(val % L_ORDER)
+        vbl.append(blind())
     for s, val in enumerate(vals):
         a, b = val - vmin, vmax - val
-        for x in (val, a, b):
+        for x in (a, b):
             v.append(x % L_ORDER)
-            vbl.append(int.from_bytes(brng.integers(0, 256, size=32, dtype=np.uint8).tobytes(), "little") % L_ORDER)
-        va, vb = _tag(COMMITTED, 3 * s + 1), _tag(COMMITTED, 3 * s + 2)
+            vbl.append(blind())
+        va, vb = _tag(COMMITTED, count + 2 * s), _tag(COMMITTED, count + 2 * s + 1)
         # (a + b) - (max - min) = 0
         tvar += [va, vb, _tag(ONE, 0)]
         tcoef += [one_b, one_b, _scalar_bytes(-(vmax - vmin))]
@@ -115,18 +124,22 @@ def bounds_check_text(count=1024, max_bytes=8, seed=20261018):
     return gadgets, inst, wtns
 
 
-def merkle_text(depth=32, seed=20261018, witness_siblings=False):
+def merkle_text(depth=32, seed=20261018, witness_siblings=False, hashers=None):
     """BASELINE config 3: `MERKLE I0 (((..(W0 I1) I2)..) I<depth>)` -- membership of leaf W0 under root I0 with MiMC
     (/root/reference/src/merkle_tree/merkle_tree_gadget.rs:39-114, /root/reference/src/prove.rs:289-321).
     Leaves are 4..32 random bytes; the root is computed with the library's mimc_hash / sponge.  With
-    witness_siblings the siblings are W1..W<depth> (each hashed in-circuit).  Returns (gadgets, inst, wtns) text."""
-    from . import api
+    witness_siblings the siblings are W1..W<depth> (each hashed in-circuit).  `hashers` = (mimc_hash, mimc_sponge)
+    callables returning ints (default: the library's host routines).  Returns (gadgets, inst, wtns) text."""
+    if hashers is None:
+        from . import api
+        hashers = (api.mimc_hash, api.mimc_sponge)
+    mimc_hash, mimc_sponge = hashers
     rng = np.random.default_rng(seed)
     leaves = [rng.integers(0, 256, size=int(rng.integers(4, 33)), dtype=np.uint8).tobytes() for _ in range(depth + 1)]
     leaves = [b if b.strip(b"\0") else b"\x01" + b[1:] for b in leaves]
-    node = api.mimc_hash(leaves[0])
+    node = mimc_hash(leaves[0])
     for k in range(1, depth + 1):
-        node = api.mimc_sponge([node, api.mimc_hash(leaves[k])])
+        node = mimc_sponge([node, mimc_hash(leaves[k])])
     root = node.to_bytes(32, "big")
     sib = "W" if witness_siblings else "I"
     tree = "(W0 %s1)" % sib

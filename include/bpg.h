@@ -178,9 +178,11 @@ uint64_t bpg_verifier_num_vars(const bpg_verifier* v); /* Verifier::get_num_vars
  * BPG_OK = accepted, BPG_E_VERIFY = rejected, BPG_E_FORMAT = malformed proof bytes. */
 int bpg_verifier_verify(bpg_verifier* v, const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32);
 
-/* ---- statement-level front end (mirrors the reference's own C ABI) ---------------------- */
-/* prove()/verify() of /root/reference/src/prove.rs:37-43 and /root/reference/src/verify.rs:36-42,
- * shaped like c_prove/c_verify/free_proof of /root/reference/interfaces/ios/src/lib.rs:21,45,55.
+/* ---- statement-level front end ---------------------------------------------------------- */
+/* prove()/verify() of /root/reference/src/prove.rs:37-43 and /root/reference/src/verify.rs:36-42 with an explicit
+ * context and injectable randomness.  The reference's own C ABI -- c_prove / c_verify / free_proof and
+ * struct ProofArtifacts, /root/reference/interfaces/ios/src/lib.rs:11-55 -- is exported under exactly those names too:
+ * see include/bulletproofs_gadgets.h.
  * blinding_seed32 seeds the commitment blindings the reference draws from thread_rng()
  * (/root/reference/src/commitments.rs:28,40, /root/reference/src/gadget.rs:32); NULL = OS entropy. */
 typedef struct bpg_proof_artifacts {
@@ -194,6 +196,79 @@ int bpg_prove(bpg_ctx* ctx, const char* name, const char* instance, const char* 
 int bpg_verify(bpg_ctx* ctx, const char* name, const char* instance, const char* gadgets, const char* commitments,
                const uint8_t* proof, size_t proof_len, const uint8_t* rng_seed32, int* accepted);
 void bpg_free_proof(bpg_proof_artifacts* a);
+
+/* ---- batches: N independent statements over a set of contexts ---------------------------- */
+/* What the reference does one process per statement (`prover <stem>` / `verifier <stem>`, /root/reference/src/bin/{prover,verifier}.rs),
+ * as a throughput call: the library runs one host thread per context (contexts of one GPU made with
+ * bpg_ctx_create_shared, or of several GPUs), each keeping one statement in flight on its stream, so the sequential Merlin
+ * rng stream of one proof overlaps the MSMs of the others.  Every job gets its own status (BPG_OK, BPG_E_VERIFY, ...).
+ * Return value: < 0 = the call itself was malformed, otherwise the number of jobs whose status is not BPG_OK. */
+#define BPG_JOB_VERIFY 1u /* prove jobs: run Verifier::verify on the fresh proof on the same context (status covers both) */
+typedef struct bpg_prove_job {
+    /* in: Transcript::new(label) -- /root/reference/src/prove.rs:45 */
+    const uint8_t* label;
+    size_t label_len;
+    /* in: m committed values and blindings (Prover::commit) */
+    const uint8_t* v32m;
+    const uint8_t* vbl32m;
+    uint64_t m;
+    /* in: the constraint system, either a resident circuit (with witness) or host arrays as for bpg_prover_load_cs */
+    const bpg_circuit* circuit;
+    const uint8_t* aL32n;
+    const uint8_t* aR32n;
+    uint64_t n;
+    const uint32_t* row_start;
+    const uint32_t* term_var;
+    const uint8_t* term_coef32;
+    uint64_t q;
+    const uint8_t* rng_seed32;    /* NULL = OS entropy */
+    const uint8_t* verify_seed32; /* used with BPG_JOB_VERIFY; NULL = OS entropy */
+    uint32_t flags;
+    /* out */
+    uint8_t* V_out32m; /* m compressed commitments */
+    uint8_t* proof_out;
+    size_t proof_cap;
+    size_t proof_len;
+    int status;
+} bpg_prove_job;
+typedef struct bpg_verify_job {
+    const uint8_t* label;
+    size_t label_len;
+    const uint8_t* V32m;
+    uint64_t m;
+    const bpg_circuit* circuit; /* or the host arrays below, as for bpg_verifier_load_cs */
+    uint64_t n;
+    const uint32_t* row_start;
+    const uint32_t* term_var;
+    const uint8_t* term_coef32;
+    uint64_t q;
+    const uint8_t* proof;
+    size_t proof_len;
+    const uint8_t* rng_seed32;
+    int status; /* BPG_OK = accepted, BPG_E_VERIFY = rejected, BPG_E_FORMAT = malformed proof */
+} bpg_verify_job;
+int bpg_r1cs_prove_batch(bpg_ctx* const* ctxs, size_t n_ctx, bpg_prove_job* jobs, size_t n_jobs);
+int bpg_r1cs_verify_batch(bpg_ctx* const* ctxs, size_t n_ctx, bpg_verify_job* jobs, size_t n_jobs);
+/* The same for statements in the reference's text formats (bpg_prove / bpg_verify per job, front end included). */
+typedef struct bpg_text_job {
+    const char* name;
+    const char* instance;
+    const char* witness;     /* prove jobs */
+    const char* gadgets;
+    const char* commitments; /* verify jobs */
+    const uint8_t* proof;    /* verify jobs */
+    size_t proof_len;
+    const uint8_t* blinding_seed32;
+    const uint8_t* rng_seed32;
+    const uint8_t* verify_seed32;
+    uint32_t flags;          /* BPG_JOB_VERIFY on prove jobs */
+    /* out */
+    bpg_proof_artifacts* artifacts; /* prove jobs; release with bpg_free_proof */
+    int accepted;                   /* verify jobs, and prove jobs with BPG_JOB_VERIFY */
+    int status;
+} bpg_text_job;
+int bpg_prove_batch(bpg_ctx* const* ctxs, size_t n_ctx, bpg_text_job* jobs, size_t n_jobs);
+int bpg_verify_batch(bpg_ctx* const* ctxs, size_t n_ctx, bpg_text_job* jobs, size_t n_jobs);
 
 /* The flat statement the real Prover / Verifier hold after assign_buffer (/root/reference/src/prove.rs:84-99,
  * /root/reference/src/verify.rs:75-90), as produced by the front end from the text formats.  Pure host code (no

@@ -44,6 +44,25 @@ def test_header_symbols_are_exported(lib):
     assert not missing, "ctypes prototypes missing for %s" % missing
     extra = [s for s in _capi.PROTOTYPES if s not in syms]
     assert not extra, "prototypes without a declaration in include/bpg.h: %s" % extra
+    # the reference's own C ABI (include/bulletproofs_gadgets.h): same names as interfaces/ios/src/lib.rs:21,45,55
+    ref_hdr = open(os.path.join(ROOT, "include", "bulletproofs_gadgets.h")).read()
+    ref_syms = sorted(set(re.findall(r"\b(c_prove|c_verify|free_proof)\s*\(", ref_hdr)))
+    assert ref_syms == ["c_prove", "c_verify", "free_proof"] == sorted(_capi.REF_PROTOTYPES)
+    for s in ref_syms:
+        assert hasattr(lib, s), "libbpg.so does not export %s" % s
+    # struct ProofArtifacts: four pointer-sized fields in the reference's order (#[repr(C)], usize lengths)
+    assert [f[0] for f in _capi.RefProofArtifacts._fields_] == ["commitments", "proof", "proof_len", "proof_cap"]
+    assert ctypes.sizeof(_capi.RefProofArtifacts) == 4 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_reference_abi_fails_loudly_without_a_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert not lib.c_prove(b"x", b"", b"W0 = 0x01", b"BOUND W0 I0 I1")     # NULL, no CPU fallback
+    assert b"no CPU fallback" in lib.bpg_last_error()
+    assert lib.c_verify(b"x", b"", b"", b"", b"\0", 1) is False
+    lib.free_proof(None)
 
 
 def test_no_cpu_fallback(lib):
@@ -197,3 +216,28 @@ def test_scalar_field_host_routines(hm_sc):
         assert _int(out) == a255 * bc % L
         hm_sc.hm_sc_reduce(_fe(a), out)
         assert _int(out) == a % L
+
+
+def test_bench_statement_is_the_reference_gadget():
+    """The numpy-built statement bench.py times (workloads.bounds_check_statement) equals, array for array, the library
+    front end's flattening of the same workload written in the reference's text formats (`BOUND W<i> I0 I1` lines,
+    /root/reference/src/bounds_check/bounds_check_gadget.rs:13-48) -- blindings aside, which the text path derives from
+    its seed.  Host only."""
+    import numpy as np
+    import bulletproof_gadgets_b200 as bpg
+    from bulletproof_gadgets_b200 import workloads as W
+    for count, nbytes in ((1, 8), (5, 8), (40, 8), (3, 2)):
+        st = W.bounds_check_statement(count, max_bytes=nbytes)
+        gad, inst, wtns = W.bounds_check_text(count, max_bytes=nbytes)
+        fs = bpg.flatten_prover("bench", inst, wtns, gad, b"\x01" * 32)
+        assert (st.n, st.m, st.q, st.nnz) == (fs.n, fs.m, fs.q, fs.nnz)
+        assert bytes(st.aL) == bytes(fs.aL) and bytes(st.aR) == bytes(fs.aR)
+        assert np.array_equal(st.row_start, fs.row_start) and np.array_equal(st.term_var, fs.term_var)
+        assert bytes(st.term_coef) == bytes(fs.term_coef)
+        assert list(st.v) == list(fs.v)
+
+
+def test_msm_reduction_index_model():
+    """Integer model of msm.cu stages 4-6 (chunks, collapsed CTAs, slot lists, bit-marginal butterfly)."""
+    from tests.model import msm_reduce_model
+    assert msm_reduce_model.main(cases=60, seed=7) == 60
