@@ -5,16 +5,17 @@
 One "step" = one pass of the hot path over one BATCH of PROOFS_PER_STEP = 32 independent statements (four rounds of the
 eight-wide lockstep in which the library runs the provers' Merlin rng streams); each statement costs m Pedersen
 commitments + Prover::prove + Verifier::verify (accepting).  value = steps x 32 / time, in proofs per second.  With
-the default 8 steps the timed region holds 256 statements, so the drain of the last <= 48 in flight weighs little
-(measured: 64 statements in the timed region read 71/s where 128 read 94/s).  Legs:
-  value  constraint system and witness already resident in HBM (bpg_circuit); proofs verified inside
-         the timed region.  `inflight` host threads (one bpg context = one stream each, generator
-         tables shared) keep several independent steps in flight on the GPU, because the prover's
-         Merlin TranscriptRng stream (2n dependent Keccak-f permutations) is a sequential host job.
-  e2e    the same steps through the C ABI with HOST buffers in pinned memory (bpg_prover_load_cs /
-         bpg_verifier_load_cs): every host->device copy of witness / constraints and the
-         device->host proof are inside the timer.
-  latency  one step at a time on one context (no overlap), resident circuit.
+the default 8 steps the timed region holds 256 statements, so the drain of the last <= 48 in flight weighs little.
+Every throughput leg is ONE call of the library's batch entry point (bpg_r1cs_prove_batch with BPG_JOB_VERIFY, or
+bpg_prove_batch for text): the library owns the `inflight` host threads, one bpg context (= one stream) each.  Legs:
+  value  constraint system and witness already resident in HBM (bpg_circuit); proofs verified inside the timed region.
+  e2e    the same statements with HOST buffers in pinned memory (bpg_prover_load_cs / bpg_verifier_load_cs inside the
+         library): every host->device copy of witness / constraints and the device->host proof are inside the timer.
+  e2e_statement  text formats in (bpg_prove_batch): the host front end is inside the timer too.
+  latency  one statement at a time on one context (no overlap), resident circuit.
+  msm / msm_stages  raw fixed-base MSM of 2^18 points and the CUDA-event time of each of its stages.
+  config4  BASELINE config 4: 4096 independent LESS_THAN / SET_MEMBER proofs, statement i on rank i mod N.
+  msm_sharded  BASELINE config 5 at N GPUs: one MSM of 2^22 points split by point range, partial points added by rank 0.
   cpu_baseline  the CPU restatement of dalek's algorithms (oracle/c, 1 core) on the same statement.
 `--impl reference` times that CPU restatement alone with all host cores (the real reference is pure
 Rust and cannot be built in this image: no cargo/rustc, crates not vendored).
@@ -36,8 +37,8 @@ sys.path.insert(0, ROOT)
 METRIC = "r1cs_prove_verify_per_sec"
 UNIT = "proof+verify/s"
 WORKLOAD = "bounds_check 64-bit x1024 in one R1CS proof (n=2^17 multipliers, m=3072, q=265216)"
-# measured on this pool's B200 by tools/imad_peak.cu (profiles/r01_imad_peak.jsonl): sustained
-# IMAD.WIDE.U32 issue rate, the instruction the field multiplication is built from
+# fallback only: the peak is measured inside every run (bpg_measure_imad_peak, a 50 ms register-only kernel);
+# tools/imad_peak.cu measured 8.157-8.167 T IMAD.WIDE.U32/s on this pool (profiles/r01_imad_peak.jsonl, r02_imad_peak.jsonl)
 IMAD_WIDE_PEAK_TOPS = 8.157
 IMAD_PER_MADD = 504  # 7 field muls x (64 + 8) 32x32->64 multiply-adds, SURVEY.md 8(d)
 PROOFS_PER_STEP = 32  # statements per step (one batch); every statement is proven and verified
@@ -45,7 +46,11 @@ try:
     HBM_PEAK_GBS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:  # noqa: BLE001
     HBM_PEAK_GBS = 6537.6   # this pool's measured copy bandwidth (MEASURED_PEAKS.json of round 1)
-SORT_TRAFFIC_BYTES = 13.76e6   # dram read+write per launch of k_digits<1> (IPP-round MSM), profiles/r01_digits_ncu_details.csv
+# dram read+write bytes per launch from the ncu captures of the CURRENT kernels (profiles/r02_msm_kernels_details.csv,
+# raw MSM of 2^18 points = the shape of an IPP-round MSM): bucket accumulation and the scatter pass of the sort
+ACC_TRAFFIC_BYTES = None
+SORT_TRAFFIC_BYTES = None
+MSM_STAGES = ["digits_histogram", "scan", "digits_scatter", "accumulate", "bucket_reduce", "final", "total"]
 
 
 def _dist():
@@ -159,33 +164,34 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--count", type=int, default=1024, help="BOUND statements per proof (1024 = BASELINE config 2)")
-    ap.add_argument("--inflight", type=int, default=0, help="steps in flight per GPU (host threads); 0 = auto")
+    ap.add_argument("--inflight", type=int, default=0, help="statements in flight per GPU (library host threads); 0 = auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip config4 / msm_sharded / e2e_statement")
+    ap.add_argument("--config4-count", type=int, default=4096)
+    ap.add_argument("--sharded-lg", type=int, default=22)
     args = ap.parse_args()
     ws, rank, local_rank = _dist()
     if args.impl == "reference":
         return run_reference(args, ws, rank)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     if ws > 1:
         torch.cuda.set_device(local_rank)
-        # The data path has no collective (independent proofs per rank): torch.distributed only provides the barrier
-        # and one max-reduce of the timing.  Measured on the 8-GPU box (32 vCPUs): with an NCCL process group alive
-        # every rank burns ~23 ms of host CPU per step in NCCL's service threads (479 vs 559 prove+verify/s,
-        # profiles/r01_bench_8gpu_{nccl,gloo}.json), and this workload is host-CPU bound there -- so gloo by default.
+        # The data path has no collective (independent proofs per rank): torch.distributed only provides the barrier,
+        # the max-reduce of the timings and the gather of <= 8 x 32-byte partial points.  Measured on the 8-GPU box
+        # (32 vCPUs): with an NCCL process group alive every rank burns ~23 ms of host CPU per step in NCCL's service
+        # threads (profiles/r01_bench_8gpu_{nccl,gloo}.json), and this workload is host-CPU bound there -- so gloo.
         backend = os.environ.get("BPG_DIST_BACKEND", "gloo")
         if backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         else:
             dist.init_process_group(backend)
     import bulletproof_gadgets_b200 as bpg
-    from bulletproof_gadgets_b200 import build, workloads as W
+    from bulletproof_gadgets_b200 import build, sharding, workloads as W
     build.build_lib()
     warmup = max(args.warmup, 3)
-    # Host threads mostly block (GPU waits, rng batcher).  Measured on one B200 with 16 vCPUs: 24 / 32 / 48 / 64 in flight
-    # = 72 / 79 / 92 / 92 prove+verify/s (profiles/r01_summary.md); the 8-GPU box has 4 vCPUs per rank and was measured
-    # at 32, so the larger default is used only where a rank has the cores for it.
     inflight = args.inflight or (48 if (os.cpu_count() or 1) // ws >= 12 else 32)
     ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
     ctxs = [ctx0] + [ctx0.shared() for _ in range(inflight - 1)]
@@ -194,37 +200,32 @@ def main():
     circuit = bpg.Circuit(ctx0, st.n, st.m, st.row_start, st.term_var, st.term_coef, st.q).set_witness(st.aL, st.aR)
     dev = torch.device("cuda", local_rank)
     streams = [torch.cuda.ExternalStream(c.get("stream"), device=dev) for c in ctxs]
-
-    def step_resident(ctx, i):
-        seed = (i + 1).to_bytes(32, "little")
-        p = bpg.Prover(ctx, bpg.Transcript(st.label))
-        coms = p.commit_batch_packed(st.v_bytes, st.vbl_bytes)
-        p.attach(circuit)
-        proof = p.prove(seed)
-        vf = bpg.Verifier(ctx, bpg.Transcript(st.label))
-        vf.commit_batch(coms)
-        vf.attach(circuit)
-        if not vf.verify(proof, seed):
-            raise SystemExit("GPU proof did not verify")
-        return proof
-
-    def step_e2e(ctx, i):
-        seed = (i + 1).to_bytes(32, "little")
-        proof, coms = W.prove_statement(bpg, ctx, st, seed)
-        if not W.verify_statement(bpg, ctx, st, proof, coms, seed):
-            raise SystemExit("GPU proof did not verify")
-        return proof
-
     gad_txt, inst_txt, wtns_txt = W.bounds_check_text(args.count, seed=20261018 + rank)
     name_txt = "bench-bound-%d" % rank
 
-    def step_statement(ctx, i):
-        """Text in, proof out: the c_prove / c_verify mirror (bpg_prove / bpg_verify), front end included on both sides."""
-        seed = (i + 1).to_bytes(32, "little")
-        proof, coms_txt, _ = bpg.prove(ctx, name_txt, inst_txt, wtns_txt, gad_txt, seed, seed)
-        if not bpg.verify(ctx, name_txt, inst_txt, proof, coms_txt, gad_txt, seed):
+    def seeds(first, n):
+        return [(first + i + 1).to_bytes(32, "little") for i in range(n)]
+
+    def run_resident(first, n, use=None):
+        sd = seeds(first, n)
+        out = bpg.prove_batch(use or ctxs, [st] * n, sd, circuits=circuit, verify=True, verify_seeds=sd)
+        if any(o[0] != 0 for o in out):
+            raise SystemExit("GPU proof did not verify: %r" % [o[0] for o in out if o[0]][:4])
+        return out
+
+    def run_e2e(first, n, use=None):
+        sd = seeds(first, n)
+        out = bpg.prove_batch(use or ctxs, [st] * n, sd, verify=True, verify_seeds=sd)   # host buffers: uploads inside
+        if any(o[0] != 0 for o in out):
             raise SystemExit("GPU proof did not verify")
-        return proof
+        return out
+
+    def run_statement(first, n, use=None):
+        sd = seeds(first, n)
+        out = bpg.prove_text_batch(use or ctxs, [(name_txt, inst_txt, wtns_txt, gad_txt)] * n, sd, sd, verify=True)
+        if not all(o[0] == 0 and o[3] for o in out):
+            raise SystemExit("GPU proof did not verify")
+        return out
 
     def barrier():
         for s in streams:
@@ -233,100 +234,134 @@ def main():
         if ws > 1:
             dist.barrier()
 
-    worker_cpu = [0.0]
+    def max_over_ranks(x):
+        if ws > 1:
+            t = torch.tensor([x], device="cuda" if dist.get_backend() == "nccl" else "cpu", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            x = float(t.item())
+        return x
 
-    def run_steps(fn, first, count, use_ctxs):
-        """`count` steps spread over the contexts: each host thread pulls the next step index."""
-        if len(use_ctxs) == 1:
-            for i in range(first, first + count):
-                fn(use_ctxs[0], i)
-            return
-        lock, nxt, errs = threading.Lock(), [first], []
-
-        def work(c):
-            try:
-                while True:
-                    with lock:
-                        i = nxt[0]
-                        nxt[0] += 1
-                    if i >= first + count:
-                        return
-                    fn(c, i)
-            except BaseException as e:  # noqa: BLE001
-                errs.append(e)
-            finally:
-                with lock:
-                    worker_cpu[0] += time.thread_time()   # CPU of this host thread (python + C ABI inside it)
-
-        ts = [threading.Thread(target=work, args=(c,)) for c in use_ctxs]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-
-    def timed(fn, steps, warm, use_ctxs):   # `steps` here = number of statements
-        run_steps(fn, 0, max(warm * PROOFS_PER_STEP, len(use_ctxs)) if len(use_ctxs) > 1 else warm, use_ctxs)
+    def timed(fn, nstat, warm_stat, use=None):
+        fn(0, warm_stat, use)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(streams[0])
-        run_steps(fn, 1000, steps, use_ctxs)
+        fn(1000, nstat, use)
         for s in streams:
             s.synchronize()
         e1.record(streams[0])
         e1.synchronize()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if ws > 1:
-            t = torch.tensor([ms], device="cuda" if dist.get_backend() == "nccl" else "cpu", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    nproofs = args.steps * PROOFS_PER_STEP
+    nwarm = max(warmup * PROOFS_PER_STEP, inflight)
     launches0 = sum(c.get("launches") for c in ctxs)
     stat0 = [bpg.lib().bpg_rng_batcher_stat(k) for k in range(3)]
     cpu0 = time.process_time()
-    nproofs = args.steps * PROOFS_PER_STEP
-    ms_res = timed(step_resident, nproofs, warmup, ctxs)
+    ms_res = timed(run_resident, nproofs, nwarm)
     cpu_res = time.process_time() - cpu0
-    cpu_res_workers = worker_cpu[0]
     launches = sum(c.get("launches") for c in ctxs) - launches0
-    ms_e2e = timed(step_e2e, nproofs, warmup, ctxs)
-    ms_stmt = timed(step_statement, nproofs, warmup, ctxs)
+    ms_e2e = timed(run_e2e, nproofs, nwarm)
+    ms_stmt = None if args.no_extra_legs else timed(run_statement, nproofs, nwarm)
     stat1 = [bpg.lib().bpg_rng_batcher_stat(k) for k in range(3)]
     cpu_parts = {k: sum(c.get("cpu_%s_ns" % k) for c in ctxs) * 1e-9 for k in ("sync", "commit", "prove", "verify", "rng")}
-    lat_steps = 10
-    ms_lat = timed(step_resident, lat_steps, warmup, ctxs[:1])
+    lat_n = 10
+    ms_lat = timed(run_resident, lat_n, 3, ctxs[:1])
     sampler.stop_flag = True
 
-    # dominant kernel (MSM bucket accumulation): one instrumented step, CUDA events around every launch
+    # one instrumented statement: CUDA events around every MSM stage (synchronous mode of the library)
     ctx0.set("time_accum", 1)
-    step_resident(ctx0, 10 ** 6)
+    run_resident(10 ** 6, 1, ctxs[:1])
     acc_ns, acc_entries = ctx0.get("sum_accum_ns"), ctx0.get("sum_entries")
     sct_ns, sct_points = ctx0.get("sum_scatter_ns"), ctx0.get("sum_points")
+    step_stage_ms = {nm: ctx0.get("stage_ns_%d" % i) * 1e-6 for i, nm in enumerate(MSM_STAGES)}
+    step_msms = ctx0.get("timed_msms")
     ctx0.set("time_accum", 0)
+    imad_wide_peak, imad32_peak = ctx0.measure_imad_peak()
+    peak_tops = imad_wide_peak / 1e12
 
     # second half of the BASELINE metric: raw fixed-base MSM (verifier mega-MSM shape), 2n' = 2^18 points, uniform
     # scalars resident in HBM; whole MSM (all stages + 128-byte read-back + host ristretto compression)
-    import numpy as np
     npts = 2 * st.n
     sc_np = np.random.default_rng(7).integers(0, 256, size=(npts, 32), dtype=np.uint8)
     sc_np[:, 31] &= 0x0F
     d_sc = torch.from_numpy(sc_np).to(dev)
+    msm_call = lambda: ctx0.msm_gens_dev(d_sc.data_ptr(), st.n, d_sc.data_ptr() + 32 * st.n, st.n)
     for _ in range(3):
-        ctx0.msm_gens_dev(d_sc.data_ptr(), st.n, d_sc.data_ptr() + 32 * st.n, st.n)
+        msm_call()
     streams[0].synchronize()
     msm_runs = []
     for _ in range(5):      # wall clock around synchronous calls: median of five batches of ten
         t0 = time.perf_counter()
         for _ in range(10):
-            ctx0.msm_gens_dev(d_sc.data_ptr(), st.n, d_sc.data_ptr() + 32 * st.n, st.n)
+            msm_call()
         msm_runs.append((time.perf_counter() - t0) / 10)
     msm_s = sorted(msm_runs)[len(msm_runs) // 2]
+    ctx0.set("time_accum", 1)
+    for _ in range(5):
+        msm_call()
+    msm_stage_us = {nm: ctx0.get("stage_ns_%d" % i) / ctx0.get("timed_msms") / 1e3 for i, nm in enumerate(MSM_STAGES)}
+    msm_cl = ctx0.get("last_chunk_len")
+    ctx0.set("time_accum", 0)
+    del d_sc
+
+    config4 = msm_sharded = None
+    if not args.no_extra_legs:
+        # ---- BASELINE config 4: a batch of independent small proofs, statement i on rank i mod N (strong scaling) ----
+        texts = W.batch_texts(args.config4_count)
+        mine = sharding.shard_jobs(args.config4_count, ws, rank)
+        jobs = [("batch-%d" % i, texts[i][1], texts[i][2], texts[i][0]) for i in mine]
+        sd = [(i + 1).to_bytes(32, "little") for i in mine]
+
+        def run_c4(first, n, use=None):
+            out = bpg.prove_text_batch(ctxs, jobs[:n], sd[:n], sd[:n], verify=True)
+            if not all(o[0] == 0 and o[3] for o in out):
+                raise SystemExit("config 4: a proof did not verify")
+
+        ms_c4 = timed(run_c4, len(jobs), min(len(jobs), 4 * inflight))
+        config4 = {"proofs": args.config4_count, "value": args.config4_count / (ms_c4 * 1e-3), "unit": UNIT, "scaling": "strong",
+                   "workload": "LESS_THAN (n=379) / SET_MEMBER k=16 (n=32) alternating, statement i on rank i mod N; text in, "
+                               "proof out and verified (bpg_prove_batch with BPG_JOB_VERIFY), front end inside the timer",
+                   "ms": ms_c4}
+        # ---- BASELINE config 5 at N GPUs: ONE MSM of 2^lg points split by contiguous point range ----
+        lg = args.sharded_lg
+        half = 1 << (lg - 1)
+        g0, g1 = sharding.point_ranges(half, ws)[rank]
+        ctx0.gens_ensure(half)
+        rng_s = np.random.default_rng(99)          # every rank draws the same scalars and keeps its slice
+        allsc = rng_s.integers(0, 256, size=(2 * half, 32), dtype=np.uint8)
+        allsc[:, 31] &= 0x0F
+        dG = torch.from_numpy(allsc[g0:g1].copy()).to(dev)
+        dH = torch.from_numpy(allsc[half + g0: half + g1].copy()).to(dev)
+        part_call = lambda: ctx0.msm_gens_range_dev(dG.data_ptr(), g0, g1 - g0, dH.data_ptr(), g0, g1 - g0)
+        for _ in range(3):
+            part = part_call()
+        barrier()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        for _ in range(reps):
+            part = part_call()
+            if ws > 1:
+                parts = [None] * ws
+                dist.all_gather_object(parts, part)       # 32 bytes per rank, host side
+            else:
+                parts = [part]
+            total_pt = sharding.point_sum(parts) if rank == 0 else None
+        e1.record(streams[0])
+        e1.synchronize()
+        ms_sh = max_over_ranks(e0.elapsed_time(e1)) / reps
+        msm_sharded = {"points": 2 * half, "mpoints_per_s": 2 * half / (ms_sh * 1e-3) / 1e6, "ms": ms_sh, "scaling": "strong",
+                       "result": total_pt.hex() if total_pt else None,
+                       "frac_of_imad_peak": 16 * 2 * half * IMAD_PER_MADD / (ms_sh * 1e-3) / (ws * imad_wide_peak),
+                       "note": "uniform scalars resident in HBM, every rank multiplies its contiguous range of G and H, the "
+                               "N compressed partial points are gathered on the host (gloo) and added by bpg_point_sum; "
+                               "the gather and the sum are inside the timed region"}
+        del dG, dH
 
     dist_backend = dist.get_backend() if ws > 1 else None
     if ws > 1:
@@ -339,7 +374,7 @@ def main():
     e2e_value = ws * nproofs / (ms_e2e * 1e-3)
     achieved = acc_entries * IMAD_PER_MADD / (acc_ns * 1e-9) / 1e12 if acc_ns else None
     lg = max(st.n - 1, 0).bit_length()
-    # bytes crossing PCIe per e2e step, counted from the buffers handed to the C ABI plus the library's own uploads
+    # bytes crossing PCIe per e2e statement, counted from the buffers handed to the C ABI plus the library's own uploads
     csr = 4 * (st.q + 1) + 36 * st.nnz
     h2d = 2 * 32 * st.n + csr            # bpg_prover_load_cs: a_L, a_R, CSR constraints
     h2d += csr                           # bpg_verifier_load_cs
@@ -347,46 +382,52 @@ def main():
     h2d += 128 * st.n                    # 64-byte TranscriptRng draws for s_L, s_R (reduced mod l on the device)
     h2d += 32 * (6 + st.m + 5 + 2 * lg) * 2  # verifier: compressed points + head scalars
     d2h = 32 * st.m + 128 * (3 + 2 * lg) + 9 * 32 + 64 + 128 + 16  # commitments, A/S/L/R points, t scalars, a/b, check point, flags
+    kernel_ms_per_statement = acc_ns * 1e-6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
                    "proofs_per_step": PROOFS_PER_STEP, "inflight": inflight, "dist_backend": (dist_backend if ws > 1 else None),
+                   "api": "bpg_r1cs_prove_batch (BPG_JOB_VERIFY): library-owned host threads, one context per statement in flight",
                    "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
-                   "rng": "transcript rng seeded per step; proofs byte-identical to the CPU oracle",
-                   "window_bits": ctx0.get("window_bits"), "task_len": 32},
+                   "rng": "transcript rng seeded per statement; proofs byte-identical to the CPU oracle",
+                   "window_bits": ctx0.get("window_bits"), "chunk_len": "device-derived (one wave of equal chunks)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d * PROOFS_PER_STEP, "d2h_bytes_per_step": d2h * PROOFS_PER_STEP},
-        "e2e_statement": {"value": ws * nproofs / (ms_stmt * 1e-3), "unit": UNIT, "ms_per_step": ms_stmt / args.steps,
-                          "note": "text formats in, proof + commitments text out and back in: bpg_prove / bpg_verify (the "
-                                  "c_prove / c_verify mirror), host front end (parse, gadgets, witness assignment, "
-                                  "flattening) inside the timed region on both sides"},
-        "latency": {"ms_per_proof": ms_lat / lat_steps, "proofs": lat_steps,
+        "latency": {"ms_per_proof": ms_lat / lat_n, "proofs": lat_n,
                     "note": "one proof+verify at a time on one context; the prover waits on the host for the sequential "
                             "Merlin TranscriptRng stream (2n Keccak-f permutations)"},
-        "msm": {"points": npts, "mpoints_per_s": npts / msm_s / 1e6, "ms": msm_s * 1e3, "ms_batches": [round(x * 1e3, 4) for x in msm_runs], "scalars": "uniform mod l",
-                "frac_of_imad_peak_whole_msm": 16 * npts * IMAD_PER_MADD / msm_s / (IMAD_WIDE_PEAK_TOPS * 1e12),
-                "note": "one GPU; sweep 2^10..2^22 in profiles/r01_configs_1gpu.jsonl (tools/bench_configs.py)"},
+        "msm": {"points": npts, "mpoints_per_s": npts / msm_s / 1e6, "ms": msm_s * 1e3, "ms_batches": [round(x * 1e3, 4) for x in msm_runs],
+                "scalars": "uniform mod l", "chunk_len": msm_cl,
+                "frac_of_imad_peak_whole_msm": 16 * npts * IMAD_PER_MADD / msm_s / imad_wide_peak,
+                "stage_us": {k: round(v, 1) for k, v in msm_stage_us.items()},
+                "stage_note": "CUDA events between the launches of one MSM in the library's synchronous timing mode "
+                              "(each figure carries ~3 us of event / launch gap); `ms` is wall clock without events",
+                "note": "one GPU; sweep 2^12..2^22 in profiles/r02_msm_stages.jsonl (tools/gpu_msm_stages.py)"},
+        "msm_stages_per_statement_ms": {"msms": step_msms, **{k: round(v, 4) for k, v in step_stage_ms.items()}},
         "gpu_launches": launches,
-        "host": {"cores": os.cpu_count(), "cpu_s_per_proof_rank0": cpu_res / (nproofs + max(warmup * PROOFS_PER_STEP, inflight)),
-                 "cpu_s_per_proof_worker_threads": cpu_res_workers / (nproofs + max(warmup * PROOFS_PER_STEP, inflight)),
-                 "live_threads_cpu_s": _thread_cpu_by_name(),
+        "host": {"cores": os.cpu_count(), "cpu_s_per_proof_rank0": cpu_res / (nproofs + nwarm),
                  "rng_streams": stat1[0] - stat0[0], "rng_vector_batches": stat1[1] - stat0[1],
                  "rng_streams_alone": stat1[2] - stat0[2],
                  "thread_cpu_s_total_all_legs": cpu_parts,
-                 "note": "process CPU time of rank 0 over the resident leg (incl. its warm-up steps); the Merlin rng "
+                 "note": "process CPU time of rank 0 over the resident leg (incl. its warm-up statements); the Merlin rng "
                          "streams of proofs in flight run eight at a time (AVX-512) when batches form"},
         "roofline": {"kernel": "k_accumulate (MSM bucket accumulation, mixed Edwards adds)", "bound": "imad",
-                     "achieved": achieved, "peak": IMAD_WIDE_PEAK_TOPS, "unit": "T IMAD.WIDE/s",
-                     "frac": achieved / IMAD_WIDE_PEAK_TOPS if achieved else None, "traffic": 719.5e6,
-                     "traffic_note": "dram bytes read+write per launch from profiles/r01_accumulate_ncu_details_v2.csv "
-                                     "(IPP-round MSM, 4.19 M entries x 96 B = 403 MB algorithmic gather)",
-                     "peak_source": "tools/imad_peak.cu on this pool (profiles/r01_imad_peak.jsonl); IMAD.WIDE.U32 issues at "
-                                    "28/clk/SM vs 64 for 32-bit IMAD; not in MEASURED_PEAKS.json",
+                     "achieved": achieved, "peak": peak_tops, "unit": "T IMAD.WIDE/s",
+                     "frac": achieved / peak_tops if achieved else None, "traffic": ACC_TRAFFIC_BYTES,
+                     "traffic_note": "dram bytes read+write per launch, ncu --set full of this kernel inside a raw MSM of 2^18 "
+                                     "points (profiles/r02_msm_kernels_details.csv); algorithmic gather 4.19 M entries x 96 B = 403 MB",
+                     "peak_source": "measured in this run: bpg_measure_imad_peak (register-only IMAD.WIDE.U32 issue-rate kernel, "
+                                    "~50 ms); not in MEASURED_PEAKS.json",
+                     "frac_of_int32_imad_peak": achieved * 1e12 / imad32_peak if achieved else None,
+                     "int32_imad_peak_tops": imad32_peak / 1e12,
+                     "int32_note": "the same work against the 32-bit IMAD issue rate north_star literally names: one IMAD.WIDE "
+                                   "counted as one instruction (count it as two 32-bit multiplies and the fraction doubles)",
                      "work": "%d mixed adds x %d IMAD.WIDE" % (acc_entries, IMAD_PER_MADD),
-                     "kernel_ms_per_proof": acc_ns * 1e-6, "share_of_step": acc_ns * 1e-6 / (ms_lat / lat_steps),
-                     "share_note": "share of one un-overlapped proof+verify (the latency leg)"},
+                     "kernel_ms_per_proof": kernel_ms_per_statement,
+                     "share_of_step": kernel_ms_per_statement * PROOFS_PER_STEP / per_step_ms,
+                     "share_note": "kernel time of one statement x statements per step / timed throughput step"},
         # the sort stage north_star asks to see against HBM: digit decomposition + scatter by bucket.  Algorithmic bytes
         # per launch: 32 B per scalar read + 4 B per entry written + 4 B per entry of offset reads.
         "roofline_sort": {"kernel": "k_digits<1> (signed-digit decomposition + counting-sort scatter)", "bound": "hbm",
@@ -395,11 +436,18 @@ def main():
                           "frac": (32 * sct_points + 8 * acc_entries) / (sct_ns * 1e-9) / 1e9 / HBM_PEAK_GBS if sct_ns else None,
                           "traffic": SORT_TRAFFIC_BYTES, "kernel_ms_per_proof": sct_ns * 1e-6,
                           "note": "the scatter pass places entries at bucket offset + the rank the histogram pass's atomicAdd "
-                                  "returned (no atomics of its own); bound by 4-byte scattered stores through L2, not by HBM bytes. "
-                                  "`traffic` is the ncu capture of the earlier atomic version (profiles/r01_digits_ncu_details.csv); "
-                                  "the rank array adds 4 B per entry each way, L2-resident"},
+                                  "returned (no atomics of its own); bound by 4-byte scattered stores through L2, not by HBM bytes"},
         "clocks": sampler.summary(),
     }
+    if ms_stmt is not None:
+        line["e2e_statement"] = {"value": ws * nproofs / (ms_stmt * 1e-3), "unit": UNIT, "ms_per_step": ms_stmt / args.steps,
+                                 "note": "text formats in, proof + commitments text out and back in: bpg_prove_batch (the batched "
+                                         "c_prove / c_verify), host front end (parse, gadgets, witness assignment, flattening) "
+                                         "inside the timed region on both sides"}
+    if config4:
+        line["config4"] = config4
+    if msm_sharded:
+        line["msm_sharded"] = msm_sharded
     if not args.no_cpu_baseline:
         from oracle import coracle
         cst = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank)
@@ -407,7 +455,7 @@ def main():
         p_c, coms_c = coracle.prove_flat(cst, (1).to_bytes(32, "little"), cache_gens=False)
         ok = coracle.verify_flat(cst, coms_c, p_c, (1).to_bytes(32, "little"), cache_gens=False)
         dt = time.perf_counter() - t0
-        same = p_c == step_resident(ctx0, 0)
+        same = p_c == run_resident(0, 1, ctxs[:1])[0][1]
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "the full statement once (prove+verify, generators rebuilt per run as the reference "
                                           "does): %.1f s; CPU proof accepted=%s, byte-identical to the GPU proof=%s" % (dt, ok, same)}

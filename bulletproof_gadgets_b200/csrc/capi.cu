@@ -75,14 +75,127 @@ void* d2h_stage(bpg_ctx* ctx, size_t offset, const void* d_src, size_t bytes) {
 }
 bool host_is_ristretto_identity(const ge_ext& p) { return ge_is_ristretto_identity(p); }
 
+// Device self-test of the field layer: the dedicated squaring against the general product, on pseudo-random 256-bit
+// values whose limbs are biased towards 0 and 2^32-1 (carry chains) -- see bpg_selftest_field.
+__global__ void __launch_bounds__(128) k_selftest_field(uint64_t n, uint64_t seed, uint32_t* __restrict__ bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + 0x9e3779b97f4a7c15ull * (i + 1);
+    auto next = [&]() {
+        x += 0x9e3779b97f4a7c15ull;
+        uint64_t z = x;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    };
+    fe a;
+    const uint64_t shape = next();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t sel = (uint32_t)(shape >> (4 * k)) & 15u;
+        const uint32_t r = (uint32_t)next();
+        a.v[k] = sel == 0 ? 0u : sel == 1 ? 0xffffffffu : sel == 2 ? 0xfffffffeu : sel == 3 ? 1u : r;
+    }
+    const fe s1 = fe_canon(fe_sqr(a)), s2 = fe_canon(fe_mul(a, a));
+    // (a + 1)^2 - a^2 - 2a - 1 == 0 ties the squaring to the adder as well
+    const fe a1 = fe_add(a, fe_one());
+    const fe lhs = fe_sub(fe_sub(fe_sub(fe_sqr(a1), fe_sqr(a)), fe_add(a, a)), fe_one());
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) diff |= s1.v[k] ^ s2.v[k];
+    if (diff || !fe_is_zero(lhs)) atomicAdd(bad, 1u);
+}
+
+// Sustained issue rate of the integer multiplier: 64 independent multiply-adds per thread and iteration, no memory traffic.
+// MODE 0: 32x32 -> 64-bit multiply-add (IMAD.WIDE.U32, what the field multiplication is made of), MODE 1: 32-bit IMAD.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed, int iters) {
+    const uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    uint64_t x0 = threadIdx.x, x1 = a, x2 = b, x3 = a ^ b, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
+    uint32_t y0 = 1, y1 = 2, y2 = 3, y3 = 4, y4 = 5, y5 = 6, y6 = 7, y7 = 8;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (MODE == 0) {
+                x0 = (uint64_t)a * (uint32_t)x0 + x0, x1 = (uint64_t)b * (uint32_t)x1 + x1;
+                x2 = (uint64_t)a * (uint32_t)x2 + x2, x3 = (uint64_t)b * (uint32_t)x3 + x3;
+                x4 = (uint64_t)a * (uint32_t)x4 + x4, x5 = (uint64_t)b * (uint32_t)x5 + x5;
+                x6 = (uint64_t)a * (uint32_t)x6 + x6, x7 = (uint64_t)b * (uint32_t)x7 + x7;
+            } else {
+                y0 = a * y0 + b, y1 = b * y1 + a, y2 = a * y2 + b, y3 = b * y3 + a;
+                y4 = a * y4 + b, y5 = b * y5 + a, y6 = a * y6 + b, y7 = b * y7 + a;
+            }
+        }
+    }
+    const uint64_t s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32) ^ y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7;
+}
+
 extern "C" {
 
 const char* bpg_last_error(void) { return g_err; }
 
+int bpg_measure_imad_peak(bpg_ctx* ctx, double* imad_wide_per_s, double* imad32_per_s) {
+    if (!ctx || !imad_wide_per_s || !imad32_per_s) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, iters = 8000;
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, (size_t)blocks * 256 * 4));
+    cudaEvent_t e0 = ctx->ev_stage[0], e1 = ctx->ev_stage[1];
+    double best[2] = {0, 0};
+    cudaError_t err = cudaSuccess;
+    for (int mode = 0; mode < 2 && err == cudaSuccess; mode++)
+        for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {
+            cudaEventRecord(e0, ctx->stream);
+            if (mode == 0) k_imad_peak<0><<<blocks, 256, 0, ctx->stream>>>(d, rep + 1, iters);
+            else k_imad_peak<1><<<blocks, 256, 0, ctx->stream>>>(d, rep + 1, iters);
+            cudaEventRecord(e1, ctx->stream);
+            err = cudaEventSynchronize(e1);
+            float ms = 0;
+            if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+            const double rate = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
+            if (rep && rate > best[mode]) best[mode] = rate;  // first repetition = warm-up
+        }
+    ctx->launches += 8;
+    cudaFree(d);
+    CUDA_TRY(err);
+    *imad_wide_per_s = best[0];
+    *imad32_per_s = best[1];
+    return BPG_OK;
+}
+
+int bpg_selftest_field(bpg_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!ctx || !mismatches) return BPG_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, 4));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 4, ctx->stream));
+    if (n) k_selftest_field<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(n, seed, d);
+    ctx->launches++;
+    uint32_t h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = ctx_sync(ctx);
+    cudaFree(d);
+    CUDA_TRY(e);
+    *mismatches = h;
+    return BPG_OK;
+}
+
+static int ctx_init(bpg_ctx* ctx, int device);
+// takes over one reference of `store`: released again when the context cannot be built
 static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
     bpg_ctx* ctx = new bpg_ctx();
     ctx->device = device;
     ctx->store = store;
+    const int rc = ctx_init(ctx, device);
+    if (rc != BPG_OK) {
+        bpg_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return BPG_OK;
+}
+static int ctx_init(bpg_ctx* ctx, int device) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {
         // Per-proof device buffers (bulk-loaded circuits) come from a pool private to this context: with the device's
@@ -109,7 +222,6 @@ static int ctx_new(int device, GensStore* store, bpg_ctx** out) {
     if (const char* e = getenv("BPG_TASK_LEN")) ctx->task_len = atoi(e) > 0 && atoi(e) < (1 << 20) ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
-    *out = ctx;
     return BPG_OK;
 }
 
@@ -150,6 +262,7 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
         (*out)->task_len = parent->task_len;
         (*out)->target_chunks = parent->target_chunks;
         (*out)->cl_min = parent->cl_min;
+        (*out)->acc_variant = parent->acc_variant;
         (*out)->use_tickets = parent->use_tickets;
     }
     return rc;
@@ -158,7 +271,7 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
 void bpg_ctx_destroy(bpg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx_sync(ctx);
+    if (ctx->stream && ctx->ev_sync) ctx_sync(ctx);  // (a context whose construction failed half-way has neither)
     MsmWork& w = ctx->work;
     w.hist.release();
     w.bucket_off.release();
@@ -166,17 +279,20 @@ void bpg_ctx_destroy(bpg_ctx* ctx) {
     w.entries.release();
     w.partials.release();
     w.blockres.release();
+    w.reduce_cnt.release();
+    w.reduce_dbg.release();
     w.scan_tmp.release();
     w.tickets.release();
     ctx->d_scalars.release();
     ctx->d_points.release();
     r1cs_release_work(ctx);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
-    for (int k = 0; k <= MSM_STAGES; k++) cudaEventDestroy(ctx->ev_stage[k]);
-    cudaEventDestroy(ctx->ev_sync);
-    cudaStreamDestroy(ctx->stream);
+    for (int k = 0; k <= MSM_STAGES; k++)
+        if (ctx->ev_stage[k]) cudaEventDestroy(ctx->ev_stage[k]);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
-    gens_store_release(ctx->store);
+    if (ctx->store) gens_store_release(ctx->store);
     delete ctx;
 }
 
@@ -201,6 +317,9 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "target_chunks") {
         if (value < 0 || value > (1 << 24)) return BPG_E_ARG;
         ctx->target_chunks = (int)value;
+    } else if (k == "acc_variant") {
+        if (value < 0 || value > 2) return BPG_E_ARG;
+        ctx->acc_variant = (int)value;
     } else if (k == "cl_min") {
         if (value < 1 || value > 4096) return BPG_E_ARG;
         ctx->cl_min = (int)value;
@@ -277,7 +396,7 @@ static int msm_gens_common(bpg_ctx* ctx, const uint32_t* d_sG, uint64_t nG, cons
                            const uint32_t* d_sB, const uint32_t* d_sBb, uint8_t out32[32], uint64_t g_start = 0,
                            uint64_t h_start = 0) {
     const uint64_t cap = ctx->table.capacity;
-    if (g_start + nG > cap || h_start + nH > cap) {
+    if (nG > cap || nH > cap || g_start > cap - nG || h_start > cap - nH) {  // no wrap-around in the sums
         bpg_set_error("msm: %llu/%llu scalars exceed generator capacity %llu", (unsigned long long)nG,
                       (unsigned long long)nH, (unsigned long long)cap);
         return BPG_E_GENS_LEN;
@@ -322,6 +441,10 @@ int bpg_msm_gens_range(bpg_ctx* ctx, const uint8_t* sG, uint64_t g_start, uint64
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!sG) nG = 0;
     if (!sH) nH = 0;
+    if (nG > (1ull << 31) || nH > (1ull << 31) || g_start > (1ull << 31) || h_start > (1ull << 31)) {
+        bpg_set_error("msm: range exceeds 2^31 points");
+        return BPG_E_GENS_LEN;
+    }
     int rc;
     if ((rc = check_scalars(sG, nG)) || (rc = check_scalars(sH, nH)) || (sB && (rc = check_scalars(sB, 1))) ||
         (sBb && (rc = check_scalars(sBb, 1))))
@@ -361,17 +484,23 @@ int bpg_point_sum(const uint8_t* points32n, uint64_t n, uint8_t out32[32]) {
     return BPG_OK;
 }
 
-int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH, const void* d_sB,
-                     const void* d_sBb, uint8_t out32[32]) {
+int bpg_msm_gens_range_dev(bpg_ctx* ctx, const void* d_sG, uint64_t g_start, uint64_t nG, const void* d_sH, uint64_t h_start,
+                           uint64_t nH, const void* d_sB, const void* d_sBb, uint8_t out32[32]) {
     if (!ctx || !out32) return BPG_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!d_sG) nG = 0;
     if (!d_sH) nH = 0;
-    uint64_t need = nG > nH ? nG : nH;
+    if (nG > (1ull << 31) || nH > (1ull << 31) || g_start > (1ull << 31) || h_start > (1ull << 31)) return BPG_E_GENS_LEN;
+    const uint64_t need = g_start + nG > h_start + nH ? g_start + nG : h_start + nH;
     int rc;
     if ((rc = gens_build(ctx, need ? need : 1))) return rc;
     return msm_gens_common(ctx, (const uint32_t*)d_sG, nG, (const uint32_t*)d_sH, nH, (const uint32_t*)d_sB,
-                           (const uint32_t*)d_sBb, out32);
+                           (const uint32_t*)d_sBb, out32, g_start, h_start);
+}
+
+int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH, const void* d_sB,
+                     const void* d_sBb, uint8_t out32[32]) {
+    return bpg_msm_gens_range_dev(ctx, d_sG, 0, nG, d_sH, 0, nH, d_sB, d_sBb, out32);
 }
 
 // ---------------------------------------------------------------------------- transcript

@@ -107,7 +107,9 @@ struct MsmWork {
     DevBuf<MsmMeta> meta;
     DevBuf<uint32_t> entries;       // [K*N] (row | sign << 31), sorted by bucket
     DevBuf<ge_ext> partials;        // slot (chunk t, bucket b) = t + b
-    DevBuf<ge_ext> blockres;        // [2][G / buckets-per-CTA][REDUCE_MAXV] ping-pong of the reduction butterfly
+    DevBuf<ge_ext> blockres;        // CTA / group / set states of the reduction butterfly (msm.cu: ReduceScratch)
+    DevBuf<unsigned long long> reduce_dbg;  // diagnostic phase stamps of k_bucket_reduce (BPG_REDUCE_TRACE)
+    DevBuf<uint32_t> reduce_cnt;    // arrival counters of the reduction's group and set stages (zero between launches)
     DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan (multi-CTA fallback)
     DevBuf<uint32_t> tickets;       // [16][points] rank of each entry inside its bucket (histogram pass -> scatter pass)
 };
@@ -130,6 +132,7 @@ struct bpg_ctx {
     int task_len = 0;         // entries per k_accumulate thread; 0 = derived on the device: one full wave of equal chunks
     int target_chunks = 0;    // chunks aimed at when task_len == 0 (0 = SMs x resident CTAs x threads), at least cl_min entries each
     int cl_min = 8;
+    int acc_variant = 0;      // k_accumulate variant (msm.cu): 0 = 4 CTAs/SM, 1 = next row prefetched, 2 = 5 CTAs/SM
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
     int sm_count = 148;
     // counters for bench.py ("gpu_launches")

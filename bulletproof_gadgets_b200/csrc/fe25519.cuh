@@ -404,36 +404,19 @@ BPG_HD void fe_mul_wide(uint32_t r[16], const fe& a, const fe& b) {
 BPG_HD fe fe_fold(const uint32_t t[16]) {
     fe r;
 #ifdef __CUDA_ARCH__
-    uint32_t r8;
+    // r = t[0..8) + 38 * t[8..16): the eight 32x32->64 products 38 * t[8+k] ride two carry chains of four
+    // IMAD.WIDE each (even k on limbs k, k+1; odd k likewise one limb up), as the rows of the product do
+    uint32_t acc[9];
     const uint32_t k38 = 38u;
-    // lo halves: r[k] = t[k] + lo(38*t[8+k]) (+carry), carry-out into r8
-    asm("mad.lo.cc.u32 %0, %17, %25, %9;\n\t"
-        "madc.lo.cc.u32 %1, %18, %25, %10;\n\t"
-        "madc.lo.cc.u32 %2, %19, %25, %11;\n\t"
-        "madc.lo.cc.u32 %3, %20, %25, %12;\n\t"
-        "madc.lo.cc.u32 %4, %21, %25, %13;\n\t"
-        "madc.lo.cc.u32 %5, %22, %25, %14;\n\t"
-        "madc.lo.cc.u32 %6, %23, %25, %15;\n\t"
-        "madc.lo.cc.u32 %7, %24, %25, %16;\n\t"
-        "addc.u32 %8, 0, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7]), "=r"(r8)
-        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]),
-          "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]), "r"(k38));
-    // hi halves: r[k+1] += hi(38*t[8+k])
-    asm("mad.hi.cc.u32 %0, %8, %16, %0;\n\t"
-        "madc.hi.cc.u32 %1, %9, %16, %1;\n\t"
-        "madc.hi.cc.u32 %2, %10, %16, %2;\n\t"
-        "madc.hi.cc.u32 %3, %11, %16, %3;\n\t"
-        "madc.hi.cc.u32 %4, %12, %16, %4;\n\t"
-        "madc.hi.cc.u32 %5, %13, %16, %5;\n\t"
-        "madc.hi.cc.u32 %6, %14, %16, %6;\n\t"
-        "madc.hi.u32 %7, %15, %16, %7;"
-        : "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]),
-          "+r"(r8)
-        : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
-          "r"(k38));
-    // r8 <= 38 + 37 + 1; fold it, then a possible final wrap (value then < 2^12)
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = t[k];
+    acc[8] = 0;
+    FE_MADROW9(acc, t[8], t[10], t[12], t[14], k38);
+    FE_MADROW8(acc + 1, t[9], t[11], t[13], t[15], k38);
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = acc[k];
+    uint32_t r8 = acc[8];
+    // r8 <= 1 + 37 + 1; fold it, then a possible final wrap (value then < 2^12)
     uint32_t k = r8 * 38u, c2;
     asm("add.cc.u32 %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, 0;\n\t"
@@ -474,7 +457,116 @@ BPG_HD fe fe_mul(const fe& a, const fe& b) {
     return fe_fold(t);
 }
 
-BPG_HD fe fe_sqr(const fe& a) { return fe_mul(a, a); }
+// Dedicated squaring: 28 cross products + 8 squares = 36 IMAD.WIDE instead of 64 (every doubling, the inverse-square-root
+// chains of the ristretto codec and the generator-table build are squaring-heavy).  The carry-chain schedule below is
+// generated and checked limb by limb by tools/gen_fe_sqr.py.
+#ifdef __CUDA_ARCH__
+#define FE_SQ_MADROW7(acc, a0, a1, a2, b)                                                                     \
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"                                                                  \
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"                                                                 \
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"                                                                 \
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"                                                                 \
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"                                                                 \
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"                                                                 \
+        "addc.u32 %6, %6, 0;"                                                                                 \
+        : "+r"((acc)[0]), "+r"((acc)[1]), "+r"((acc)[2]), "+r"((acc)[3]), "+r"((acc)[4]), "+r"((acc)[5]),     \
+          "+r"((acc)[6])                                                                                      \
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b))
+#define FE_SQ_MADROW5(acc, a0, a1, b)                                                                         \
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"                                                                   \
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"                                                                  \
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"                                                                  \
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"                                                                  \
+        "addc.u32 %4, %4, 0;"                                                                                 \
+        : "+r"((acc)[0]), "+r"((acc)[1]), "+r"((acc)[2]), "+r"((acc)[3]), "+r"((acc)[4])                      \
+        : "r"(a0), "r"(a1), "r"(b))
+#define FE_SQ_MADROW3(acc, a0, b)                                                                             \
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"                                                                   \
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"                                                                  \
+        "addc.u32 %2, %2, 0;"                                                                                 \
+        : "+r"((acc)[0]), "+r"((acc)[1]), "+r"((acc)[2])                                                      \
+        : "r"(a0), "r"(b))
+#endif
+
+// r[0..16) = a*a
+BPG_HD void fe_sqr_wide(uint32_t r[16], const fe& a) {
+#ifdef __CUDA_ARCH__
+    uint32_t E[17], O[16];
+#pragma unroll
+    for (int k = 0; k < 17; k++) E[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) O[k] = 0;
+    // cross products a_i a_j, i < j (even columns -> E, odd columns -> O, as in fe_mul_wide)
+    FE_MADROW9(O + 0, a.v[1], a.v[3], a.v[5], a.v[7], a.v[0]);
+    FE_SQ_MADROW7(E + 2, a.v[2], a.v[4], a.v[6], a.v[0]);
+    FE_SQ_MADROW7(O + 2, a.v[2], a.v[4], a.v[6], a.v[1]);
+    FE_SQ_MADROW7(E + 4, a.v[3], a.v[5], a.v[7], a.v[1]);
+    FE_SQ_MADROW7(O + 4, a.v[3], a.v[5], a.v[7], a.v[2]);
+    FE_SQ_MADROW5(E + 6, a.v[4], a.v[6], a.v[2]);
+    FE_SQ_MADROW5(O + 6, a.v[4], a.v[6], a.v[3]);
+    FE_SQ_MADROW5(E + 8, a.v[5], a.v[7], a.v[3]);
+    FE_SQ_MADROW5(O + 8, a.v[5], a.v[7], a.v[4]);
+    FE_SQ_MADROW3(E + 10, a.v[6], a.v[4]);
+    FE_SQ_MADROW3(O + 10, a.v[6], a.v[5]);
+    FE_SQ_MADROW3(E + 12, a.v[7], a.v[5]);
+    FE_SQ_MADROW3(O + 12, a.v[7], a.v[6]);
+    // C = E + (O << 32)
+    r[0] = E[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]),
+          "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
+          "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+    // 2C
+#pragma unroll
+    for (int k = 15; k > 0; k--) r[k] = __funnelshift_l(r[k - 1], r[k], 1);
+    r[0] <<= 1;
+    // + a_i^2 at limbs 2i, 2i+1: one carry chain (the product fits 512 bits, so no carry leaves the top)
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+          "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+#else
+    fe_mul_wide(r, a, a);
+#endif
+}
+
+BPG_HD fe fe_sqr(const fe& a) {
+    uint32_t t[16];
+    fe_sqr_wide(t, a);
+    return fe_fold(t);
+}
 
 // small-constant multiply (k < 2^31)
 BPG_HD fe fe_mul_small(const fe& a, uint32_t k) {

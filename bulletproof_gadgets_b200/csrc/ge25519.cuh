@@ -87,6 +87,24 @@ BPG_HD ge_ext ge_madd(const ge_ext& p, const ge_niels& q, bool neg) {
     return r;
 }
 
+// The same with the sign already applied to the (y+x, y-x) pair by the caller (qa = neg ? y+x : y-x, qb = the other one --
+// the bucket kernel swaps the two load addresses instead of selecting 16 limbs); only F / G still depend on the sign.
+BPG_HD ge_ext ge_madd_swapped(const ge_ext& p, const fe& qa, const fe& qb, const fe& t2d, bool neg) {
+    fe A = fe_mul(fe_sub(p.Y, p.X), qa);
+    fe B = fe_mul(fe_add(p.Y, p.X), qb);
+    fe C = fe_mul(p.T, t2d);
+    fe Dd = fe_add(p.Z, p.Z);
+    fe E = fe_sub(B, A), H = fe_add(B, A);
+    fe DmC = fe_sub(Dd, C), DpC = fe_add(Dd, C);
+    fe F = fe_select(neg, DpC, DmC), G = fe_select(neg, DmC, DpC);
+    ge_ext r;
+    r.X = fe_mul(E, F);
+    r.Y = fe_mul(G, H);
+    r.Z = fe_mul(F, G);
+    r.T = fe_mul(E, H);
+    return r;
+}
+
 // r = 2p: dbl-2008-hwcd (a=-1), 4M + 4S
 BPG_HD ge_ext ge_dbl(const ge_ext& p) {
     fe A = fe_sqr(p.X), B = fe_sqr(p.Y);
@@ -103,6 +121,25 @@ BPG_HD ge_ext ge_dbl(const ge_ext& p) {
     r.Y = fe_mul(G, H);
     r.Z = fe_mul(F, G);
     r.T = fe_mul(E, H);
+    return r;
+}
+
+// 2p without the T coordinate (3M + 4S): for runs of doublings, where only the last one needs T (ge_dbl reads X, Y, Z only)
+BPG_HD ge_ext ge_dbl_not(const ge_ext& p) {
+    fe A = fe_sqr(p.X), B = fe_sqr(p.Y);
+    fe C = fe_sqr(p.Z);
+    C = fe_add(C, C);
+    fe Dn = fe_neg(A);
+    fe xy = fe_add(p.X, p.Y);
+    fe E = fe_sub(fe_sub(fe_sqr(xy), A), B);
+    fe G = fe_add(Dn, B);
+    fe F = fe_sub(G, C);
+    fe H = fe_sub(Dn, B);
+    ge_ext r;
+    r.X = fe_mul(E, F);
+    r.Y = fe_mul(G, H);
+    r.Z = fe_mul(F, G);
+    r.T = p.T;  // not maintained
     return r;
 }
 

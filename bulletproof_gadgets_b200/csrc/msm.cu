@@ -27,11 +27,11 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "circuit.hpp"
 #include "ctx.hpp"
 
-#define FINAL_THREADS 256
 #define BR_THREADS 128  // buckets per CTA of k_bucket_reduce
 #define BR_CAP 8       // partial slots a lane sums alone before the warp shares the rest of a heavy bucket
 #define SMALL_MSM_MAX_POINTS 4096u  // MSMs up to 2 x this many points use the 8-bit-window table
@@ -184,6 +184,23 @@ __device__ __forceinline__ ge_niels load_niels(const ge_niels* __restrict__ rows
     q.t2d.v[4] = f.x, q.t2d.v[5] = f.y, q.t2d.v[6] = f.z, q.t2d.v[7] = f.w;
     return q;
 }
+// the (y+x, y-x) pair comes back as (qa, qb) = neg ? (y+x, y-x) : (y-x, y+x): the sign of the digit swaps two addresses
+struct niels_swapped {
+    fe qa, qb, t2d;
+};
+__device__ __forceinline__ niels_swapped load_niels_swapped(const ge_niels* __restrict__ rows, uint32_t row, bool neg) {
+    const uint4* p = reinterpret_cast<const uint4*>(rows + row);
+    const int oa = neg ? 0 : 2, ob = 2 - oa;
+    uint4 a = __ldg(p + oa), b = __ldg(p + oa + 1), c = __ldg(p + ob), d = __ldg(p + ob + 1), e = __ldg(p + 4), f = __ldg(p + 5);
+    niels_swapped q;
+    q.qa.v[0] = a.x, q.qa.v[1] = a.y, q.qa.v[2] = a.z, q.qa.v[3] = a.w;
+    q.qa.v[4] = b.x, q.qa.v[5] = b.y, q.qa.v[6] = b.z, q.qa.v[7] = b.w;
+    q.qb.v[0] = c.x, q.qb.v[1] = c.y, q.qb.v[2] = c.z, q.qb.v[3] = c.w;
+    q.qb.v[4] = d.x, q.qb.v[5] = d.y, q.qb.v[6] = d.z, q.qb.v[7] = d.w;
+    q.t2d.v[0] = e.x, q.t2d.v[1] = e.y, q.t2d.v[2] = e.z, q.t2d.v[3] = e.w;
+    q.t2d.v[4] = f.x, q.t2d.v[5] = f.y, q.t2d.v[6] = f.z, q.t2d.v[7] = f.w;
+    return q;
+}
 __device__ __forceinline__ void store_ext(ge_ext* dst, const ge_ext& p) {
     uint4* o = reinterpret_cast<uint4*>(dst);
     const fe* f[4] = {&p.X, &p.Y, &p.Z, &p.T};
@@ -220,6 +237,18 @@ __device__ __forceinline__ void block_tree_reduce(ge_ext* sh, ge_ext& mine, uint
     }
 }
 
+__device__ __forceinline__ ge_ext shfl_ext(const ge_ext& p, int src) {
+    ge_ext r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.X.v[i] = __shfl_sync(0xffffffffu, p.X.v[i], src);
+        r.Y.v[i] = __shfl_sync(0xffffffffu, p.Y.v[i], src);
+        r.Z.v[i] = __shfl_sync(0xffffffffu, p.Z.v[i], src);
+        r.T.v[i] = __shfl_sync(0xffffffffu, p.T.v[i], src);
+    }
+    return r;
+}
+
 // smallest j in (lo, hi] with bucket_off[j] > e; the entry e lives in bucket j - 1
 __device__ __forceinline__ uint32_t bucket_upper(const uint32_t* __restrict__ bucket_off, uint32_t lo, uint32_t hi, uint32_t e) {
     while (lo < hi) {
@@ -231,14 +260,18 @@ __device__ __forceinline__ uint32_t bucket_upper(const uint32_t* __restrict__ bu
 
 // Chunk t = sorted entries [t*CL, (t+1)*CL).  Partial slot of (chunk t, bucket b) = t + b: buckets are sorted along the
 // entries, so the sum is unique, and the slots of one bucket are contiguous: chunks off[b]/CL .. (off[b+1]-1)/CL, every one
-// of them used.  A CTA whose ACC_THREADS chunks all lie inside ONE bucket (0/1-valued a_L vectors, the 16 digit buckets of
-// a_R = -1: a single bucket holds 2^16 .. 2^21 entries) adds its threads' sums in shared memory and emits one partial at
-// the slot of its first chunk; k_bucket_reduce derives the same predicate from bucket_off and skips the other slots.
-__global__ void __launch_bounds__(ACC_THREADS, 4)
+// of them used.  A warp whose 32 chunks all lie inside ONE bucket (0/1-valued a_L vectors, the 16 digit buckets of
+// a_R = -1: a single bucket holds 2^16 .. 2^21 entries; small MSMs on the 128-bucket table) adds its lanes' sums with
+// shuffles and emits one partial at the slot of its first chunk, and a CTA whose warps all did so emits one partial for
+// the CTA; k_bucket_reduce derives the same predicates from bucket_off and skips the other slots.
+// VARIANT 0: 4 CTAs per SM (<= 128 registers); 1: the next Niels row in flight during the addition, 3 CTAs per SM;
+// 2: 5 CTAs per SM (<= 96 registers, a few spilled words outside the inner loop)
+template <int VARIANT>
+__global__ void __launch_bounds__(ACC_THREADS, VARIANT == 1 ? 3 : VARIANT == 2 ? 5 : 4)
     k_accumulate(const ge_niels* __restrict__ rows, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ bucket_off, const MsmMeta* __restrict__ meta, uint32_t G,
                  ge_ext* __restrict__ partials) {
-    __shared__ ge_ext sh[ACC_THREADS];
+    __shared__ ge_ext sh[ACC_THREADS / 32];
     __shared__ uint32_t sh_b0;
     const uint32_t E = meta->E, CL = meta->CL;
     const uint64_t blk_e0 = (uint64_t)blockIdx.x * ACC_THREADS * CL;
@@ -259,8 +292,38 @@ __global__ void __launch_bounds__(ACC_THREADS, 4)
     const uint32_t b0 = sh_b0;
     const uint64_t blk_e1 = min(blk_e0 + (uint64_t)ACC_THREADS * CL, (uint64_t)E);
     const bool uniform = blk_e1 <= bucket_off[b0 + 1];
+    // the same test per warp (32 consecutive chunks inside one bucket)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t bw0 = __shfl_sync(0xffffffffu, b, 0);
+    const uint64_t w_e0 = (uint64_t)(t - lane) * CL;
+    const uint64_t w_e1 = min(w_e0 + (uint64_t)32 * CL, (uint64_t)E);
+    const bool w_uniform = w_e0 < E && w_e1 <= bucket_off[bw0 + 1];
     ge_ext acc = ge_identity();
-    if (active) {
+    if (active && VARIANT == 1) {  // variant: the Niels row of entry e+1 is in flight while entry e is added
+        uint32_t ent = __ldg(entries + e0);
+        ge_niels q = load_niels(rows, ent & 0x7fffffffu);
+#pragma unroll 1
+        for (uint32_t e = e0; e < e1; e++) {
+            if (e == next) {
+                store_ext(partials + t + b, acc);
+                acc = ge_identity();
+                b++;
+                next = bucket_off[b + 1];
+                if (next == e) {
+                    const uint32_t j = bucket_upper(bucket_off, b + 1, G, e);
+                    b = j - 1;
+                    next = bucket_off[j];
+                }
+            }
+            const bool neg = ent >> 31;
+            const ge_niels cur = q;
+            if (e + 1 < e1) {
+                ent = __ldg(entries + e + 1);
+                q = load_niels(rows, ent & 0x7fffffffu);
+            }
+            acc = ge_madd(acc, cur, neg);
+        }
+    } else if (active) {
         uint32_t ent = __ldg(entries + e0);
 #pragma unroll 1
         for (uint32_t e = e0; e < e1; e++) {
@@ -275,69 +338,139 @@ __global__ void __launch_bounds__(ACC_THREADS, 4)
                     next = bucket_off[j];
                 }
             }
-            ge_niels q = load_niels(rows, ent & 0x7fffffffu);
             const bool neg = ent >> 31;
+            const niels_swapped q = load_niels_swapped(rows, ent & 0x7fffffffu, neg);
             if (e + 1 < e1) ent = __ldg(entries + e + 1);
-            acc = ge_madd(acc, q, neg);
+            acc = ge_madd_swapped(acc, q.qa, q.qb, q.t2d, neg);
         }
     }
-    if (!uniform) {
+    if (!w_uniform) {  // (a uniform CTA consists of uniform warps)
         if (active) store_ext(partials + t + b, acc);
         return;
     }
-    block_tree_reduce(sh, acc, threadIdx.x, ACC_THREADS);
-    if (threadIdx.x == 0) store_ext(partials + blockIdx.x * ACC_THREADS + b0, load_ext(sh));
+    // all 32 chunks of this warp lie in bucket bw0: one partial per warp, at the slot of the warp's first chunk
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        const ge_ext other = shfl_ext(acc, (int)(lane ^ o));
+        acc = ge_add(acc, other);
+    }
+    if (!uniform) {
+        if (lane == 0) store_ext(partials + t + bw0, acc);
+        return;
+    }
+    // all chunks of the CTA lie in bucket b0: one partial per CTA
+    const uint32_t wid = threadIdx.x >> 5;
+    if (lane == 0) store_ext(sh + wid, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t nw = (uint32_t)((blk_e1 - blk_e0 + (uint64_t)32 * CL - 1) / ((uint64_t)32 * CL));  // warps with work
+#pragma unroll 1
+        for (uint32_t k = 1; k < nw; k++) acc = ge_add(acc, load_ext(sh + k));
+        store_ext(partials + blockIdx.x * ACC_THREADS + b0, acc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // stage 5 / 6: sum_b (b + 1) * S_b without scalar multiplications
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ ge_ext shfl_ext(const ge_ext& p, int src) {
-    ge_ext r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        r.X.v[i] = __shfl_sync(0xffffffffu, p.X.v[i], src);
-        r.Y.v[i] = __shfl_sync(0xffffffffu, p.Y.v[i], src);
-        r.Z.v[i] = __shfl_sync(0xffffffffu, p.Z.v[i], src);
-        r.T.v[i] = __shfl_sync(0xffffffffu, p.T.v[i], src);
-    }
-    return r;
-}
-
-// The partial slots of bucket gb as a virtual list: chunks before the first collapsed CTA, one slot per collapsed CTA
-// (see k_accumulate), chunks after the last one.
+// The partial slots of bucket gb as a virtual list of five runs (see k_accumulate): single chunks before the first
+// collapsed warp, collapsed warps before the first collapsed CTA, collapsed CTAs, collapsed warps after them, single
+// chunks after the last collapsed warp.
 struct SlotList {
-    uint32_t gb, t_lo, n_pre, k_lo, n_col, t_post, n;
+    uint32_t gb, n;
+    uint32_t s0, n0;  // chunks   s0 + i
+    uint32_t s1, n1;  // warps    32 * (s1 + i)
+    uint32_t s2, n2;  // CTAs     ACC_THREADS * (s2 + i)
+    uint32_t s3, n3;  // warps    32 * (s3 + i)
+    uint32_t s4;      // chunks   s4 + i
     __device__ __forceinline__ uint32_t slot(uint32_t i) const {
-        if (i < n_pre) return t_lo + i + gb;
-        i -= n_pre;
-        if (i < n_col) return (k_lo + i) * ACC_THREADS + gb;
-        return t_post + (i - n_col) + gb;
+        if (i < n0) return s0 + i + gb;
+        i -= n0;
+        if (i < n1) return 32 * (s1 + i) + gb;
+        i -= n1;
+        if (i < n2) return ACC_THREADS * (s2 + i) + gb;
+        i -= n2;
+        if (i < n3) return 32 * (s3 + i) + gb;
+        return s4 + (i - n3) + gb;
     }
 };
+// units [u_lo, u_hi) of `span` chunks that lie completely inside the bucket's entries [lo, hi) (the last unit may be cut by E)
+__device__ __forceinline__ void whole_units(uint32_t lo, uint32_t hi, uint32_t E, uint64_t span_entries, uint32_t* u_lo, uint32_t* u_hi) {
+    *u_lo = (uint32_t)((lo + span_entries - 1) / span_entries);
+    *u_hi = hi == E ? (uint32_t)((E + span_entries - 1) / span_entries) : (uint32_t)(hi / span_entries);
+}
 __device__ __forceinline__ SlotList slot_list(uint32_t gb, uint32_t lo, uint32_t hi, uint32_t E, uint32_t CL) {
     SlotList L;
     L.gb = gb;
-    L.t_lo = L.n_pre = L.k_lo = L.n_col = L.t_post = L.n = 0;
+    L.n = L.s0 = L.n0 = L.s1 = L.n1 = L.s2 = L.n2 = L.s3 = L.n3 = L.s4 = 0;
     if (hi <= lo) return L;
     const uint32_t t_lo = lo / CL, t_hi = (hi - 1) / CL;
-    const uint64_t bcl = (uint64_t)ACC_THREADS * CL;
-    // CTA k of k_accumulate collapsed into one partial iff  lo <= k*bcl  and  min((k+1)*bcl, E) <= hi
-    const uint32_t k_lo = (uint32_t)((lo + bcl - 1) / bcl);
-    const uint32_t k_hi = hi == E ? (uint32_t)((E + bcl - 1) / bcl) : (uint32_t)(hi / bcl);
-    L.t_lo = t_lo;
-    uint32_t n_post = 0;
-    if (k_hi <= k_lo) {
-        L.n_pre = t_hi - t_lo + 1;
-    } else {
-        L.n_pre = k_lo * ACC_THREADS - t_lo;
-        L.k_lo = k_lo;
-        L.n_col = k_hi - k_lo;
-        L.t_post = k_hi * ACC_THREADS;
-        n_post = t_hi >= L.t_post ? t_hi - L.t_post + 1 : 0;
+    uint32_t w_lo, w_hi, k_lo, k_hi;
+    whole_units(lo, hi, E, (uint64_t)32 * CL, &w_lo, &w_hi);
+    L.s0 = t_lo;
+    if (w_hi <= w_lo) {  // no collapsed warp
+        L.n = L.n0 = t_hi - t_lo + 1;
+        return L;
     }
-    L.n = L.n_pre + L.n_col + n_post;
+    L.n0 = 32 * w_lo - t_lo;
+    L.s4 = 32 * w_hi;
+    const uint32_t n4 = t_hi >= L.s4 ? t_hi - L.s4 + 1 : 0;
+    whole_units(lo, hi, E, (uint64_t)ACC_THREADS * CL, &k_lo, &k_hi);
+    const uint32_t wpb = ACC_THREADS / 32;
+    if (k_hi <= k_lo) {  // no collapsed CTA
+        L.s1 = w_lo;
+        L.n1 = w_hi - w_lo;
+    } else {
+        L.s1 = w_lo;
+        L.n1 = wpb * k_lo - w_lo;
+        L.s2 = k_lo;
+        L.n2 = k_hi - k_lo;
+        L.s3 = wpb * k_hi;
+        L.n3 = w_hi > L.s3 ? w_hi - L.s3 : 0;
+    }
+    L.n = L.n0 + L.n1 + L.n2 + L.n3 + n4;
     return L;
+}
+
+__device__ __forceinline__ ge_ext load_ext_cg(const ge_ext* src) {  // L2 loads: data written by other SMs
+    const uint4* o = reinterpret_cast<const uint4*>(src);
+    ge_ext p;
+    fe* f[4] = {&p.X, &p.Y, &p.Z, &p.T};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint4 a = __ldcg(o + 2 * k), b = __ldcg(o + 2 * k + 1);
+        f[k]->v[0] = a.x, f[k]->v[1] = a.y, f[k]->v[2] = a.z, f[k]->v[3] = a.w;
+        f[k]->v[4] = b.x, f[k]->v[5] = b.y, f[k]->v[6] = b.z, f[k]->v[7] = b.w;
+    }
+    return p;
+}
+
+// Butterfly levels over `nseg` segment states of L + 1 values each (state s at src + s * REDUCE_MAXV), all threads of the
+// CTA: joins neighbours until one state of L + log2(nseg) + 1 values is left; returns where it lives (ping-pong a / b).
+__device__ const ge_ext* butterfly_levels(const ge_ext* src, ge_ext* a, ge_ext* b, uint32_t nseg, uint32_t* L_io) {
+    uint32_t L = *L_io;
+    const ge_ext* cur = src;
+    ge_ext* nxt = a;
+    while (nseg > 1) {
+        const uint32_t nv = L + 2, items = (nseg >> 1) * nv;
+#pragma unroll 1
+        for (uint32_t i = threadIdx.x; i < items; i += blockDim.x) {
+            const uint32_t q = i / nv, v = i - q * nv;
+            const ge_ext* A = cur + (size_t)(2 * q) * REDUCE_MAXV;
+            const ge_ext* B = A + REDUCE_MAXV;
+            ge_ext r;
+            if (v == L + 1) r = load_ext_cg(B);
+            else r = ge_add(load_ext_cg(A + v), load_ext_cg(B + v));
+            store_ext(nxt + (size_t)q * REDUCE_MAXV + v, r);
+        }
+        __syncthreads();
+        cur = nxt;
+        nxt = nxt == a ? b : a;
+        nseg >>= 1;
+        L++;
+    }
+    *L_io = L;
+    return cur;
 }
 
 // One thread per bucket (BR_THREADS consecutive buckets of one set per CTA; a set with fewer buckets gets one CTA).
@@ -345,41 +478,73 @@ __device__ __forceinline__ SlotList slot_list(uint32_t gb, uint32_t lo, uint32_t
 // is strided over the warp.  Phase 2: butterfly over the bucket-index bits.  After level k every aligned segment of
 // 2^(k+1) threads holds, at its positions 0 .. k+1:  R = sum of the segment,  M_j = sum of its buckets with index bit
 // j set (j <= k).  Joining the lower half A and the upper half B: R = R_A + R_B, M_j = M_j,A + M_j,B (j < k), M_k = R_B
-// -- one addition per lane.  The CTA emits lv + 1 points; k_reduce_final continues across CTAs.
+// -- one addition per lane.  Phase 3: the CTA that arrives last in its group of `gsize` CTAs joins the group's states
+// (log2 gsize more levels), and the last group of a set joins the group states and finishes
+//     sum_b (b + 1) S_b = R + sum_j 2^j M_j          (lane i doubles M_{i-1} i-1 times, then a warp tree).
+// No scalar multiplication anywhere; the serial part is lv + log2(nb / bpb) additions and c - 2 doublings.
+struct ReduceScratch {
+    ge_ext* cta;     // [br_blocks][REDUCE_MAXV] CTA states; also ping-pong a of the group stage
+    ge_ext* tmp;     // [br_blocks][REDUCE_MAXV] ping-pong b of the group stage
+    ge_ext* grp;     // [n_groups][REDUCE_MAXV] group states
+    ge_ext* fin;     // [2][n_groups][REDUCE_MAXV] ping-pong of the set stage
+    uint32_t* cnt;   // [n_groups + nsets] arrival counters, zero between launches
+    unsigned long long* dbg;  // diagnostic mode: [gridDim.x][8] %globaltimer stamps of the phases of every CTA (or NULL)
+};
+__device__ __forceinline__ void phase_stamp(const ReduceScratch& sc, int phase) {
+    if (sc.dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sc.dbg[(size_t)blockIdx.x * 8 + phase] = t;
+    }
+}
 __global__ void __launch_bounds__(BR_THREADS)
     k_bucket_reduce(const ge_ext* __restrict__ partials, const uint32_t* __restrict__ bucket_off,
                     const MsmMeta* __restrict__ meta, uint32_t bpb /* buckets per CTA, power of two <= BR_THREADS */,
-                    uint32_t lv /* log2(bpb) */, ge_ext* __restrict__ blockres) {
+                    uint32_t lv /* log2(bpb) */, uint32_t nblk /* CTAs per set */, uint32_t gsize /* CTAs per group */,
+                    ReduceScratch sc, ge_ext* __restrict__ result) {
     __shared__ ge_ext sh[BR_THREADS];
+    __shared__ uint32_t sh_last;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t E = meta->E, CL = meta->CL;
+    phase_stamp(sc, 0);
     ge_ext val = ge_identity();
     SlotList L;
-    L.gb = L.t_lo = L.n_pre = L.k_lo = L.n_col = L.t_post = L.n = 0;
+    L.gb = L.n = L.s0 = L.n0 = L.s1 = L.n1 = L.s2 = L.n2 = L.s3 = L.n3 = L.s4 = 0;
     if (tid < bpb) {
         const uint32_t gb = blockIdx.x * bpb + tid;
         L = slot_list(gb, bucket_off[gb], bucket_off[gb + 1], E, CL);
-        if (L.n) val = load_ext(partials + L.slot(0));
-        const uint32_t own = min(L.n, (uint32_t)BR_CAP);
+    }
+    // Lanes walk their own slots up to twice the warp's average (balanced buckets: every lane busy, no cooperation
+    // needed); only what an outlier bucket holds beyond that is strided over the whole warp.
+    uint32_t tot = L.n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const uint32_t cap = max((uint32_t)BR_CAP, 2 * (tot >> 5) + 4);
+    if (L.n) val = load_ext(partials + L.slot(0));
+    {
+        const uint32_t own = min(L.n, cap);
 #pragma unroll 1
         for (uint32_t i = 1; i < own; i++) val = ge_add(val, load_ext(partials + L.slot(i)));
     }
-    // heavy buckets: every lane of the warp takes a strided share of the slots beyond the first BR_CAP
-    uint32_t heavy = __ballot_sync(0xffffffffu, L.n > BR_CAP);
+    uint32_t heavy = __ballot_sync(0xffffffffu, L.n > cap);
     while (heavy) {
         const int owner = __ffs(heavy) - 1;
         heavy &= heavy - 1;
         SlotList H;
         H.gb = __shfl_sync(0xffffffffu, L.gb, owner);
-        H.t_lo = __shfl_sync(0xffffffffu, L.t_lo, owner);
-        H.n_pre = __shfl_sync(0xffffffffu, L.n_pre, owner);
-        H.k_lo = __shfl_sync(0xffffffffu, L.k_lo, owner);
-        H.n_col = __shfl_sync(0xffffffffu, L.n_col, owner);
-        H.t_post = __shfl_sync(0xffffffffu, L.t_post, owner);
         H.n = __shfl_sync(0xffffffffu, L.n, owner);
+        H.s0 = __shfl_sync(0xffffffffu, L.s0, owner);
+        H.n0 = __shfl_sync(0xffffffffu, L.n0, owner);
+        H.s1 = __shfl_sync(0xffffffffu, L.s1, owner);
+        H.n1 = __shfl_sync(0xffffffffu, L.n1, owner);
+        H.s2 = __shfl_sync(0xffffffffu, L.s2, owner);
+        H.n2 = __shfl_sync(0xffffffffu, L.n2, owner);
+        H.s3 = __shfl_sync(0xffffffffu, L.s3, owner);
+        H.n3 = __shfl_sync(0xffffffffu, L.n3, owner);
+        H.s4 = __shfl_sync(0xffffffffu, L.s4, owner);
         ge_ext part = ge_identity();
 #pragma unroll 1
-        for (uint32_t i = BR_CAP + lane; i < H.n; i += 32) part = ge_add(part, load_ext(partials + H.slot(i)));
+        for (uint32_t i = cap + lane; i < H.n; i += 32) part = ge_add(part, load_ext(partials + H.slot(i)));
 #pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
             const ge_ext other = shfl_ext(part, lane ^ o);
@@ -387,7 +552,8 @@ __global__ void __launch_bounds__(BR_THREADS)
         }
         if ((int)lane == owner) val = ge_add(val, part);
     }
-    // butterfly
+    phase_stamp(sc, 1);
+    // butterfly inside the CTA
 #pragma unroll 1
     for (uint32_t k = 0; k < lv; k++) {
         const uint32_t h = 1u << k, p = tid & (2 * h - 1);
@@ -405,47 +571,58 @@ __global__ void __launch_bounds__(BR_THREADS)
         if (p <= k) val = ge_add(val, other);
         else if (p == k + 1 && k >= 2) val = other;
     }
-    if (tid <= lv) store_ext(blockres + (size_t)blockIdx.x * REDUCE_MAXV + tid, val);
-}
-
-// One CTA per bucket set: the butterfly levels lv .. c-2 over the nblk segment states left by k_bucket_reduce (ping-pong
-// between the two halves of `blockres`), then  result = R + sum_j 2^j M_j  (lane i doubles M_{i-1} i-1 times).
-__global__ void __launch_bounds__(FINAL_THREADS)
-    k_reduce_final(ge_ext* __restrict__ blockres, uint32_t nblk /* CTAs of k_bucket_reduce per set */, uint32_t lv,
-                   size_t half /* points per ping-pong half */, ge_ext* __restrict__ result) {
-    const uint32_t s = blockIdx.x, tid = threadIdx.x;
-    ge_ext* cur = blockres + (size_t)s * nblk * REDUCE_MAXV;
-    ge_ext* nxt = cur + half;
-    uint32_t nseg = nblk, L = lv;  // every segment holds L + 1 values
-    while (nseg > 1) {
-        const uint32_t nv = L + 2, items = (nseg >> 1) * nv;
-#pragma unroll 1
-        for (uint32_t i = tid; i < items; i += FINAL_THREADS) {
-            const uint32_t q = i / nv, v = i - q * nv;
-            const ge_ext* A = cur + (size_t)(2 * q) * REDUCE_MAXV;
-            const ge_ext* B = A + REDUCE_MAXV;
-            ge_ext r;
-            if (v == L + 1) r = load_ext(B);
-            else r = ge_add(load_ext(A + v), load_ext(B + v));
-            store_ext(nxt + (size_t)q * REDUCE_MAXV + v, r);
-        }
+    if (tid <= lv) store_ext(sc.cta + (size_t)blockIdx.x * REDUCE_MAXV + tid, val);
+    phase_stamp(sc, 2);
+    // group stage: the last CTA of the group to arrive joins the group's states
+    const uint32_t set = blockIdx.x / nblk, ngrp = nblk / gsize;  // groups per set
+    const uint32_t group = blockIdx.x / gsize;                    // global group index
+    uint32_t Lc = lv;
+    const ge_ext* state = sc.cta + (size_t)blockIdx.x * REDUCE_MAXV;
+    if (gsize > 1) {
+        __threadfence();
         __syncthreads();
-        ge_ext* tmp = cur;
-        cur = nxt;
-        nxt = tmp;
-        nseg >>= 1;
-        L++;
+        if (tid == 0) sh_last = atomicAdd(sc.cnt + group, 1u) == gsize - 1;
+        __syncthreads();
+        if (!sh_last) return;
+        if (tid == 0) sc.cnt[group] = 0;
+        __threadfence();
+        const size_t g0 = (size_t)group * gsize * REDUCE_MAXV;
+        state = butterfly_levels(sc.cta + g0, sc.tmp + g0, sc.cta + g0, gsize, &Lc);
+        phase_stamp(sc, 3);
+    }
+    // set stage: the last group of the set joins the group states and finishes
+    if (ngrp > 1) {
+        if (tid <= Lc) store_ext(sc.grp + (size_t)group * REDUCE_MAXV + tid, load_ext_cg(state + tid));
+        __threadfence();
+        __syncthreads();
+        const uint32_t nctr = gridDim.x / gsize;  // group counters come first
+        if (tid == 0) sh_last = atomicAdd(sc.cnt + nctr + set, 1u) == ngrp - 1;
+        __syncthreads();
+        if (!sh_last) return;
+        if (tid == 0) sc.cnt[nctr + set] = 0;
+        __threadfence();
+        const size_t s0 = (size_t)set * ngrp * REDUCE_MAXV, half = (size_t)nctr * REDUCE_MAXV;
+        state = butterfly_levels(sc.grp + s0, sc.fin + s0, sc.fin + half + s0, ngrp, &Lc);
+        phase_stamp(sc, 4);
+    } else {
+        __syncthreads();  // `state` was written by this CTA's threads
     }
     if (tid >= 32) return;
-    ge_ext v = tid <= L ? load_ext(cur + tid) : ge_identity();
+    ge_ext v = tid <= Lc ? load_ext_cg(state + tid) : ge_identity();
+    if (tid >= 2 && tid <= Lc) {
 #pragma unroll 1
-    for (uint32_t k = 1; k < tid && tid <= L; k++) v = ge_dbl(v);
+        for (uint32_t k = 2; k < tid; k++) v = ge_dbl_not(v);
+        v = ge_dbl(v);
+    }
+    __syncwarp();
+    phase_stamp(sc, 5);
 #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
         const ge_ext other = shfl_ext(v, (int)(tid ^ o));
         v = ge_add(v, other);
     }
-    if (tid == 0) store_ext(result + s, v);
+    if (tid == 0) store_ext(result + set, v);
+    phase_stamp(sc, 6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -516,13 +693,19 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     const uint64_t max_partials = (uint64_t)acc_blocks * ACC_THREADS + G + 1;
     const uint32_t bpb = nb < BR_THREADS ? nb : BR_THREADS, lv = ilog2(bpb);
     const uint32_t br_blocks = G / bpb, nblk = nb / bpb;
-    const size_t half = (size_t)br_blocks * REDUCE_MAXV;
+    const uint32_t gsize = nblk >= 64 ? 16u : nblk >= 4 ? 4u : nblk;  // CTAs per group (power of two dividing nblk)
+    const uint32_t n_groups = br_blocks / gsize;
     MsmWork& w = ctx->work;
     int rc;
     if ((rc = w.hist.ensure(G + 16)) || (rc = w.bucket_off.ensure(G + 16)) || (rc = w.meta.ensure(1)) ||
         (rc = w.entries.ensure(max_entries + 1)) || (rc = w.partials.ensure(max_partials)) ||
-        (rc = w.blockres.ensure(2 * half)))
+        (rc = w.blockres.ensure((2 * (size_t)br_blocks + 3 * (size_t)n_groups) * REDUCE_MAXV)) ||
+        (rc = w.reduce_cnt.ensure(n_groups + nsets)))
         return rc;
+    if (w.reduce_cnt.fresh) {  // arrival counters: zero between launches (the last arriver re-zeroes its counter)
+        CUDA_TRY(cudaMemsetAsync(w.reduce_cnt.p, 0, w.reduce_cnt.cap * 4, st));
+        w.reduce_cnt.fresh = false;
+    }
 
     uint32_t* tickets = nullptr;  // rank of every entry inside its bucket (unrolled K <= 16 path of k_digits only)
     if (ctx->use_tickets && tb.K <= 16 && total > 0) {
@@ -553,13 +736,29 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
         if (!tickets) w.hist_dirty = true;  // the scatter pass used it as its cursor
     }
     CUDA_TRY(mark());
-    k_accumulate<<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
+    if (ctx->acc_variant == 2)
+        k_accumulate<2><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
+    else if (ctx->acc_variant == 1)
+        k_accumulate<1><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
+    else
+        k_accumulate<0><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
     CUDA_TRY(mark());
-    k_bucket_reduce<<<br_blocks, BR_THREADS, 0, st>>>(w.partials.p, w.bucket_off.p, w.meta.p, bpb, lv, w.blockres.p);
+    ReduceScratch rs;
+    rs.cta = w.blockres.p;
+    rs.tmp = rs.cta + (size_t)br_blocks * REDUCE_MAXV;
+    rs.grp = rs.tmp + (size_t)br_blocks * REDUCE_MAXV;
+    rs.fin = rs.grp + (size_t)n_groups * REDUCE_MAXV;
+    rs.cnt = w.reduce_cnt.p;
+    rs.dbg = nullptr;
+    if (timed && getenv("BPG_REDUCE_TRACE")) {
+        if ((rc = w.reduce_dbg.ensure((size_t)br_blocks * 8))) return rc;
+        CUDA_TRY(cudaMemsetAsync(w.reduce_dbg.p, 0, (size_t)br_blocks * 64, st));
+        rs.dbg = w.reduce_dbg.p;
+    }
+    k_bucket_reduce<<<br_blocks, BR_THREADS, 0, st>>>(w.partials.p, w.bucket_off.p, w.meta.p, bpb, lv, nblk, gsize, rs, d_out);
     CUDA_TRY(mark());
-    k_reduce_final<<<nsets, FINAL_THREADS, 0, st>>>(w.blockres.p, nblk, lv, half, d_out);
     CUDA_TRY(mark());
-    ctx->launches += 3;
+    ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     if (timed) {  // diagnostic mode: synchronous, reads back the entry count and the chunk length
         CUDA_TRY(ctx_sync(ctx));
@@ -578,6 +777,18 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
         if (total > 0) {
             ctx->sum_scatter_ms += ms[2];
             ctx->sum_points += total;
+        }
+        if (rs.dbg) {  // phase profile of the reduction kernel: latest stamp of every phase relative to the earliest start
+            std::vector<unsigned long long> h((size_t)br_blocks * 8);
+            CUDA_TRY(cudaMemcpy(h.data(), rs.dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull, last[8] = {0};
+            for (uint32_t b = 0; b < br_blocks; b++)
+                if (h[(size_t)b * 8]) t0 = std::min(t0, h[(size_t)b * 8]);
+            for (uint32_t b = 0; b < br_blocks; b++)
+                for (int k = 0; k < 8; k++) last[k] = std::max(last[k], h[(size_t)b * 8 + k]);
+            fprintf(stderr, "[bpg reduce] ctas %u: last start +%.1f, slots summed +%.1f, cta butterfly +%.1f, group +%.1f, set +%.1f, "
+                    "doublings +%.1f, done +%.1f us\n", br_blocks, (last[0] - t0) * 1e-3, (last[1] - t0) * 1e-3, (last[2] - t0) * 1e-3,
+                    last[3] ? (last[3] - t0) * 1e-3 : 0.0, last[4] ? (last[4] - t0) * 1e-3 : 0.0, (last[5] - t0) * 1e-3, (last[6] - t0) * 1e-3);
         }
         if (getenv("BPG_ACC_TRACE"))
             fprintf(stderr, "[bpg msm] sets %u points %llu entries %u CL %u | digits0 %.1f scan %.1f digits1 %.1f accumulate %.1f "

@@ -82,65 +82,90 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict_
 // sets of 2^15), writes the G+1 offsets, re-zeroes the histogram for the next MSM and derives the chunk geometry of the
 // bucket-accumulation kernel from the entry count E (msm.cu).
 // ------------------------------------------------------------------------------------------
-// Each thread owns PER consecutive counters (PER = G / 1024 rounded up to a multiple of 4, <= 64), so G <= 65 536 is ONE
-// pass: all loads in flight at once, one block scan, stores.  Larger G loops over tiles of 65 536.
-#define SM_MAXPER 64
-template <int PER>
-__device__ __forceinline__ uint32_t scan_tile(uint32_t* __restrict__ hist, uint32_t* __restrict__ off, uint32_t base, uint32_t G,
-                                              uint32_t carry, uint32_t* sh) {
-    const uint32_t idx = base + threadIdx.x * PER;
-    uint32_t v[PER], s = 0;
-    const bool vec = (G % 4) == 0;  // base and idx are multiples of 4: whole uint4 groups are inside or outside
-    if (vec) {
-#pragma unroll
-        for (int k = 0; k < PER / 4; k++) {
-            uint4 q = make_uint4(0u, 0u, 0u, 0u);
-            if (idx + 4 * k < G) q = *reinterpret_cast<const uint4*>(hist + idx + 4 * k);
-            v[4 * k] = q.x, v[4 * k + 1] = q.y, v[4 * k + 2] = q.z, v[4 * k + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < PER; k++) v[k] = idx + k < G ? hist[idx + k] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < PER; k++) s += v[k];
-    uint32_t total;
-    uint32_t pre = carry + block_exclusive_scan(s, &total, sh);
-    if (vec) {
-#pragma unroll
-        for (int k = 0; k < PER / 4; k++) {
-            uint4 q;
-            q.x = pre, pre += v[4 * k];
-            q.y = pre, pre += v[4 * k + 1];
-            q.z = pre, pre += v[4 * k + 2];
-            q.w = pre, pre += v[4 * k + 3];
-            if (idx + 4 * k < G) {
-                *reinterpret_cast<uint4*>(off + idx + 4 * k) = q;
-                *reinterpret_cast<uint4*>(hist + idx + 4 * k) = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < PER; k++) {
-            if (idx + k < G) {
-                off[idx + k] = pre;
-                hist[idx + k] = 0u;
-            }
-            pre += v[k];
-        }
-    }
-    return total;
-}
+// Warp w owns the contiguous range [w * span, (w + 1) * span), span = G / 32 rounded up to a multiple of 128, and walks it
+// in steps of 128 counters: one coalesced uint4 load per lane and step, all steps in flight at once, a shuffle scan per
+// step, then the 32 warp totals are scanned through shared memory.  G <= 32 768 is one pass (8 steps); larger G loops (two bucket sets: two passes).
+#define SM_STEPS 8
 __global__ void __launch_bounds__(1024) k_scan_meta(uint32_t* __restrict__ hist, uint32_t* __restrict__ off, uint32_t G,
                                                     uint32_t target_chunks, uint32_t cl_min, uint32_t cl_fixed,
                                                     MsmMeta* __restrict__ meta) {
-    __shared__ uint32_t sh[32];
+    __shared__ uint32_t sh_tot[32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool vec = (G % 4) == 0;
     uint32_t carry = 0;
-    if (G <= 1024 * 4) carry = scan_tile<4>(hist, off, 0, G, 0, sh);
-    else if (G <= 1024 * 16) carry = scan_tile<16>(hist, off, 0, G, 0, sh);
-    else if (G <= 1024 * 32) carry = scan_tile<32>(hist, off, 0, G, 0, sh);
-    else
-        for (uint32_t base = 0; base < G; base += 1024 * SM_MAXPER) carry += scan_tile<SM_MAXPER>(hist, off, base, G, carry, sh);
+    for (uint32_t tile = 0; tile < G; tile += 32u * 128u * SM_STEPS) {
+        const uint32_t tile_n = min(G - tile, 32u * 128u * SM_STEPS);
+        const uint32_t span = ((tile_n + 31) / 32 + 127) / 128 * 128;
+        const uint32_t steps = span / 128;
+        const uint32_t w0 = tile + wid * span;
+        uint32_t v[SM_STEPS][4];
+#pragma unroll
+        for (int k = 0; k < SM_STEPS; k++) {
+            const uint32_t idx = w0 + k * 128 + lane * 4;
+            v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0;
+            if ((uint32_t)k < steps && idx < tile + tile_n) {
+                if (vec) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(hist + idx);
+                    v[k][0] = q.x, v[k][1] = q.y, v[k][2] = q.z, v[k][3] = q.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (idx + j < tile + tile_n) v[k][j] = hist[idx + j];
+                }
+            }
+        }
+        // exclusive prefix of every lane's group of four inside the warp's range
+        uint32_t pre[SM_STEPS], run = 0;
+#pragma unroll
+        for (int k = 0; k < SM_STEPS; k++) {
+            const uint32_t s = v[k][0] + v[k][1] + v[k][2] + v[k][3];
+            uint32_t inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += t;
+            }
+            pre[k] = run + inc - s;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) sh_tot[wid] = run;
+        __syncthreads();
+        uint32_t wtot = sh_tot[lane], winc = wtot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += t;
+        }
+        const uint32_t wbase = carry + __shfl_sync(0xffffffffu, winc - wtot, wid);
+        const uint32_t tile_total = __shfl_sync(0xffffffffu, winc, 31);
+#pragma unroll
+        for (int k = 0; k < SM_STEPS; k++) {
+            const uint32_t idx = w0 + k * 128 + lane * 4;
+            if ((uint32_t)k < steps && idx < tile + tile_n) {
+                uint32_t p = wbase + pre[k];
+                if (vec) {
+                    uint4 q;
+                    q.x = p, p += v[k][0];
+                    q.y = p, p += v[k][1];
+                    q.z = p, p += v[k][2];
+                    q.w = p;
+                    *reinterpret_cast<uint4*>(off + idx) = q;
+                    *reinterpret_cast<uint4*>(hist + idx) = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (idx + j < tile + tile_n) {
+                            off[idx + j] = p;
+                            hist[idx + j] = 0u;
+                        }
+                        p += v[k][j];
+                    }
+                }
+            }
+        }
+        carry += tile_total;
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         const uint32_t E = carry;
         off[G] = E;

@@ -52,6 +52,15 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value);
 /* counters: "launches" (kernels launched so far), "accum_us" / "accum_entries" (last timed MSM) */
 int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key);
 
+/* Device self-test of the field layer (no reference counterpart): n pseudo-random 256-bit values with limbs biased towards
+ * 0 and 2^32-1; checks the dedicated squaring against the general product and (a+1)^2 - a^2 - 2a - 1 == 0. */
+int bpg_selftest_field(bpg_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
+
+/* Sustained issue rate of the integer multiplier on this GPU, in instructions (thread level) per second: 32x32->64-bit
+ * multiply-add (IMAD.WIDE.U32, the unit of the MSM roofline) and 32-bit IMAD.  A ~50 ms register-only kernel; the
+ * denominator bench.py reports `roofline.frac` against (no reference counterpart). */
+int bpg_measure_imad_peak(bpg_ctx* ctx, double* imad_wide_per_s, double* imad32_per_s);
+
 /* BulletproofGens::new(capacity, 1) + PedersenGens::default()
  *   -- /root/reference/src/prove.rs:46,78 ; /root/reference/src/verify.rs:45,70.
  * Derives G_i, H_i (SHAKE256 "GeneratorsChain" stream on the host, Elligator on the GPU) and
@@ -79,6 +88,8 @@ int bpg_point_sum(const uint8_t* points32n, uint64_t n, uint8_t out32[32]);
 /* Same with DEVICE pointers (scalars already resident in HBM, canonical). */
 int bpg_msm_gens_dev(bpg_ctx* ctx, const void* d_sG, uint64_t nG, const void* d_sH, uint64_t nH,
                      const void* d_sB, const void* d_sBb, uint8_t out32[32]);
+int bpg_msm_gens_range_dev(bpg_ctx* ctx, const void* d_sG, uint64_t g_start, uint64_t nG, const void* d_sH, uint64_t h_start,
+                           uint64_t nH, const void* d_sB, const void* d_sBb, uint8_t out32[32]);
 /* sum s[i]*P_i over arbitrary compressed points (dalek vartime_multiscalar_mul /
  * optional_multiscalar_mul).  Returns BPG_E_VERIFY if a point does not decode. */
 int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars32n, const uint8_t* points32n, uint64_t n, uint8_t out32[32]);

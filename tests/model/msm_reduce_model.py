@@ -21,28 +21,30 @@ def accumulate(entries, off, G, CL):
     E = off[G]
     partials = {}
     nblocks = (E + ACC_THREADS * CL - 1) // (ACC_THREADS * CL)
+
+    def put(slot, v):
+        assert slot not in partials
+        partials[slot] = v
+
     for blk in range(nblocks + 1):           # one block beyond the end: must exit
         blk_e0 = blk * ACC_THREADS * CL
         if blk_e0 >= E:
             continue
-        accs, b0 = [], None
         blk_e1 = min(blk_e0 + ACC_THREADS * CL, E)
+        lanes = []                            # per thread: (active, acc, b_final, b_start)
         for tid in range(ACC_THREADS):
             t = blk * ACC_THREADS + tid
             e0 = t * CL
             if e0 >= E:
-                accs.append((0, None))
+                lanes.append((False, 0, 0, 0))
                 continue
             e1 = min(e0 + CL, E)
             j = bucket_upper(off, 0, G, e0)
             b, nxt = j - 1, off[j]
-            if tid == 0:
-                b0 = b
-            acc = 0
+            b_start, acc = b, 0
             for e in range(e0, e1):
                 if e == nxt:
-                    assert (t + b) not in partials
-                    partials[t + b] = acc
+                    put(t + b, acc)
                     acc = 0
                     b += 1
                     nxt = off[b + 1]
@@ -50,32 +52,56 @@ def accumulate(entries, off, G, CL):
                         j = bucket_upper(off, b + 1, G, e)
                         b, nxt = j - 1, off[j]
                 acc += entries[e]
-            accs.append((acc, t + b))
+            lanes.append((True, acc, b, b_start))
+        b0 = lanes[0][3]
         uniform = blk_e1 <= off[b0 + 1]
-        if not uniform:
-            for acc, slot in accs:
-                if slot is not None:
-                    assert slot not in partials
-                    partials[slot] = acc
-        else:
-            s = blk * ACC_THREADS + b0
-            assert s not in partials
-            partials[s] = sum(a for a, _ in accs)
+        warp_sums = []
+        for w in range(ACC_THREADS // 32):
+            t0 = blk * ACC_THREADS + 32 * w
+            w_e0 = t0 * CL
+            w_e1 = min(w_e0 + 32 * CL, E)
+            bw0 = lanes[32 * w][3]
+            w_uniform = w_e0 < E and w_e1 <= off[bw0 + 1]
+            if not w_uniform:
+                assert not (uniform and w_e0 < E)
+                for k in range(32):
+                    act, acc, b, _ = lanes[32 * w + k]
+                    if act:
+                        put(t0 + k + b, acc)
+                continue
+            tot = sum(lanes[32 * w + k][1] for k in range(32))
+            if not uniform:
+                put(t0 + bw0, tot)
+            else:
+                warp_sums.append(tot)
+        if uniform:
+            nw = (blk_e1 - blk_e0 + 32 * CL - 1) // (32 * CL)
+            assert nw == len(warp_sums)
+            put(blk * ACC_THREADS + b0, sum(warp_sums))
     return partials
+
+
+def whole_units(lo, hi, E, span):
+    return (lo + span - 1) // span, ((E + span - 1) // span if hi == E else hi // span)
 
 
 def slot_list(gb, lo, hi, E, CL):
     if hi <= lo:
         return []
     t_lo, t_hi = lo // CL, (hi - 1) // CL
-    bcl = ACC_THREADS * CL
-    k_lo = (lo + bcl - 1) // bcl
-    k_hi = (E + bcl - 1) // bcl if hi == E else hi // bcl
-    if k_hi <= k_lo:
+    w_lo, w_hi = whole_units(lo, hi, E, 32 * CL)
+    if w_hi <= w_lo:
         return [t + gb for t in range(t_lo, t_hi + 1)]
-    out = [t + gb for t in range(t_lo, k_lo * ACC_THREADS)]
-    out += [k * ACC_THREADS + gb for k in range(k_lo, k_hi)]
-    out += [t + gb for t in range(k_hi * ACC_THREADS, t_hi + 1)]
+    out = [t + gb for t in range(t_lo, 32 * w_lo)]
+    k_lo, k_hi = whole_units(lo, hi, E, ACC_THREADS * CL)
+    wpb = ACC_THREADS // 32
+    if k_hi <= k_lo:
+        out += [32 * w + gb for w in range(w_lo, w_hi)]
+    else:
+        out += [32 * w + gb for w in range(w_lo, wpb * k_lo)]
+        out += [ACC_THREADS * k + gb for k in range(k_lo, k_hi)]
+        out += [32 * w + gb for w in range(wpb * k_hi, w_hi)]
+    out += [t + gb for t in range(32 * w_hi, t_hi + 1)]
     return out
 
 

@@ -32,6 +32,16 @@ def test_generators_match_golden_and_oracle(ctx):
     assert ctx.gens_compressed("H", 4000, 96) == coracle.gens("H", 4000, 96)
 
 
+def test_field_selftest_on_device(ctx):
+    """fe_sqr (36 IMAD.WIDE schedule, tools/gen_fe_sqr.py) == fe_mul(a, a) on 4 M biased values, on the device."""
+    import ctypes
+    import bulletproof_gadgets_b200 as bpg
+    bad = ctypes.c_uint64(99)
+    for seed in (1, 2):
+        assert bpg.lib().bpg_selftest_field(ctx._h, 1 << 21, seed, ctypes.byref(bad)) == 0
+        assert bad.value == 0
+
+
 EDGE_CASES = [
     ([], [], None, None), ([1], [], None, None), ([], [], 1, None), ([], [], None, 5), ([0, 0], [0], 0, 0),
     ([L - 1], [2], 3, L - 4), ([1] * 64, [1] * 64, None, None), ([2**255 - 1], [2**252], None, None),

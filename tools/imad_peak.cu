@@ -55,6 +55,21 @@ __global__ void __launch_bounds__(128, 4) k_madd(ge_ext* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// latency of a dependent chain of point operations in one thread (what the bucket reduction's serial part is made of)
+template <int OP>
+__global__ void __launch_bounds__(128) k_chain(ge_ext* out, int iters) {
+    ge_ext p = ge_identity(), q;
+    for (int i = 0; i < 8; i++) { p.X.v[i] = threadIdx.x * 977 + i; p.Y.v[i] = blockIdx.x * 131 + i * 7 + 1; p.Z.v[i] = 3 * i + 1; p.T.v[i] = 5 * i + 2; }
+    q = p;
+    q.X.v[0] ^= 0x55;
+    for (int it = 0; it < iters; it++) {
+        if (OP == 0) p = ge_add(p, q);
+        else if (OP == 1) p = ge_dbl(p);
+        else p = ge_dbl_not(p);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = p;
+}
+
 int main() {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
@@ -92,6 +107,24 @@ int main() {
         }
         ops = (double)sms * 16 * 128 * it2;
         printf("{\"op\": \"ge_madd\", \"ms\": %.3f, \"Gops\": %.2f, \"sm_cycles_per_thread_op_at_max_clock\": %.3f}\n", best, ops / best / 1e6, (best * 1e-3) * clk * 1e3 * sms / ops);
+    }
+    {
+        const char* ops[3] = {"ge_add", "ge_dbl", "ge_dbl_not"};
+        const int geo[4][2] = {{1, 32}, {1, 128}, {148, 128}, {148, 512}};
+        const int it3 = 2000;
+        for (int op = 0; op < 3; op++)
+            for (int g = 0; g < 4; g++) {
+                float best = 1e9;
+                for (int rep = 0; rep < 4; rep++) {
+                    cudaEventRecord(e0);
+                    if (op == 0) k_chain<0><<<geo[g][0], geo[g][1]>>>((ge_ext*)out, it3);
+                    if (op == 1) k_chain<1><<<geo[g][0], geo[g][1]>>>((ge_ext*)out, it3);
+                    if (op == 2) k_chain<2><<<geo[g][0], geo[g][1]>>>((ge_ext*)out, it3);
+                    cudaEventRecord(e1); cudaEventSynchronize(e1);
+                    float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
+                }
+                printf("{\"op\": \"%s chain\", \"blocks\": %d, \"threads\": %d, \"ns_per_dependent_op\": %.1f}\n", ops[op], geo[g][0], geo[g][1], best * 1e6 / it3);
+            }
     }
     cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(e)); return 1; }
     return 0;
