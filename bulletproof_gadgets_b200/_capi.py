@@ -52,6 +52,10 @@ class TextJob(ctypes.Structure):
 JOB_VERIFY = 1
 
 
+class BitRun(ctypes.Structure):
+    _fields_ = [("first", c_uint64), ("nbits", c_uint32), ("reserved", c_uint32), ("value", c_uint8 * 32)]
+
+
 class FlatStatementC(ctypes.Structure):
     _fields_ = [("n", c_uint64), ("m", c_uint64), ("q", c_uint64), ("nnz", c_uint64), ("v32m", POINTER(c_uint8)),
                 ("vbl32m", POINTER(c_uint8)), ("V32m", POINTER(c_uint8)), ("aL32n", POINTER(c_uint8)),
@@ -101,6 +105,8 @@ PROTOTYPES = {
     "bpg_prover_multiply": (c_int, [c_void_p, _u32p, c_char_p, c_size_t, _u32p, c_char_p, c_size_t, _u32p]),
     "bpg_prover_constrain": (c_int, [c_void_p, _u32p, c_char_p, c_size_t]),
     "bpg_prover_load_cs": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64]),
+    "bpg_prover_load_cs_bits": (c_int, [c_void_p, c_uint64, POINTER(BitRun), c_uint64, c_void_p, c_void_p, c_void_p, c_uint64,
+                                        c_void_p, c_void_p, c_void_p, c_uint64]),
     "bpg_prover_num_constraints": (c_uint64, [c_void_p]),
     "bpg_prover_num_multipliers": (c_uint64, [c_void_p]),
     "bpg_prover_prove": (c_int, [c_void_p, c_char_p, c_char_p, c_size_t, POINTER(c_size_t)]),

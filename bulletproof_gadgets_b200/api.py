@@ -342,6 +342,18 @@ class Prover(_CS):
         check(lib().bpg_prover_load_cs(self._h, _buf(aL), _buf(aR), _nbytes(aL) // 32, row_start.ctypes.data,
                                        term_var.ctypes.data, _buf(term_coef), q))
 
+    def load_cs_bits(self, n, runs, aLh, aRh, host_index, row_start, term_var, term_coef, q):
+        """bpg_prover_load_cs_bits: `runs` = [(first, nbits, value int)], the other multipliers as compact arrays (bytes, 32 B
+        each) with their multiplier indices.  Witness bits are generated on the device."""
+        import numpy as np
+        arr = (_capi.BitRun * max(len(runs), 1))()
+        for k, (first, nbits, value) in enumerate(runs):
+            arr[k].first, arr[k].nbits = first, nbits
+            arr[k].value[:] = list(int(value).to_bytes(32, "little"))
+        idx = np.asarray(host_index, dtype=np.uint32)
+        check(lib().bpg_prover_load_cs_bits(self._h, n, arr, len(runs), _buf(aLh), _buf(aRh), idx.ctypes.data if idx.size else None,
+                                            idx.size, row_start.ctypes.data, term_var.ctypes.data, _buf(term_coef), q))
+
     def num_constraints(self):
         return lib().bpg_prover_num_constraints(self._h)
 

@@ -7,6 +7,8 @@
 // stored column-wise so that one thread (or one CTA for long columns) owns each output of the flatten
 // kernel.  Sums mod l are exact, so the order of terms inside a column is irrelevant: the scatter uses
 // atomics and needs no sort.
+#include <vector>
+
 #include "circuit.hpp"
 #include "kernels.hpp"
 
@@ -85,6 +87,36 @@ __global__ void __launch_bounds__(256) k_witness(sc* __restrict__ aL, sc* __rest
     aL[i] = l;
     aR[i] = r;
     aO[i] = sc_mul(l, r);
+}
+
+// Witness generation on the device for the reference's range proof (/root/reference/src/utils.rs:13-31):
+// multipliers [first, first + nbits) of a run are  a_L = 1 - bit_i(value), a_R = bit_i(value), a_O = 0.  One CTA per run.
+__global__ void __launch_bounds__(64) k_witness_bits(const bpg_bit_run* __restrict__ runs, sc* __restrict__ aL, sc* __restrict__ aR,
+                                                    sc* __restrict__ aO) {
+    const bpg_bit_run r = runs[blockIdx.x];
+    const uint32_t* v = reinterpret_cast<const uint32_t*>(r.value);
+    for (uint32_t i = threadIdx.x; i < r.nbits; i += blockDim.x) {
+        const uint32_t bit = (v[i >> 5] >> (i & 31)) & 1u;
+        sc l = sc_zero(), rr = sc_zero();
+        l.v[0] = 1u - bit;
+        rr.v[0] = bit;
+        aL[r.first + i] = l;
+        aR[r.first + i] = rr;
+        aO[r.first + i] = sc_zero();
+    }
+}
+// multipliers the host did assign: compact arrays scattered to their indices, reduced, a_O = a_L * a_R
+__global__ void __launch_bounds__(256) k_witness_scatter(const sc* __restrict__ hL, const sc* __restrict__ hR,
+                                                        const uint32_t* __restrict__ index, uint32_t h, sc* __restrict__ aL,
+                                                        sc* __restrict__ aR, sc* __restrict__ aO, uint32_t* __restrict__ err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    if ((hL[i].v[7] | hR[i].v[7]) >> 31) atomicOr(err, 2u);
+    const sc l = sc_reduce(hL[i]), r = sc_reduce(hR[i]);
+    const uint32_t k = index[i];
+    aL[k] = l;
+    aR[k] = r;
+    aO[k] = sc_mul(l, r);
 }
 
 static int dalloc(bpg_ctx* ctx, bool pooled, void** p, size_t bytes) {
@@ -228,6 +260,81 @@ int circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR3
             bpg_set_error("multiplier assignment with bit 255 set (not a valid Scalar)");
             return BPG_E_ARG;
         }
+    }
+    c->has_witness = true;
+    return BPG_OK;
+}
+
+int circuit_set_witness_bits(bpg_circuit* c, const bpg_bit_run* runs, uint64_t n_runs, const uint8_t* aL32h,
+                             const uint8_t* aR32h, const uint32_t* host_index, uint64_t h) {
+    bpg_ctx* ctx = c->ctx;
+    const size_t n = c->n;
+    // every multiplier must be assigned exactly once: runs and host indices partition [0, n)
+    {
+        std::vector<uint8_t> seen(n ? n : 1, 0);
+        uint64_t covered = 0;
+        for (uint64_t r = 0; r < n_runs; r++) {
+            if (runs[r].nbits > 256 || runs[r].first > n || runs[r].nbits > n - runs[r].first) {
+                bpg_set_error("bit run %llu out of range", (unsigned long long)r);
+                return BPG_E_ARG;
+            }
+            for (uint32_t i = 0; i < runs[r].nbits; i++) covered += !seen[runs[r].first + i]++;
+        }
+        for (uint64_t i = 0; i < h; i++) {
+            if (host_index[i] >= n) {
+                bpg_set_error("host multiplier index out of range");
+                return BPG_E_ARG;
+            }
+            covered += !seen[host_index[i]]++;
+        }
+        uint64_t total = h;
+        for (uint64_t r = 0; r < n_runs; r++) total += runs[r].nbits;
+        if (covered != n || total != n) {
+            bpg_set_error("bit runs and host multipliers do not partition the %zu multipliers", n);
+            return BPG_E_ARG;
+        }
+    }
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (!c->d_aL) {
+        if ((rc = dalloc(ctx, c->pooled, (void**)&c->d_aL, 32 * (n + 1))) ||
+            (rc = dalloc(ctx, c->pooled, (void**)&c->d_aR, 32 * (n + 1))) ||
+            (rc = dalloc(ctx, c->pooled, (void**)&c->d_aO, 32 * (n + 1))))
+            return rc;
+    }
+    bpg_bit_run* d_runs = nullptr;
+    sc *d_hL = nullptr, *d_hR = nullptr;
+    uint32_t *d_idx = nullptr, *d_err = nullptr;
+    if ((rc = dalloc(ctx, true, (void**)&d_err, 4))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, st));
+    if (n_runs) {
+        if ((rc = dalloc(ctx, true, (void**)&d_runs, sizeof(bpg_bit_run) * n_runs))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_runs, runs, sizeof(bpg_bit_run) * n_runs, cudaMemcpyHostToDevice, st));
+        k_witness_bits<<<(uint32_t)n_runs, 64, 0, st>>>(d_runs, c->d_aL, c->d_aR, c->d_aO);
+        ctx->launches++;
+    }
+    if (h) {
+        if ((rc = dalloc(ctx, true, (void**)&d_hL, 32 * h)) || (rc = dalloc(ctx, true, (void**)&d_hR, 32 * h)) ||
+            (rc = dalloc(ctx, true, (void**)&d_idx, 4 * h)))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_hL, aL32h, 32 * h, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_hR, aR32h, 32 * h, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_idx, host_index, 4 * h, cudaMemcpyHostToDevice, st));
+        k_witness_scatter<<<(uint32_t)((h + 255) / 256), 256, 0, st>>>(d_hL, d_hR, d_idx, (uint32_t)h, c->d_aL, c->d_aR, c->d_aO, d_err);
+        ctx->launches++;
+    }
+    const uint32_t* errp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_err, 4));
+    if (!errp) return BPG_E_CUDA;
+    CUDA_TRY(ctx_sync(ctx));  // the host arrays may be released by the caller after this returns
+    const uint32_t err = *errp;
+    dfree(ctx, true, d_err);
+    dfree(ctx, true, d_runs);
+    dfree(ctx, true, d_hL);
+    dfree(ctx, true, d_hR);
+    dfree(ctx, true, d_idx);
+    if (err) {
+        bpg_set_error("multiplier assignment with bit 255 set (not a valid Scalar)");
+        return BPG_E_ARG;
     }
     c->has_witness = true;
     return BPG_OK;

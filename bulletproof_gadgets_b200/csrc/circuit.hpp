@@ -22,6 +22,10 @@ int circuit_build(bpg_ctx* ctx, uint64_t n, uint64_t m, uint64_t q, const uint32
                   const uint8_t* term_coef32, bool pooled, bpg_circuit** out);
 // multiplier assignments: raw 32-byte scalars (< 2^255), reduced on the device; a_O = a_L * a_R
 int circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR32n);
+// f3: multipliers of range-proof bit runs are generated on the device; the `h` others come as compact host arrays with
+// their multiplier indices.  Runs and indices must partition [0, n).
+int circuit_set_witness_bits(bpg_circuit* c, const bpg_bit_run* runs, uint64_t n_runs, const uint8_t* aL32h,
+                             const uint8_t* aR32h, const uint32_t* host_index, uint64_t h);
 void circuit_free(bpg_circuit* c);
 
 // scan.cu: out[i] = sum_{j<i} in[i] for i in [0, n]  (n+1 outputs; in and out may alias); scratch >= n/2048 + 2 words

@@ -763,6 +763,11 @@ struct Flat {
     // go to the caller as they are.  (S is eight little-endian 32-bit limbs = the ABI's 32-byte scalar.)
     Owned<S> aL, aR, aO;  // aO: prover-side cache of a_L * a_R for LC evaluation
     uint32_t n = 0;       // multipliers assigned so far
+    // f3: runs of consecutive multipliers whose assignments are (1 - bit, bit) -- the reference's range proof
+    // (utils.rs:13-31) -- are handed to the library as VALUES (bpg_prover_load_cs_bits builds them in HBM); the other
+    // multipliers are listed in host_index
+    std::vector<bpg_bit_run> bit_runs;
+    std::vector<uint32_t> host_index;
     Owned<uint32_t> row_start, term_var;
     Owned<S> term_coef;
     size_t rows = 0, nnz = 0;
@@ -804,6 +809,28 @@ struct Flat {
         aL.p[n] = l;
         aR.p[n] = r;
         aO.p[n] = s_mul(l, r);
+        host_index.push_back(n);
+    }
+    static int as_bit(const S& x) {  // 0, 1, or -1 when x is neither
+        uint32_t hi = 0;
+        for (int k = 1; k < 8; k++) hi |= x.v[k];
+        return hi == 0 && x.v[0] <= 1 ? (int)x.v[0] : -1;
+    }
+    void assign_alloc(const S& l, const S& r) {  // allocate_multiplier(Some((l, r)))
+        const int bl = as_bit(l), br = as_bit(r);
+        if (bl < 0 || br < 0 || bl + br != 1) return assign(l, r);
+        aL.p[n] = l;
+        aR.p[n] = r;
+        aO.p[n] = s_zero();
+        if (bit_runs.empty() || bit_runs.back().first + bit_runs.back().nbits != n || bit_runs.back().nbits == 256) {
+            bpg_bit_run run;
+            memset(&run, 0, sizeof run);
+            run.first = n;
+            bit_runs.push_back(run);
+        }
+        bpg_bit_run& run = bit_runs.back();
+        if (br) run.value[run.nbits >> 3] |= (uint8_t)(1u << (run.nbits & 7));
+        run.nbits++;
     }
     void replay(const Buffer& buf, bool proving) {  // assign_buffer (prove.rs:84-99 / verify.rs:75-90)
         size_t n_total = 0, q_total = 0, nnz_total = 0;
@@ -835,7 +862,7 @@ struct Flat {
                 constrain(oa, true, mkvar(K_LEFT, i));
                 constrain(ob, true, mkvar(K_RIGHT, i));
             } else if (o.kind == Op::ALLOC) {
-                if (proving) assign(buf.vals[o.val], buf.vals[o.val + 1]);
+                if (proving) assign_alloc(buf.vals[o.val], buf.vals[o.val + 1]);
                 n++;
             } else if (o.kind == Op::CON) {
                 constrain(buf.a_of(o));
@@ -1424,7 +1451,21 @@ int bpg_prove(bpg_ctx* ctx, const char* name, const char* instance, const char* 
                           *coef = reinterpret_cast<const uint8_t*>(st.term_coef.p);
             // every commitment precedes every challenge, so one batched launch keeps the transcript order
             rc = bpg_prover_commit_batch(p, v, vb, st.v.size(), V.data(), nullptr);
-            if (!rc) rc = bpg_prover_load_cs(p, aL, aR, st.n, st.row_start.p, st.term_var.p, coef, st.rows);
+            static const bool f3 = [] {
+                const char* e = getenv("BPG_F3");  // BPG_F3=0: upload every multiplier from the host (A/B measurements)
+                return !e || atoi(e) != 0;
+            }();
+            if (!rc && f3 && !st.bit_runs.empty()) {
+                // witness generation on the device: bit runs go over as values, only the other multipliers as scalars
+                const size_t h = st.host_index.size();
+                std::vector<S> hL(h ? h : 1), hR(h ? h : 1);
+                for (size_t i = 0; i < h; i++) hL[i] = st.aL.p[st.host_index[i]], hR[i] = st.aR.p[st.host_index[i]];
+                rc = bpg_prover_load_cs_bits(p, st.n, st.bit_runs.data(), st.bit_runs.size(), reinterpret_cast<const uint8_t*>(hL.data()),
+                                             reinterpret_cast<const uint8_t*>(hR.data()), st.host_index.data(), h, st.row_start.p,
+                                             st.term_var.p, coef, st.rows);
+            } else if (!rc) {
+                rc = bpg_prover_load_cs(p, aL, aR, st.n, st.row_start.p, st.term_var.p, coef, st.rows);
+            }
             if (!rc) rc = bpg_prover_prove(p, rng_seed32, proof.data(), proof.size(), &proof_len);
             free(v), free(vb);
         }

@@ -103,22 +103,35 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
             if (tickets) {
                 const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
                 uint32_t tk[16];
+                // Structured scalars (a_L in {0,1}, a_R in {0,-1}: every entry of a window falls into ONE bucket) would
+                // serialise on a single L2 address.  Windows in which neighbouring lanes collide are found first (one vote
+                // per window); the common case -- none -- keeps the 16 independent atomics of a thread in flight together.
+                uint32_t dup = 0;
 #pragma unroll
                 for (int w = 0; w < 16; w++) {
-                    const uint32_t key = gbv[w];
-                    // Structured scalars (a_L in {0,1}, a_R in {0,-1}: every entry of a window falls into ONE bucket)
-                    // would serialise on a single L2 address.  When neighbouring lanes collide, the lanes of a warp that
-                    // share a bucket send one atomic for all of them and split the returned range by lane order.
-                    const uint32_t nxt = __shfl_down_sync(0xffffffffu, key, 1);
-                    if (__any_sync(0xffffffffu, key != DG_NONE && key == nxt && lane < 31)) {
-                        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-                        const int leader = __ffs(peers) - 1;
-                        uint32_t b0 = 0;
-                        if (key != DG_NONE && (int)lane == leader) b0 = atomicAdd(&hist[key], (uint32_t)__popc(peers));
-                        b0 = __shfl_sync(0xffffffffu, b0, leader);
-                        tk[w] = b0 + __popc(peers & lt);
-                    } else if (key != DG_NONE) {
-                        tk[w] = atomicAdd(&hist[key], 1u);
+                    const uint32_t nxt = __shfl_down_sync(0xffffffffu, gbv[w], 1);
+                    if (__any_sync(0xffffffffu, gbv[w] != DG_NONE && gbv[w] == nxt && lane < 31)) dup |= 1u << w;
+                }
+                if (dup == 0) {
+#pragma unroll
+                    for (int w = 0; w < 16; w++)
+                        if (gbv[w] != DG_NONE) tk[w] = atomicAdd(&hist[gbv[w]], 1u);
+                } else {
+                    // the lanes of a warp that share a bucket send one atomic for all of them and split the returned
+                    // range by lane order
+#pragma unroll
+                    for (int w = 0; w < 16; w++) {
+                        const uint32_t key = gbv[w];
+                        if ((dup >> w) & 1u) {
+                            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                            const int leader = __ffs(peers) - 1;
+                            uint32_t b0 = 0;
+                            if (key != DG_NONE && (int)lane == leader) b0 = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+                            b0 = __shfl_sync(0xffffffffu, b0, leader);
+                            tk[w] = b0 + __popc(peers & lt);
+                        } else if (key != DG_NONE) {
+                            tk[w] = atomicAdd(&hist[key], 1u);
+                        }
                     }
                 }
                 if (in) {
@@ -445,48 +458,130 @@ __device__ __forceinline__ ge_ext load_ext_cg(const ge_ext* src) {  // L2 loads:
     return p;
 }
 
-// Butterfly levels over `nseg` segment states of L + 1 values each (state s at src + s * REDUCE_MAXV), all threads of the
-// CTA: joins neighbours until one state of L + log2(nseg) + 1 values is left; returns where it lives (ping-pong a / b).
-__device__ const ge_ext* butterfly_levels(const ge_ext* src, ge_ext* a, ge_ext* b, uint32_t nseg, uint32_t* L_io) {
-    uint32_t L = *L_io;
-    const ge_ext* cur = src;
-    ge_ext* nxt = a;
+// ---- four-warp point arithmetic on shared memory -------------------------------------------------------------------
+// A lone warp runs a point addition in ~2.3 us (tools/imad_peak.cu: it is bound by its own scheduler's share of the
+// multiplier pipe, however few lanes are active), and the serial part of the reduction is ~35 such operations.  Here the
+// four warps of the CTA -- one per scheduler -- each compute ONE of the four independent field products of a stage, for up
+// to 32 point operations at a time (lane = operation): an addition takes three product times instead of nine.
+__device__ __forceinline__ fe lds_fe(const fe* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 a = q[0], b = q[1];
+    fe r;
+    r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fe(fe* p, const fe& f) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(f.v[0], f.v[1], f.v[2], f.v[3]);
+    q[1] = make_uint4(f.v[4], f.v[5], f.v[6], f.v[7]);
+}
+struct alignas(16) CoopScratch {
+    fe s[4][32];
+};
+// (__noinline__ throughout: every inlined copy of a point operation is ~25 KB of straight-line code that runs a handful
+// of times per launch -- the first version of this kernel spent more time on instruction-cache misses than on arithmetic)
+// *a += *b (shared memory, a != b) for the lanes with `live`; all BR_THREADS threads call it together
+__device__ __noinline__ void coop_add(ge_ext* a, const ge_ext* b, bool live, CoopScratch* scr) {
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (live) {
+        fe r;
+        if (w == 0) r = fe_mul(fe_sub(lds_fe(&a->Y), lds_fe(&a->X)), fe_sub(lds_fe(&b->Y), lds_fe(&b->X)));
+        else if (w == 1) r = fe_mul(fe_add(lds_fe(&a->Y), lds_fe(&a->X)), fe_add(lds_fe(&b->Y), lds_fe(&b->X)));
+        else if (w == 2) r = fe_mul(fe_mul(lds_fe(&a->T), fe_2D()), lds_fe(&b->T));
+        else {
+            r = fe_mul(lds_fe(&a->Z), lds_fe(&b->Z));
+            r = fe_add(r, r);
+        }
+        sts_fe(&scr->s[w][lane], r);
+    }
+    __syncthreads();
+    if (live) {
+        const fe A = lds_fe(&scr->s[0][lane]), B = lds_fe(&scr->s[1][lane]), C = lds_fe(&scr->s[2][lane]), D = lds_fe(&scr->s[3][lane]);
+        if (w == 0) sts_fe(&a->X, fe_mul(fe_sub(B, A), fe_sub(D, C)));       // E F
+        else if (w == 1) sts_fe(&a->Y, fe_mul(fe_add(D, C), fe_add(B, A)));  // G H
+        else if (w == 2) sts_fe(&a->Z, fe_mul(fe_sub(D, C), fe_add(D, C)));  // F G
+        else sts_fe(&a->T, fe_mul(fe_sub(B, A), fe_add(B, A)));              // E H
+    }
+    __syncthreads();
+}
+// *p = 2 * *p
+__device__ __noinline__ void coop_dbl(ge_ext* p, bool live, CoopScratch* scr) {
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (live) {
+        fe r;
+        if (w == 0) r = fe_sqr(lds_fe(&p->X));
+        else if (w == 1) r = fe_sqr(lds_fe(&p->Y));
+        else if (w == 2) {
+            r = fe_sqr(lds_fe(&p->Z));
+            r = fe_add(r, r);
+        } else r = fe_sqr(fe_add(lds_fe(&p->X), lds_fe(&p->Y)));
+        sts_fe(&scr->s[w][lane], r);
+    }
+    __syncthreads();
+    if (live) {
+        const fe A = lds_fe(&scr->s[0][lane]), B = lds_fe(&scr->s[1][lane]), C = lds_fe(&scr->s[2][lane]), S = lds_fe(&scr->s[3][lane]);
+        const fe G = fe_sub(B, A), H = fe_neg(fe_add(A, B));  // a = -1:  D = -A,  G = D + B,  H = D - B
+        if (w == 0) sts_fe(&p->X, fe_mul(fe_sub(fe_sub(S, A), B), fe_sub(G, C)));  // E F
+        else if (w == 1) sts_fe(&p->Y, fe_mul(G, H));
+        else if (w == 2) sts_fe(&p->Z, fe_mul(fe_sub(G, C), G));                     // F G
+        else sts_fe(&p->T, fe_mul(fe_sub(fe_sub(S, A), B), H));                       // E H
+    }
+    __syncthreads();
+}
+
+// one thread, one addition: *dst = *a + *b (any address space)
+__device__ __noinline__ void pt_add(ge_ext* dst, const ge_ext* a, const ge_ext* b) {
+    const ge_ext r = ge_add(load_ext(a), load_ext(b));
+    store_ext(dst, r);
+}
+
+// Butterfly levels over `nseg` segment STATES of L + 1 values each, in shared memory (state s at pts + s * stride *
+// REDUCE_MAXV, stride doubling with every level): joins neighbours in place until state 0 holds L + log2(nseg) + 1 values.
+__device__ __noinline__ void state_levels(ge_ext* pts, uint32_t nseg, uint32_t* L_io, CoopScratch* scr) {
+    uint32_t L = *L_io, stride = 1;
+    const uint32_t lane = threadIdx.x & 31;
     while (nseg > 1) {
-        const uint32_t nv = L + 2, items = (nseg >> 1) * nv;
+        const uint32_t nv = L + 1, items = (nseg >> 1) * nv;
+        if (items > 64) {  // plenty of parallel work: one addition per thread
 #pragma unroll 1
-        for (uint32_t i = threadIdx.x; i < items; i += blockDim.x) {
-            const uint32_t q = i / nv, v = i - q * nv;
-            const ge_ext* A = cur + (size_t)(2 * q) * REDUCE_MAXV;
-            const ge_ext* B = A + REDUCE_MAXV;
-            ge_ext r;
-            if (v == L + 1) r = load_ext_cg(B);
-            else r = ge_add(load_ext_cg(A + v), load_ext_cg(B + v));
-            store_ext(nxt + (size_t)q * REDUCE_MAXV + v, r);
+            for (uint32_t i = threadIdx.x; i < items; i += blockDim.x) {
+                const uint32_t q = i / nv, v = i - q * nv;
+                ge_ext* A = pts + (size_t)(2 * q) * stride * REDUCE_MAXV + v;
+                pt_add(A, A, A + (size_t)stride * REDUCE_MAXV);
+            }
+            __syncthreads();
+        } else {
+#pragma unroll 1
+            for (uint32_t base = 0; base < items; base += 32) {
+                const uint32_t i = base + lane, q = i / nv, v = i - q * nv;
+                ge_ext* A = pts + (size_t)(2 * q) * stride * REDUCE_MAXV + v;
+                coop_add(A, A + (size_t)stride * REDUCE_MAXV, i < items, scr);
+            }
+        }
+        for (uint32_t q = threadIdx.x; q < (nseg >> 1); q += blockDim.x) {  // M_L of the joined segment = R of its upper half
+            ge_ext* A = pts + (size_t)(2 * q) * stride * REDUCE_MAXV;
+            store_ext(A + L + 1, load_ext(A + (size_t)stride * REDUCE_MAXV));
         }
         __syncthreads();
-        cur = nxt;
-        nxt = nxt == a ? b : a;
         nseg >>= 1;
+        stride <<= 1;
         L++;
     }
     *L_io = L;
-    return cur;
 }
 
 // One thread per bucket (BR_THREADS consecutive buckets of one set per CTA; a set with fewer buckets gets one CTA).
-// Phase 1: S_b = sum of the bucket's partial slots; lanes walk the first BR_CAP slots alone, the rest of a heavy bucket
-// is strided over the warp.  Phase 2: butterfly over the bucket-index bits.  After level k every aligned segment of
-// 2^(k+1) threads holds, at its positions 0 .. k+1:  R = sum of the segment,  M_j = sum of its buckets with index bit
-// j set (j <= k).  Joining the lower half A and the upper half B: R = R_A + R_B, M_j = M_j,A + M_j,B (j < k), M_k = R_B
-// -- one addition per lane.  Phase 3: the CTA that arrives last in its group of `gsize` CTAs joins the group's states
-// (log2 gsize more levels), and the last group of a set joins the group states and finishes
-//     sum_b (b + 1) S_b = R + sum_j 2^j M_j          (lane i doubles M_{i-1} i-1 times, then a warp tree).
-// No scalar multiplication anywhere; the serial part is lv + log2(nb / bpb) additions and c - 2 doublings.
+// Phase 1: S_b = sum of the bucket's partial slots; lanes walk their own slots, the excess of an outlier bucket is
+// strided over the warp.  Phase 2: butterfly over the bucket-index bits, in shared memory with the four-warp arithmetic.
+// After level k every aligned segment of 2^(k+1) positions holds, at its positions 0 .. k+1:  R = sum of the segment,
+// M_j = sum of its buckets with index bit j set (j <= k).  Joining the lower half A and the upper half B:
+// R = R_A + R_B, M_j = M_j,A + M_j,B (j < k), M_k = R_B.  Phase 3: the CTA that arrives last in its group of `gsize`
+// CTAs joins the group's states (log2 gsize more levels), and the last group of a set joins the group states and finishes
+//     sum_b (b + 1) S_b = R + sum_j 2^j M_j          (value i is doubled i - 1 times, then a tree over the c values).
+// No scalar multiplication anywhere; the serial part is log2(nb) additions and c - 2 doublings at four-warp latency.
 struct ReduceScratch {
-    ge_ext* cta;     // [br_blocks][REDUCE_MAXV] CTA states; also ping-pong a of the group stage
-    ge_ext* tmp;     // [br_blocks][REDUCE_MAXV] ping-pong b of the group stage
+    ge_ext* cta;     // [br_blocks][REDUCE_MAXV] CTA states
     ge_ext* grp;     // [n_groups][REDUCE_MAXV] group states
-    ge_ext* fin;     // [2][n_groups][REDUCE_MAXV] ping-pong of the set stage
     uint32_t* cnt;   // [n_groups + nsets] arrival counters, zero between launches
     unsigned long long* dbg;  // diagnostic mode: [gridDim.x][8] %globaltimer stamps of the phases of every CTA (or NULL)
 };
@@ -500,14 +595,16 @@ __device__ __forceinline__ void phase_stamp(const ReduceScratch& sc, int phase) 
 __global__ void __launch_bounds__(BR_THREADS)
     k_bucket_reduce(const ge_ext* __restrict__ partials, const uint32_t* __restrict__ bucket_off,
                     const MsmMeta* __restrict__ meta, uint32_t bpb /* buckets per CTA, power of two <= BR_THREADS */,
-                    uint32_t lv /* log2(bpb) */, uint32_t nblk /* CTAs per set */, uint32_t gsize /* CTAs per group */,
+                    uint32_t lv /* log2(bpb) */, uint32_t nblk /* CTAs per set */, uint32_t gsize /* CTAs per group <= 16 */,
                     ReduceScratch sc, ge_ext* __restrict__ result) {
-    __shared__ ge_ext sh[BR_THREADS];
+    __shared__ ge_ext pts[16 * REDUCE_MAXV];  // bucket sums of the CTA, later up to 16 segment states
+    __shared__ CoopScratch scr;
     __shared__ uint32_t sh_last;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t E = meta->E, CL = meta->CL;
     phase_stamp(sc, 0);
-    ge_ext val = ge_identity();
+    ge_ext* mine = pts + tid;                 // this thread's bucket sum
+    ge_ext* part = pts + BR_THREADS + tid;    // scratch of the cooperative path
     SlotList L;
     L.gb = L.n = L.s0 = L.n0 = L.s1 = L.n1 = L.s2 = L.n2 = L.s3 = L.n3 = L.s4 = 0;
     if (tid < bpb) {
@@ -520,11 +617,12 @@ __global__ void __launch_bounds__(BR_THREADS)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     const uint32_t cap = max((uint32_t)BR_CAP, 2 * (tot >> 5) + 4);
-    if (L.n) val = load_ext(partials + L.slot(0));
-    {
+    {   // (the one point addition of this kernel that stays inline: every lane is busy here, the loop is hot)
+        ge_ext val = L.n ? load_ext(partials + L.slot(0)) : ge_identity();
         const uint32_t own = min(L.n, cap);
 #pragma unroll 1
         for (uint32_t i = 1; i < own; i++) val = ge_add(val, load_ext(partials + L.slot(i)));
+        store_ext(mine, val);
     }
     uint32_t heavy = __ballot_sync(0xffffffffu, L.n > cap);
     while (heavy) {
@@ -542,42 +640,41 @@ __global__ void __launch_bounds__(BR_THREADS)
         H.s3 = __shfl_sync(0xffffffffu, L.s3, owner);
         H.n3 = __shfl_sync(0xffffffffu, L.n3, owner);
         H.s4 = __shfl_sync(0xffffffffu, L.s4, owner);
-        ge_ext part = ge_identity();
+        store_ext(part, ge_identity());
 #pragma unroll 1
-        for (uint32_t i = cap + lane; i < H.n; i += 32) part = ge_add(part, load_ext(partials + H.slot(i)));
+        for (uint32_t i = cap + lane; i < H.n; i += 32) pt_add(part, part, partials + H.slot(i));
+        __syncwarp();
 #pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) {
-            const ge_ext other = shfl_ext(part, lane ^ o);
-            part = ge_add(part, other);
+        for (uint32_t o = 16; o > 0; o >>= 1) {
+            if (lane < o) pt_add(part, part, part + o);
+            __syncwarp();
         }
-        if ((int)lane == owner) val = ge_add(val, part);
+        if ((int)lane == owner) pt_add(mine, mine, part - lane);
+        __syncwarp();
     }
     phase_stamp(sc, 1);
-    // butterfly inside the CTA
+    // butterfly inside the CTA: position = thread
+    __syncthreads();
 #pragma unroll 1
     for (uint32_t k = 0; k < lv; k++) {
-        const uint32_t h = 1u << k, p = tid & (2 * h - 1);
-        ge_ext other = val;
-        if (k < 5) {
-            const int src = p <= k ? (int)(lane + h) : (p == k + 1 ? (int)(lane - p + h) : (int)lane);
-            other = shfl_ext(val, src);
-        } else {
-            store_ext(sh + tid, val);
-            __syncthreads();
-            if (p <= k) other = load_ext(sh + tid + h);
-            else if (p == k + 1) other = load_ext(sh + tid - p + h);
+        const uint32_t h = 1u << k, nv = k + 1, items = (bpb >> (k + 1)) * nv;
+#pragma unroll 1
+        for (uint32_t base = 0; base < items; base += 32) {
+            const uint32_t i = base + lane, seg = i / nv, p = i - seg * nv;
+            ge_ext* A = pts + (size_t)seg * 2 * h + p;
+            coop_add(A, A + h, i < items, &scr);
+        }
+        if (k >= 2) {  // M_k = R of the upper half; for k < 2 position k + 1 IS the upper half's position 0
+            if (tid < (bpb >> (k + 1))) store_ext(pts + (size_t)tid * 2 * h + k + 1, load_ext(pts + (size_t)tid * 2 * h + h));
             __syncthreads();
         }
-        if (p <= k) val = ge_add(val, other);
-        else if (p == k + 1 && k >= 2) val = other;
     }
-    if (tid <= lv) store_ext(sc.cta + (size_t)blockIdx.x * REDUCE_MAXV + tid, val);
+    if (tid <= lv) store_ext(sc.cta + (size_t)blockIdx.x * REDUCE_MAXV + tid, load_ext(pts + tid));
     phase_stamp(sc, 2);
     // group stage: the last CTA of the group to arrive joins the group's states
     const uint32_t set = blockIdx.x / nblk, ngrp = nblk / gsize;  // groups per set
     const uint32_t group = blockIdx.x / gsize;                    // global group index
     uint32_t Lc = lv;
-    const ge_ext* state = sc.cta + (size_t)blockIdx.x * REDUCE_MAXV;
     if (gsize > 1) {
         __threadfence();
         __syncthreads();
@@ -586,13 +683,17 @@ __global__ void __launch_bounds__(BR_THREADS)
         if (!sh_last) return;
         if (tid == 0) sc.cnt[group] = 0;
         __threadfence();
-        const size_t g0 = (size_t)group * gsize * REDUCE_MAXV;
-        state = butterfly_levels(sc.cta + g0, sc.tmp + g0, sc.cta + g0, gsize, &Lc);
+        for (uint32_t i = tid; i < gsize * (lv + 1); i += BR_THREADS) {
+            const uint32_t s_ = i / (lv + 1), v = i - s_ * (lv + 1);
+            store_ext(pts + (size_t)s_ * REDUCE_MAXV + v, load_ext_cg(sc.cta + ((size_t)group * gsize + s_) * REDUCE_MAXV + v));
+        }
+        __syncthreads();
+        state_levels(pts, gsize, &Lc, &scr);
         phase_stamp(sc, 3);
     }
     // set stage: the last group of the set joins the group states and finishes
     if (ngrp > 1) {
-        if (tid <= Lc) store_ext(sc.grp + (size_t)group * REDUCE_MAXV + tid, load_ext_cg(state + tid));
+        if (tid <= Lc) store_ext(sc.grp + (size_t)group * REDUCE_MAXV + tid, load_ext(pts + tid));
         __threadfence();
         __syncthreads();
         const uint32_t nctr = gridDim.x / gsize;  // group counters come first
@@ -601,27 +702,27 @@ __global__ void __launch_bounds__(BR_THREADS)
         if (!sh_last) return;
         if (tid == 0) sc.cnt[nctr + set] = 0;
         __threadfence();
-        const size_t s0 = (size_t)set * ngrp * REDUCE_MAXV, half = (size_t)nctr * REDUCE_MAXV;
-        state = butterfly_levels(sc.grp + s0, sc.fin + s0, sc.fin + half + s0, ngrp, &Lc);
+        for (uint32_t i = tid; i < ngrp * (Lc + 1); i += BR_THREADS) {
+            const uint32_t s_ = i / (Lc + 1), v = i - s_ * (Lc + 1);
+            store_ext(pts + (size_t)s_ * REDUCE_MAXV + v, load_ext_cg(sc.grp + ((size_t)set * ngrp + s_) * REDUCE_MAXV + v));
+        }
+        __syncthreads();
+        state_levels(pts, ngrp, &Lc, &scr);
         phase_stamp(sc, 4);
-    } else {
-        __syncthreads();  // `state` was written by this CTA's threads
     }
-    if (tid >= 32) return;
-    ge_ext v = tid <= Lc ? load_ext_cg(state + tid) : ge_identity();
-    if (tid >= 2 && tid <= Lc) {
+    // pts[0 .. Lc] = R, M_0 .. M_{Lc-1}:  value i >= 2 is doubled i - 1 times, then everything is added up
+    for (uint32_t i = tid; i < 32; i += BR_THREADS)
+        if (i > Lc) store_ext(pts + i, ge_identity());
+    __syncthreads();
 #pragma unroll 1
-        for (uint32_t k = 2; k < tid; k++) v = ge_dbl_not(v);
-        v = ge_dbl(v);
-    }
-    __syncwarp();
+    for (uint32_t rep = 1; rep < Lc; rep++) coop_dbl(pts + lane, lane >= rep + 1 && lane <= Lc, &scr);
     phase_stamp(sc, 5);
 #pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {
-        const ge_ext other = shfl_ext(v, (int)(tid ^ o));
-        v = ge_add(v, other);
+    for (uint32_t o = 8; o > 0; o >>= 1) coop_add(pts + lane, pts + lane + o, lane < o, &scr);  // c <= 16 values
+    if (tid < 32) {
+        // (one warp copies the 128 bytes out)
+        if (tid < 8) reinterpret_cast<uint4*>(result + set)[tid] = reinterpret_cast<const uint4*>(pts)[tid];
     }
-    if (tid == 0) store_ext(result + set, v);
     phase_stamp(sc, 6);
 }
 
@@ -684,7 +785,8 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     // chunk geometry: CL is fixed by the knob or derived on the device from the true entry count; the host only needs
     // an upper bound on the number of chunks to size the grid and the partial-slot array
     const uint32_t cl_fixed = (uint32_t)ctx->task_len, cl_min = (uint32_t)ctx->cl_min;
-    const uint32_t target = ctx->target_chunks ? (uint32_t)ctx->target_chunks : (uint32_t)ctx->sm_count * 4u * ACC_THREADS;
+    // default: one and a half waves of resident CTAs (measured best at 2^18 and 2^20: tools/gpu_acc_sweep.py)
+    const uint32_t target = ctx->target_chunks ? (uint32_t)ctx->target_chunks : (uint32_t)ctx->sm_count * 6u * ACC_THREADS;
     uint64_t max_chunks;
     if (cl_fixed) max_chunks = (max_entries + cl_fixed - 1) / cl_fixed;
     else max_chunks = std::min<uint64_t>((max_entries + cl_min - 1) / cl_min, target);
@@ -693,13 +795,19 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     const uint64_t max_partials = (uint64_t)acc_blocks * ACC_THREADS + G + 1;
     const uint32_t bpb = nb < BR_THREADS ? nb : BR_THREADS, lv = ilog2(bpb);
     const uint32_t br_blocks = G / bpb, nblk = nb / bpb;
-    const uint32_t gsize = nblk >= 64 ? 16u : nblk >= 4 ? 4u : nblk;  // CTAs per group (power of two dividing nblk)
+    // CTAs per group and groups per set: powers of two, at most 16 each (the states of a stage live in shared memory)
+    uint32_t gsize = nblk >= 64 ? 16u : nblk >= 4 ? 4u : nblk;
+    while (nblk / gsize > 16) gsize <<= 1;
+    if (gsize > 16) {
+        bpg_set_error("msm_run: more than 2^15 buckets per set are not supported");
+        return BPG_E_ARG;
+    }
     const uint32_t n_groups = br_blocks / gsize;
     MsmWork& w = ctx->work;
     int rc;
     if ((rc = w.hist.ensure(G + 16)) || (rc = w.bucket_off.ensure(G + 16)) || (rc = w.meta.ensure(1)) ||
         (rc = w.entries.ensure(max_entries + 1)) || (rc = w.partials.ensure(max_partials)) ||
-        (rc = w.blockres.ensure((2 * (size_t)br_blocks + 3 * (size_t)n_groups) * REDUCE_MAXV)) ||
+        (rc = w.blockres.ensure(((size_t)br_blocks + (size_t)n_groups) * REDUCE_MAXV)) ||
         (rc = w.reduce_cnt.ensure(n_groups + nsets)))
         return rc;
     if (w.reduce_cnt.fresh) {  // arrival counters: zero between launches (the last arriver re-zeroes its counter)
@@ -745,9 +853,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     CUDA_TRY(mark());
     ReduceScratch rs;
     rs.cta = w.blockres.p;
-    rs.tmp = rs.cta + (size_t)br_blocks * REDUCE_MAXV;
-    rs.grp = rs.tmp + (size_t)br_blocks * REDUCE_MAXV;
-    rs.fin = rs.grp + (size_t)n_groups * REDUCE_MAXV;
+    rs.grp = rs.cta + (size_t)br_blocks * REDUCE_MAXV;
     rs.cnt = w.reduce_cnt.p;
     rs.dbg = nullptr;
     if (timed && getenv("BPG_REDUCE_TRACE")) {

@@ -937,6 +937,25 @@ int bpg_prover_load_cs(bpg_prover* p, const uint8_t* aL32n, const uint8_t* aR32n
     p->circ = p->owned;
     return BPG_OK;
 }
+int bpg_prover_load_cs_bits(bpg_prover* p, uint64_t n, const bpg_bit_run* runs, uint64_t n_runs, const uint8_t* aL32h,
+                            const uint8_t* aR32h, const uint32_t* host_index, uint64_t h, const uint32_t* row_start,
+                            const uint32_t* term_var, const uint8_t* term_coef32, uint64_t q) {
+    if (!p || (n_runs && !runs) || (h && (!aL32h || !aR32h || !host_index))) return BPG_E_ARG;
+    if (p->circ || !p->aL.empty() || p->cs.num_constraints()) {
+        bpg_set_error("load_cs: the bulk loader must be the only constraint-system call on a prover");
+        return BPG_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    int rc = circuit_build(p->ctx, n, p->v.size(), q, row_start, term_var, term_coef32, true, &p->owned);
+    if (rc) return rc;
+    if ((rc = circuit_set_witness_bits(p->owned, runs, n_runs, aL32h, aR32h, host_index, h))) {
+        circuit_free(p->owned);
+        p->owned = nullptr;
+        return rc;
+    }
+    p->circ = p->owned;
+    return BPG_OK;
+}
 uint64_t bpg_prover_num_constraints(const bpg_prover* p) {
     return !p ? 0 : p->circ ? p->circ->q : p->cs.num_constraints();
 }

@@ -145,6 +145,20 @@ int bpg_prover_constrain(bpg_prover* p, const uint32_t* vars, const uint8_t* coe
  * Replaces the op-by-op replay of /root/reference/src/prove.rs:84-99 (assign_buffer). */
 int bpg_prover_load_cs(bpg_prover* p, const uint8_t* aL32n, const uint8_t* aR32n, uint64_t n,
                        const uint32_t* row_start, const uint32_t* term_var, const uint8_t* term_coef32, uint64_t q);
+/* The same with WITNESS GENERATION ON THE DEVICE for the reference's range proof (/root/reference/src/utils.rs:13-31:
+ * for i < n_bits, allocate_multiplier((1 - bit_i(x), bit_i(x)))): the caller passes the values, not the bits.  Multipliers
+ * [first, first + nbits) of run r get a_L = 1 - bit_i(value), a_R = bit_i(value), a_O = 0 in HBM; the h multipliers no run
+ * covers come as compact host arrays aL32h / aR32h with their multiplier indices.  Runs and indices must partition
+ * [0, n).  A BOUND x1024 statement (n = 2^17) uploads 2048 values instead of 8 MB of bit scalars. */
+typedef struct bpg_bit_run {
+    uint64_t first;
+    uint32_t nbits; /* <= 256 */
+    uint32_t reserved;
+    uint8_t value[32]; /* little-endian, the range proof's x_assignment */
+} bpg_bit_run;
+int bpg_prover_load_cs_bits(bpg_prover* p, uint64_t n, const bpg_bit_run* runs, uint64_t n_runs, const uint8_t* aL32h,
+                            const uint8_t* aR32h, const uint32_t* host_index, uint64_t h, const uint32_t* row_start,
+                            const uint32_t* term_var, const uint8_t* term_coef32, uint64_t q);
 /* Prover::num_constraints / get_num_multiplications (FairAds fork) -- /root/reference/src/prove.rs:75,78 */
 uint64_t bpg_prover_num_constraints(const bpg_prover* p);
 uint64_t bpg_prover_num_multipliers(const bpg_prover* p);

@@ -109,3 +109,51 @@ def test_text_batch_matches_golden(eng):
     assert [a for _, a in bpg.verify_text_batch(ctxs, bad)] == [False] * len(texts)
     for c in ctxs[1:]:
         c.close()
+
+
+def _bit_runs(st):
+    """(runs, host_index): maximal runs of multipliers assigned (1 - b, b), as the reference's range proof allocates them."""
+    runs, host = [], []
+    cur = None
+    for i in range(st.n):
+        l = int.from_bytes(bytes(st.aL[32 * i: 32 * i + 32]), "little")
+        r = int.from_bytes(bytes(st.aR[32 * i: 32 * i + 32]), "little")
+        if l in (0, 1) and r in (0, 1) and l + r == 1:
+            if cur is None or cur[0] + cur[1] != i or cur[1] == 256:
+                cur = [i, 0, 0]
+                runs.append(cur)
+            cur[2] |= r << cur[1]
+            cur[1] += 1
+        else:
+            host.append(i)
+            cur = None
+    return [tuple(x) for x in runs], host
+
+
+def test_device_witness_generation_f3(eng):
+    """range-proof bits built in HBM from the values (bpg_prover_load_cs_bits) give the same proof bytes as
+    uploading every multiplier, and as the oracle; partial coverage (LESS_THAN: 378 bit multipliers + 1 product) and a
+    statement without any bit run work; runs that do not partition the multipliers are rejected."""
+    bpg, W, ctx = eng
+    cases = [W.bounds_check_statement(5, max_bytes=8, label=b"f3-a"), W.bounds_check_statement(3, max_bytes=1, label=b"f3-b")]
+    gad, inst, wtns = W.batch_texts(2)[0]
+    cases.append(bpg.flatten_prover("f3-lt", inst, wtns, gad, b"\x04" * 32))
+    for st in cases:
+        runs, host = _bit_runs(st)
+        assert sum(r[1] for r in runs) + len(host) == st.n and runs
+        aLh = b"".join(bytes(st.aL[32 * i: 32 * i + 32]) for i in host)
+        aRh = b"".join(bytes(st.aR[32 * i: 32 * i + 32]) for i in host)
+        p = bpg.Prover(ctx, bpg.Transcript(st.label))
+        coms = p.commit_batch_packed(st.v_bytes, st.vbl_bytes)
+        p.load_cs_bits(st.n, runs, aLh, aRh, host, st.row_start, st.term_var, st.term_coef, st.q)
+        proof = p.prove(b"\x07" * 32)
+        want, coms_c = coracle.prove_flat(st, b"\x07" * 32)
+        assert proof == want and coms == b"".join(coms_c)
+        assert W.prove_statement(bpg, ctx, st, b"\x07" * 32)[0] == proof
+    st = cases[0]
+    runs, host = _bit_runs(st)
+    for bad in (runs[:-1], runs + [runs[0]], [(runs[0][0], runs[0][1] + 1, runs[0][2])] + runs[1:]):
+        p = bpg.Prover(ctx, bpg.Transcript(st.label))
+        p.commit_batch_packed(st.v_bytes, st.vbl_bytes)
+        with pytest.raises(bpg.BpgError):
+            p.load_cs_bits(st.n, bad, b"", b"", [], st.row_start, st.term_var, st.term_coef, st.q)
