@@ -65,7 +65,9 @@ struct MsmSegment {
 struct MsmSegments {
     MsmSegment seg[MSM_MAX_SEGMENTS];
     uint32_t nseg;
-    uint32_t total;  // sum of counts
+    uint32_t total;     // sum of counts
+    uint32_t var_base;  // variable-base form: ONE table row per point (no per-window multiples), window w accumulates
+                        // into bucket set set_id + w; the caller combines the K window sums with doublings
 };
 
 // Fixed-base table: rows[w][i] = affine Niels form of 2^(c*w) * P_i, i < n_points (row stride = n_points)
@@ -172,6 +174,8 @@ cudaError_t ctx_sync(bpg_ctx* ctx);
 // msm.cu
 // asynchronous on ctx->stream; writes nsets extended points to the DEVICE array d_out
 int msm_run(bpg_ctx* ctx, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out);
+// the same over an explicit table (variable-base MSM: rows = the affine Niels forms of the caller's points)
+int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out);
 // copies n <= 32 extended points from device to host (through pinned staging) and waits for the stream
 int fetch_points(bpg_ctx* ctx, const ge_ext* d_pts, uint32_t n, ge_ext* h_out);
 // queues a small device->host copy into the pinned staging page (offset + bytes <= 4096); valid after ctx_sync()

@@ -46,5 +46,9 @@ void pk_compress(cudaStream_t st, const ge_ext* in, uint8_t* out, uint32_t n);
 void pk_decompress(cudaStream_t st, const uint8_t* in, ge_ext* out, uint32_t n, uint32_t* fail);
 // out = sum_i s_i * P_i for arbitrary (dynamic) points; blockres scratch >= ceil(n/64) points
 void pk_dyn_msm(cudaStream_t st, const ge_ext* pts, const sc* s, uint32_t n, ge_ext* blockres, ge_ext* out);
+// rows[i] = affine Niels form of the i-th ristretto encoding (identity + *fail++ when it does not decode)
+void pk_decompress_niels(cudaStream_t st, const uint8_t* in, ge_niels* rows, uint32_t n, uint32_t* fail);
+// out = sum_w 2^(c w) W[w], w < K
+void pk_window_combine(cudaStream_t st, const ge_ext* W, int K, int c, ge_ext* out);
 // out = a + b
 void pk_add2(cudaStream_t st, const ge_ext* a, const ge_ext* b, ge_ext* out);

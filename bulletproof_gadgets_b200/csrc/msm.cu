@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
     if (sg.mode == 1) set += ((i % sg.period) >= (sg.period >> 1)) ? 0u : 1u;
     if (sg.mode == 2) set += ((i % sg.period) < (sg.period >> 1)) ? 0u : 1u;
     const uint32_t point = sg.point_base + i;
+    const uint32_t row_stride = segs.var_base ? 0u : n_points, set_stride = segs.var_base ? 1u : 0u;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
     uint32_t carry = 0;
     if (K <= 16) {
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
                 const uint32_t mag = neg ? ((1u << c) - raw) : raw;
                 carry = neg;
                 if (mag != 0) {  // implies nz
-                    gbv[w] = set * nb + (mag - 1);
-                    entv[w] = ((uint32_t)w * n_points + point) | (neg << 31);
+                    gbv[w] = (set + (uint32_t)w * set_stride) * nb + (mag - 1);
+                    entv[w] = ((uint32_t)w * row_stride + point) | (neg << 31);
                 }
             }
         }
@@ -171,12 +172,12 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
         uint32_t mag = neg ? ((1u << c) - raw) : raw;
         carry = neg;
         if (mag != 0) {
-            uint32_t gb = set * nb + (mag - 1);
+            uint32_t gb = (set + (uint32_t)w * set_stride) * nb + (mag - 1);
             if (!SCATTER) {
                 atomicAdd(&hist[gb], 1u);
             } else {
                 uint32_t pos = atomicAdd(&hist[gb], 1u);
-                entries[bucket_off[gb] + pos] = ((uint32_t)w * n_points + point) | (neg << 31);
+                entries[bucket_off[gb] + pos] = ((uint32_t)w * row_stride + point) | (neg << 31);
             }
         }
     }
@@ -766,9 +767,13 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
         return BPG_E_ARG;
     }
     MsmSegments segs = segs_in;
+    segs.var_base = 0;
     const bool use_small = to_small_table(ctx->table, ctx->small_table, &segs);
-    const FixedTable& tb = use_small ? ctx->small_table : ctx->table;
-    if (nsets == 0 || segs.nseg > MSM_MAX_SEGMENTS) return BPG_E_ARG;
+    return msm_run_table(ctx, use_small ? ctx->small_table : ctx->table, segs, nsets, d_out);
+}
+
+int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, uint32_t nsets, ge_ext* d_out) {
+    if (nsets == 0 || segs.nseg > MSM_MAX_SEGMENTS || !tb.rows) return BPG_E_ARG;
     cudaStream_t st = ctx->stream;
     const uint32_t nb = 1u << (tb.c - 1);
     const uint32_t G = nsets * nb;
@@ -778,7 +783,7 @@ int msm_run(bpg_ctx* ctx, const MsmSegments& segs_in, uint32_t nsets, ge_ext* d_
     }
     const uint64_t total = segs.total;
     const uint64_t max_entries = (uint64_t)tb.K * total;
-    if (max_entries >= (1ull << 32) - (1ull << 24) || (uint64_t)tb.K * tb.n_points >= (1ull << 31)) {
+    if (max_entries >= (1ull << 32) - (1ull << 24) || (uint64_t)(segs.var_base ? 1 : tb.K) * tb.n_points >= (1ull << 31)) {
         bpg_set_error("msm_run: problem too large for 32-bit entry indices");
         return BPG_E_ARG;
     }

@@ -145,6 +145,44 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_final(const ge_ext* __restr
 __global__ void k_add2(const ge_ext* a, const ge_ext* b, ge_ext* out) { *out = ge_add(*a, *b); }
 
 // ------------------------------------------------------------------------------------------
+// variable-base Pippenger (bpg_msm above a few hundred points): table rows straight from the encodings, window combine
+// ------------------------------------------------------------------------------------------
+// ristretto decoding yields an AFFINE point (Z = 1), so its Niels form (y+x, y-x, 2dxy) needs no inversion
+__global__ void __launch_bounds__(64) k_decompress_niels(const uint8_t* __restrict__ in, ge_niels* __restrict__ rows,
+                                                         uint32_t n, uint32_t* __restrict__ fail) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32];
+    for (int k = 0; k < 32; k++) b[k] = in[32 * (size_t)i + k];
+    ge_ext p;
+    ge_niels q = ge_niels_identity();
+    if (ge_ristretto_decompress(&p, b)) {
+        q.yp = fe_add(p.Y, p.X);
+        q.ym = fe_sub(p.Y, p.X);
+        q.t2d = fe_mul(p.T, fe_2D());
+    } else {
+        atomicAdd(fail, 1u);
+    }
+    rows[i] = q;
+}
+// sum_w 2^(c w) W_w by Horner from the top window (K c doublings: the serial tail of every variable-base Pippenger)
+__global__ void k_window_combine(const ge_ext* __restrict__ W, int K, int c, ge_ext* __restrict__ out) {
+    ge_ext acc = W[K - 1];
+#pragma unroll 1
+    for (int w = K - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int k = 0; k < c - 1; k++) acc = ge_dbl_not(acc);
+        acc = ge_dbl(acc);
+        acc = ge_add(acc, W[w]);
+    }
+    *out = acc;
+}
+void pk_decompress_niels(cudaStream_t st, const uint8_t* in, ge_niels* rows, uint32_t n, uint32_t* fail) {
+    if (n) k_decompress_niels<<<(n + 63) / 64, 64, 0, st>>>(in, rows, n, fail);
+}
+void pk_window_combine(cudaStream_t st, const ge_ext* W, int K, int c, ge_ext* out) { k_window_combine<<<1, 1, 0, st>>>(W, K, c, out); }
+
+// ------------------------------------------------------------------------------------------
 void pk_pedersen_table(cudaStream_t st, const ge_ext* gens_ext, uint32_t idxB, ge_niels* ped) {
     k_pedersen_table<<<1, 128, 0, st>>>(gens_ext, idxB, ped);
 }

@@ -40,6 +40,7 @@ struct ProofWork {
     DevBuf<sc> fl_part;
     DevBuf<uint8_t> wide, dyn_enc;
     DevBuf<ge_ext> dyn_pts, dyn_blk;
+    DevBuf<ge_niels> dyn_rows;  // variable-base Pippenger: one affine Niels row per caller point
     uint8_t* h_pin = nullptr;  // pinned staging
     size_t h_pin_cap = 0;
     int pin(size_t n) {
@@ -65,6 +66,7 @@ void r1cs_release_work(bpg_ctx* ctx) {
     p->dyn_enc.release();
     p->dyn_pts.release();
     p->dyn_blk.release();
+    p->dyn_rows.release();
     if (p->h_pin) cudaFreeHost(p->h_pin);
     delete p;
     ctx->pw = nullptr;
@@ -85,6 +87,15 @@ __global__ void __launch_bounds__(256) k_wide_reduce(const uint8_t* __restrict__
     hi.v[0] = c.x, hi.v[1] = c.y, hi.v[2] = c.z, hi.v[3] = c.w, hi.v[4] = d.x, hi.v[5] = d.y, hi.v[6] = d.z, hi.v[7] = d.w;
     const uint32_t Rl[8] = SC_R_LIMBS;
     out[i] = sc_add(sc_reduce(lo), sc_mul(hi, sc_const(Rl)));
+}
+
+// raw 32-byte scalars (< 2^255) -> canonical, in place; *err |= 2 when bit 255 is set (not a valid Scalar)
+__global__ void __launch_bounds__(256) k_sc_canon(sc* __restrict__ s, uint32_t n, uint32_t* __restrict__ err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc x = s[i];
+    if (x.v[7] >> 31) atomicOr(err, 2u);
+    s[i] = sc_reduce(x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -783,27 +794,62 @@ int bpg_msm(bpg_ctx* ctx, const uint8_t* scalars32n, const uint8_t* points32n, u
     ProofWork* pw = work(ctx);
     cudaStream_t st = ctx->stream;
     int rc;
-    std::vector<sc> s(n ? n : 1);
-    for (uint64_t i = 0; i < n; i++) {
-        if (scalars32n[32 * i + 31] & 0x80) return BPG_E_ARG;
-        s[i] = Scalar::from_bytes_mod_order(scalars32n + 32 * i).s;
+    if (n >= (1ull << 27)) {
+        bpg_set_error("msm: more than 2^27 points");
+        return BPG_E_ARG;
     }
-    if ((rc = pw->dyn_s.ensure(n + 1)) || (rc = pw->dyn_enc.ensure(32 * n + 32)) || (rc = pw->dyn_pts.ensure(n + 1)) ||
-        (rc = pw->dyn_blk.ensure(n / 64 + 2)) || (rc = pw->fail.ensure(1)) || (rc = ctx->d_points.ensure(64)))
+    static const uint64_t pip_min = [] {  // BPG_VARBASE_MIN: smallest n that takes the Pippenger path (A/B measurements)
+        const char* e = getenv("BPG_VARBASE_MIN");
+        return e ? (uint64_t)atoll(e) : (uint64_t)512;
+    }();
+    const bool pippenger = n >= pip_min;
+    if ((rc = pw->dyn_s.ensure(n + 1)) || (rc = pw->dyn_enc.ensure(32 * n + 32)) || (rc = pw->fail.ensure(2)) ||
+        (rc = ctx->d_points.ensure(64)))
         return rc;
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(pw->dyn_s.p, s.data(), 32 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(pw->fail.p, 0, 8, st));  // [0] undecodable points, [1] invalid scalars
+    if (n) {  // scalars go up as given and are reduced mod l on the device
+        CUDA_TRY(cudaMemcpyAsync(pw->dyn_s.p, scalars32n, 32 * n, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(pw->dyn_enc.p, points32n, 32 * n, cudaMemcpyHostToDevice, st));
+        k_sc_canon<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(pw->dyn_s.p, (uint32_t)n, pw->fail.p + 1);
+        ctx->launches++;
     }
-    CUDA_TRY(cudaMemsetAsync(pw->fail.p, 0, 4, st));
-    pk_decompress(st, pw->dyn_enc.p, pw->dyn_pts.p, (uint32_t)n, pw->fail.p);
-    pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, (uint32_t)n, pw->dyn_blk.p, ctx->d_points.p + 12);
-    ctx->launches += 3;
-    const uint32_t* failp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, pw->fail.p, 4));
+    if (pippenger) {
+        // Variable-base Pippenger (dalek: vartime_multiscalar_mul above 190 points, reached from
+        // /root/reference/src/verify.rs:71): the caller's points become a one-row-per-point table, window w of every
+        // scalar goes to bucket set w through the same sort / accumulate / reduce kernels as the fixed-base MSM, and the
+        // K window sums are combined with c doublings each.  Window width by size: ~2^(c-1) buckets <= points / 4.
+        if ((rc = pw->dyn_rows.ensure(n))) return rc;
+        int c = 8;
+        while (c < 16 && (1ull << (c + 2)) <= n) c++;
+        FixedTable tb;
+        tb.rows = pw->dyn_rows.p;
+        tb.n_points = (uint32_t)n;
+        tb.c = c;
+        tb.K = (254 + c - 1) / c;  // one spare bit: the signed recoding of a 253-bit scalar carries out of bit 252
+        tb.capacity = n;
+        pk_decompress_niels(st, pw->dyn_enc.p, pw->dyn_rows.p, (uint32_t)n, pw->fail.p);
+        MsmSegments segs;
+        memset(&segs, 0, sizeof segs);
+        seg_push(segs, pw->dyn_s.p, 0, n, 0, 0, 1);
+        segs.var_base = 1;
+        if ((rc = msm_run_table(ctx, tb, segs, (uint32_t)tb.K, ctx->d_points.p + 16))) return rc;
+        pk_window_combine(st, ctx->d_points.p + 16, tb.K, c, ctx->d_points.p + 12);
+        ctx->launches += 2;
+    } else {
+        if ((rc = pw->dyn_pts.ensure(n + 1)) || (rc = pw->dyn_blk.ensure(n / 64 + 2))) return rc;
+        pk_decompress(st, pw->dyn_enc.p, pw->dyn_pts.p, (uint32_t)n, pw->fail.p);
+        pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, (uint32_t)n, pw->dyn_blk.p, ctx->d_points.p + 12);
+        ctx->launches += 3;
+    }
+    const uint32_t* failp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, pw->fail.p, 8));
     ge_ext res;
     if (!failp) return BPG_E_CUDA;
     if ((rc = fetch_points(ctx, ctx->d_points.p + 12, 1, &res))) return rc;
-    const uint32_t fail = *failp;
+    const uint32_t fail = failp[0];
+    if (failp[1]) {
+        bpg_set_error("msm: scalar with bit 255 set (not a valid Scalar)");
+        return BPG_E_ARG;
+    }
     if (fail) {
         bpg_set_error("msm: %u point(s) failed to decompress", fail);
         return BPG_E_VERIFY;

@@ -87,6 +87,27 @@ def test_msm_arbitrary_points_vs_oracle(ctx):
     assert e.value.code == -2
 
 
+@pytest.mark.parametrize("n", [512, 777, 4096, 20000])
+def test_msm_variable_base_pippenger_vs_oracle(ctx, n):
+    """bpg_msm above 512 points takes the variable-base Pippenger path (window sums over per-window bucket sets, combined
+    with doublings): same bytes as the C oracle's vartime Pippenger and as the thread-per-point path; zero scalars, the
+    scalar l - 1, repeated points and the identity among the inputs."""
+    import bulletproof_gadgets_b200 as bpg
+    rnd = random.Random(n)
+    base = [ed.from_uniform_bytes(hashlib.shake_256(b"vb-%d" % i).digest(64)).compress() for i in range(64)]
+    pts = [base[rnd.randrange(64)] for _ in range(n)]
+    pts[3] = bytes(32)                                   # the identity encodes as 32 zero bytes
+    s = [rnd.randrange(L) for _ in range(n)]
+    s[0], s[1], s[2], s[5] = 0, L - 1, 1, 2**252
+    want = coracle.msm(s, pts)
+    assert ctx.msm(s, pts) == want
+    bits = [rnd.randrange(2) for _ in range(n)]          # 0/1 scalars: one heavy bucket in window 0
+    assert ctx.msm(bits, pts) == coracle.msm(bits, pts)
+    with pytest.raises(bpg.BpgError) as e:
+        ctx.msm(s, pts[:7] + [bytes.fromhex("01" + "00" * 31)] + pts[8:])
+    assert e.value.code == -2
+
+
 def test_pedersen_batch_vs_oracle(ctx):
     pg = O.PedersenGens()
     vs = [0, 1, L - 1, 2**255 - 1, 2**64 - 1] + [sc(b"pv", i) for i in range(60)]
