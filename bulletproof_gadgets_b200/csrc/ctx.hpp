@@ -113,6 +113,10 @@ struct MsmWork {
     DevBuf<unsigned long long> reduce_dbg;  // diagnostic phase stamps of k_bucket_reduce (BPG_REDUCE_TRACE)
     DevBuf<uint32_t> reduce_cnt;    // arrival counters of the reduction's group and set stages (zero between launches)
     DevBuf<uint32_t> scan_tmp;      // tile sums of the bucket scan (multi-CTA fallback)
+    DevBuf<uint32_t> sort_cnt, sort_base;  // shared-memory sort: [bins][CTAs] counts and their exclusive scan
+    DevBuf<uint32_t> sort_small;           // arrival counter, bin totals, bin starts
+    DevBuf<uint32_t> sort_val;             // row|sign of every entry, grouped by coarse bin
+    DevBuf<uint8_t> sort_fine;             // its fine bucket (bucket & 255)
     DevBuf<uint32_t> tickets;       // [16][points] rank of each entry inside its bucket (histogram pass -> scatter pass)
 };
 
@@ -136,6 +140,8 @@ struct bpg_ctx {
     int cl_min = 8;
     int acc_variant = 0;      // k_accumulate variant (msm.cu): 0 = 4 CTAs/SM, 1 = next row prefetched, 2 = 5 CTAs/SM
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
+    bool sort_attr_set = false;
+    int use_smem_sort = 1;  // two-level shared-memory counting sort where it applies (msm.cu k_sort_*), else k_digits
     int sm_count = 148;
     // counters for bench.py ("gpu_launches")
     uint64_t launches = 0;

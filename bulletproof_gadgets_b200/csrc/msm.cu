@@ -26,6 +26,8 @@
 //   6 final              remaining butterfly levels across CTAs, then sum (b+1) S_b = R + sum_j 2^j M_j
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -179,6 +181,289 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
                 uint32_t pos = atomicAdd(&hist[gb], 1u);
                 entries[bucket_off[gb] + pos] = ((uint32_t)w * row_stride + point) | (neg << 31);
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stages 1-3, shared-memory form (two-level counting sort; used when a bucket set has >= 256 buckets and at most 65 536
+// buckets exist in all): no global atomics and no scattered 4-byte stores.
+//   k_sort_count    CTA = 512 scalars: digits, histogram of the COARSE bin (bucket >> 8) in shared memory,
+//                   one column of the [bin][CTA] count matrix per CTA
+//   (scan)          exclusive scan of the matrix in bin-major order = where each CTA's share of each bin starts;
+//                   the same launch derives the chunk geometry from the entry count (scan.cu: k_scan_meta)
+//   k_sort_scatter  digits again; the CTA's <= 8192 entries are counting-sorted by bin in shared memory and copied out
+//                   as (bucket, row|sign) pairs: every bin run of a CTA is one contiguous, coalesced store
+//   k_sort_bins     one thread-block CLUSTER per bin (its entries are contiguous now): the CTAs count the 256 fine buckets of
+//                   their slices in shared memory, exchange the counts through distributed shared memory, write the
+//                   bucket offsets (= bucket_off, no global scan) and store their slices sorted by fine bucket
+// ------------------------------------------------------------------------------------------
+#define SORT_PTS 512          // scalars per CTA of k_sort_count / k_sort_scatter (2 per thread)
+
+// digits of scalar g -> up to 16 (bucket, row|sign) pairs; bucket DG_NONE = no entry.  K <= 16.
+__device__ __forceinline__ void decode_scalar(const MsmSegments& segs, uint32_t g, int c, int K, uint32_t nb, uint32_t n_points,
+                                              uint32_t gbv[16], uint32_t entv[16]) {
+#pragma unroll
+    for (int w = 0; w < 16; w++) gbv[w] = DG_NONE, entv[w] = 0;
+    if (g >= segs.total) return;
+    uint32_t si = 0, base = 0, end = 0;
+#pragma unroll
+    for (int k = 0; k < MSM_MAX_SEGMENTS; k++) {
+        if (k < (int)segs.nseg) {
+            end += segs.seg[k].count;
+            if (g >= end) {
+                base = end;
+                si = k + 1;
+            }
+        }
+    }
+    const MsmSegment sg = segs.seg[si];
+    const uint32_t i = g - base;
+    const uint4* sp = reinterpret_cast<const uint4*>(sg.scalars) + 2 * (size_t)i;
+    const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t set = sg.set_id;
+    if (sg.mode == 1) set += ((i % sg.period) >= (sg.period >> 1)) ? 0u : 1u;
+    if (sg.mode == 2) set += ((i % sg.period) < (sg.period >> 1)) ? 0u : 1u;
+    const uint32_t point = sg.point_base + i;
+    const uint32_t row_stride = segs.var_base ? 0u : n_points, set_stride = segs.var_base ? 1u : 0u;
+    const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
+    uint32_t carry = 0;
+#pragma unroll
+    for (int w = 0; w < 16; w++) {
+        if (w < K) {
+            const uint32_t raw = (s[0] & mask) + carry;
+#pragma unroll
+            for (int k = 0; k < 7; k++) s[k] = __funnelshift_r(s[k], s[k + 1], c);
+            s[7] >>= c;
+            const uint32_t neg = raw > half;
+            const uint32_t mag = neg ? ((1u << c) - raw) : raw;
+            carry = neg;
+            if (mag != 0) {
+                gbv[w] = (set + (uint32_t)w * set_stride) * nb + (mag - 1);
+                entv[w] = ((uint32_t)w * row_stride + point) | (neg << 31);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_count(MsmSegments segs, int c, int K, uint32_t nb, uint32_t n_points,
+                                                    uint32_t nbins, uint32_t* __restrict__ cnt /* [nbins][gridDim.x] */) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < SORT_PTS / 256; r++) {
+        uint32_t gbv[16], entv[16];
+        decode_scalar(segs, blockIdx.x * SORT_PTS + r * 256 + threadIdx.x, c, K, nb, n_points, gbv, entv);
+#pragma unroll
+        for (int w = 0; w < 16; w++)
+            if (gbv[w] != DG_NONE) atomicAdd(&h[gbv[w] >> 8], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < nbins) cnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wt /* [8] */) {  // threads 0..255, 256 values
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) wt[wid] = inc;
+    __syncthreads();
+    uint32_t add = 0;
+    for (uint32_t k = 0; k < wid; k++) add += wt[k];
+    __syncthreads();
+    return add + inc - v;
+}
+// Offsets of the [bin][CTA] count matrix without a global scan: CTA b scans row b (where each scatter CTA's share of bin b
+// starts INSIDE the bin) and publishes the bin total; the CTA that arrives last scans the <= 256 totals into bin_start[]
+// and derives the chunk geometry from the entry count.  Consumers add bin_start[bin] + pre[bin][cta].
+__global__ void __launch_bounds__(256) k_sort_scan(const uint32_t* __restrict__ cnt, uint32_t nctas, uint32_t nbins,
+                                                   uint32_t* __restrict__ pre, uint32_t* __restrict__ tot /* [nbins] */,
+                                                   uint32_t* __restrict__ bin_start /* [nbins + 1] */, uint32_t* __restrict__ arrive,
+                                                   uint32_t target_chunks, uint32_t cl_min, uint32_t cl_fixed, MsmMeta* __restrict__ meta) {
+    __shared__ uint32_t wt[8];
+    __shared__ uint32_t sh_last;
+    const uint32_t tid = threadIdx.x, b = blockIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t t0 = 0; t0 < nctas; t0 += 256) {
+        const uint32_t i = t0 + tid, v = i < nctas ? cnt[(size_t)b * nctas + i] : 0u;
+        const uint32_t ex = block_excl_scan_256(v, wt);
+        if (i < nctas) pre[(size_t)b * nctas + i] = carry + ex;
+        __shared__ uint32_t tile_total;
+        if (tid == 255) tile_total = ex + v;
+        __syncthreads();
+        carry += tile_total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        tot[b] = carry;
+        __threadfence();
+        sh_last = atomicAdd(arrive, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    const uint32_t v = tid < nbins ? __ldcg(tot + tid) : 0u;
+    const uint32_t ex = block_excl_scan_256(v, wt);
+    if (tid < nbins) bin_start[tid] = ex;
+    if (tid == 255) {
+        const uint32_t E = ex + v;
+        bin_start[nbins] = E;
+        uint32_t cl = cl_fixed;
+        if (cl == 0) {
+            cl = (uint32_t)(((uint64_t)E + target_chunks - 1) / target_chunks);
+            if (cl < cl_min) cl = cl_min;
+        }
+        meta->E = E;
+        meta->CL = cl;
+        meta->nchunks = (uint32_t)(((uint64_t)E + cl - 1) / cl);
+        meta->pad = 0;
+        *arrive = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(MsmSegments segs, int c, int K, uint32_t nb, uint32_t n_points,
+                                                      uint32_t nbins, const uint32_t* __restrict__ pre, const uint32_t* __restrict__ bin_start,
+                                                      uint32_t* __restrict__ inter_val, uint8_t* __restrict__ inter_fine) {
+    // staging: row|sign (4 B) and the 16-bit bucket (2 B) of the CTA's <= SORT_PTS * 16 entries, sorted by coarse bin
+    extern __shared__ uint32_t st_dyn[];  // SORT_PTS * 16 * 6 bytes
+    uint32_t* st_val = st_dyn;
+    uint16_t* st_key = reinterpret_cast<uint16_t*>(st_dyn + SORT_PTS * 16);
+    __shared__ uint32_t h[256], loc[256], cur[256], gbase[256], wt[8];
+    const uint32_t tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < SORT_PTS / 256; r++) {
+        uint32_t gbv[16], entv[16];
+        decode_scalar(segs, blockIdx.x * SORT_PTS + r * 256 + tid, c, K, nb, n_points, gbv, entv);
+#pragma unroll
+        for (int w = 0; w < 16; w++)
+            if (gbv[w] != DG_NONE) atomicAdd(&h[gbv[w] >> 8], 1u);
+    }
+    __syncthreads();
+    {
+        const uint32_t ex = block_excl_scan_256(h[tid], wt);
+        loc[tid] = ex;
+        cur[tid] = ex;
+        gbase[tid] = tid < nbins ? bin_start[tid] + pre[(size_t)tid * gridDim.x + blockIdx.x] : 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < SORT_PTS / 256; r++) {
+        uint32_t gbv[16], entv[16];
+        decode_scalar(segs, blockIdx.x * SORT_PTS + r * 256 + tid, c, K, nb, n_points, gbv, entv);
+#pragma unroll
+        for (int w = 0; w < 16; w++)
+            if (gbv[w] != DG_NONE) {
+                const uint32_t i = atomicAdd(&cur[gbv[w] >> 8], 1u);
+                st_val[i] = entv[w];
+                st_key[i] = (uint16_t)gbv[w];
+            }
+    }
+    __syncthreads();
+    const uint32_t n_local = loc[255] + h[255];
+    for (uint32_t j = tid; j < n_local; j += 256) {
+        const uint32_t key = st_key[j], bin = key >> 8, dst = gbase[bin] + (j - loc[bin]);
+        inter_val[dst] = st_val[j];
+        inter_fine[dst] = (uint8_t)key;
+    }
+}
+
+// bin b = entries [bin_start[b], bin_start[b + 1]) of `inter`, all of buckets [256 b, 256 b + 256).
+// One thread-block CLUSTER of SORT_CLUSTER CTAs per bin: every CTA counts the fine buckets of its slice in its own shared
+// memory, reads the other CTAs' counts through distributed shared memory (no global histogram, no second kernel), and
+// places its slice -- through a shared-memory staging buffer, so that every (CTA, bucket) run leaves as one contiguous store.
+// A bin of any size is spread over the cluster, which keeps structured scalars (one bucket holding most entries) parallel.
+#define SORT_CLUSTER 8
+#define SORT_SLICE_SMEM 4096u  // slice entries staged in shared memory (20 KB); larger slices store directly
+#define SORT_REG 16  // slice entries a thread keeps in registers between counting and placing (slices up to 4096)
+__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(256)
+    k_sort_bins(const uint32_t* __restrict__ inter_val, const uint8_t* __restrict__ inter_fine, const uint32_t* __restrict__ bin_start,
+                uint32_t nbins, uint32_t* __restrict__ bucket_off, uint32_t* __restrict__ entries) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ uint32_t h[256], lofs[256], gofs[256], cur[256], wt[8];
+    __shared__ uint32_t out_s[SORT_SLICE_SMEM];
+    __shared__ uint8_t out_k[SORT_SLICE_SMEM];
+    const uint32_t tid = threadIdx.x, rank = cluster.block_rank(), bin = blockIdx.x / SORT_CLUSTER;
+    const uint32_t b0 = bin_start[bin], b1 = bin_start[bin + 1];  // bin_start[nbins] = E
+    const uint32_t n = b1 - b0, slice = (n + SORT_CLUSTER - 1) / SORT_CLUSTER;
+    const uint32_t s0 = min(b0 + rank * slice, b1), s1 = min(s0 + slice, b1), ns = s1 - s0;
+    const bool in_regs = ns <= SORT_REG * 256;
+    h[tid] = 0;
+    __syncthreads();
+    // count; a slice of up to 4096 entries stays in registers for the placing pass (one read of the intermediate array)
+    uint32_t rv[SORT_REG], rk[SORT_REG];
+    if (in_regs) {
+#pragma unroll
+        for (int u = 0; u < SORT_REG; u++) {
+            const uint32_t j = s0 + u * 256 + tid;
+            rk[u] = j < s1 ? (uint32_t)inter_fine[j] : DG_NONE;
+            rv[u] = j < s1 ? inter_val[j] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < SORT_REG; u++)
+            if (rk[u] != DG_NONE) atomicAdd(&h[rk[u]], 1u);
+    } else {
+        for (uint32_t j0 = s0 + tid; j0 < s1; j0 += 8 * 256) {
+            uint32_t k[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) k[u] = j0 + u * 256 < s1 ? (uint32_t)inter_fine[j0 + u * 256] : DG_NONE;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (k[u] != DG_NONE) atomicAdd(&h[k[u]], 1u);
+        }
+    }
+    cluster.sync();
+    // fine bucket `tid`: entries of the lower-ranked CTAs, and of the whole bin
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < SORT_CLUSTER; q++) {
+        const uint32_t c = cluster.map_shared_rank(h, q)[tid];
+        before += q < rank ? c : 0u;
+        total += c;
+    }
+    const uint32_t off = block_excl_scan_256(total, wt);   // start of the bucket inside the bin
+    const uint32_t lo = block_excl_scan_256(h[tid], wt);   // start of the bucket inside this CTA's slice
+    gofs[tid] = b0 + off + before;                         // where this CTA's run of the bucket goes
+    lofs[tid] = lo;
+    cur[tid] = lo;
+    if (rank == 0) {
+        bucket_off[(size_t)bin * 256 + tid] = b0 + off;
+        if (bin == nbins - 1 && tid == 255) bucket_off[(size_t)nbins * 256] = b1;
+    }
+    cluster.sync();  // nobody leaves (or reuses h) while its counts are still being read
+    if (in_regs) {
+#pragma unroll
+        for (int u = 0; u < SORT_REG; u++)
+            if (rk[u] != DG_NONE) {
+                const uint32_t i = atomicAdd(&cur[rk[u]], 1u);
+                out_s[i] = rv[u];
+                out_k[i] = (uint8_t)rk[u];
+            }
+        __syncthreads();
+        for (uint32_t i = tid; i < ns; i += 256) {
+            const uint32_t k = out_k[i];
+            entries[gofs[k] + (i - lofs[k])] = out_s[i];
+        }
+    } else {  // an oversized slice (structured scalars: a few buckets hold everything, consecutive ranks = consecutive words)
+        for (uint32_t j0 = s0 + tid; j0 < s1; j0 += 8 * 256) {
+            uint32_t k[8], v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const bool ok = j0 + u * 256 < s1;
+                k[u] = ok ? (uint32_t)inter_fine[j0 + u * 256] : DG_NONE;
+                v[u] = ok ? inter_val[j0 + u * 256] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (k[u] != DG_NONE) entries[gofs[k[u]] + (atomicAdd(&cur[k[u]], 1u) - lofs[k[u]])] = v[u];
         }
     }
 }
@@ -820,14 +1105,44 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
         w.reduce_cnt.fresh = false;
     }
 
+    const bool timed = ctx->time_accum;
+    int stage = 0;
+    auto mark = [&]() -> cudaError_t { return timed ? cudaEventRecord(ctx->ev_stage[stage++], st) : cudaSuccess; };
+    const uint32_t nbins = G / 256, sort_ctas = (uint32_t)((total + SORT_PTS - 1) / SORT_PTS);
+    const bool smem_sort = ctx->use_smem_sort && tb.K <= 16 && nb >= 256 && G <= 65536 && total > 0 &&
+                           (uint64_t)nbins * sort_ctas < (1ull << 26);
+    if (smem_sort) {
+        const size_t ncnt = (size_t)nbins * sort_ctas;
+        if ((rc = w.sort_cnt.ensure(ncnt + 16)) || (rc = w.sort_base.ensure(ncnt + 16)) || (rc = w.sort_val.ensure(max_entries + 1)) || (rc = w.sort_fine.ensure(max_entries + 16)) ||
+            (rc = w.sort_small.ensure(1024)))
+            return rc;
+        if (w.sort_small.fresh) {  // [0] arrival counter (zero between launches), [8 ..] bin totals, [264 ..] bin starts
+            CUDA_TRY(cudaMemsetAsync(w.sort_small.p, 0, w.sort_small.cap * 4, st));
+            w.sort_small.fresh = false;
+        }
+        uint32_t *arrive = w.sort_small.p, *bin_tot = w.sort_small.p + 8, *bin_start = w.sort_small.p + 8 + 256;
+
+        CUDA_TRY(mark());
+        k_sort_count<<<sort_ctas, 256, 0, st>>>(segs, tb.c, tb.K, nb, tb.n_points, nbins, w.sort_cnt.p);
+        CUDA_TRY(mark());
+        k_sort_scan<<<nbins, 256, 0, st>>>(w.sort_cnt.p, sort_ctas, nbins, w.sort_base.p, bin_tot, bin_start, arrive, target, cl_min,
+                                           cl_fixed, w.meta.p);
+        CUDA_TRY(mark());
+        if (!ctx->sort_attr_set) {  // per device: once per context
+            CUDA_TRY(cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_PTS * 16 * 6));
+            ctx->sort_attr_set = true;
+        }
+        k_sort_scatter<<<sort_ctas, 256, SORT_PTS * 16 * 6, st>>>(segs, tb.c, tb.K, nb, tb.n_points, nbins, w.sort_base.p, bin_start,
+                                                                  w.sort_val.p, w.sort_fine.p);
+        k_sort_bins<<<nbins * SORT_CLUSTER, 256, 0, st>>>(w.sort_val.p, w.sort_fine.p, bin_start, nbins, w.bucket_off.p, w.entries.p);
+        CUDA_TRY(mark());
+        ctx->launches += 4;
+    } else {
     uint32_t* tickets = nullptr;  // rank of every entry inside its bucket (unrolled K <= 16 path of k_digits only)
     if (ctx->use_tickets && tb.K <= 16 && total > 0) {
         if ((rc = w.tickets.ensure((size_t)16 * total))) return rc;
         tickets = w.tickets.p;
     }
-    const bool timed = ctx->time_accum;
-    int stage = 0;
-    auto mark = [&]() -> cudaError_t { return timed ? cudaEventRecord(ctx->ev_stage[stage++], st) : cudaSuccess; };
     if (w.hist_dirty || w.hist.fresh) {  // afterwards the scan kernel leaves it zeroed for the next MSM
         CUDA_TRY(cudaMemsetAsync(w.hist.p, 0, w.hist.cap * 4, st));
         w.hist_dirty = false;
@@ -849,6 +1164,7 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
         if (!tickets) w.hist_dirty = true;  // the scatter pass used it as its cursor
     }
     CUDA_TRY(mark());
+    }
     if (ctx->acc_variant == 2)
         k_accumulate<2><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
     else if (ctx->acc_variant == 1)
