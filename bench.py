@@ -102,6 +102,23 @@ def _thread_cpu_by_name():
     return {k: round(v, 3) for k, v in sorted(out.items(), key=lambda kv: -kv[1])[:8]}
 
 
+def measure_imad_peak(gpu_index):
+    """(IMAD.WIDE.U32 per second, 32-bit IMAD per second) from the register-only issue-rate microbenchmark
+    (bulletproof_gadgets_b200/bin/imad_peak --quick, ~0.4 s); falls back to the pool's recorded figure if it cannot run."""
+    exe = os.path.join(ROOT, "bulletproof_gadgets_b200", "bin", "imad_peak")
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(gpu_index)) if "CUDA_VISIBLE_DEVICES" not in os.environ else os.environ
+        out = subprocess.run([exe, "--quick"], capture_output=True, text=True, timeout=60, env=env).stdout
+        vals = {}
+        for ln in out.splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                vals[d["op"]] = d["Tops"] * 1e12
+        return vals["IMAD.WIDE.U32"], vals["IMAD"]
+    except Exception:  # noqa: BLE001
+        return IMAD_WIDE_PEAK_TOPS * 1e12, 18.5e12
+
+
 def run_reference(args, ws, rank):
     """CPU restatement (oracle/c) on all host cores; bounded sample: BOUND x128 per worker per step."""
     if rank != 0:
@@ -194,8 +211,9 @@ def main():
     warmup = max(args.warmup, 3)
     inflight = args.inflight or (48 if (os.cpu_count() or 1) // ws >= 12 else 32)
     ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
-    # roofline denominator, measured BEFORE the load (a kernel timed alone sees these clocks: the "burst" figure) ...
-    imad_wide_peak, imad32_peak = ctx0.measure_imad_peak()
+    # roofline denominator, measured in this run BEFORE the load (a kernel timed alone sees these clocks: the "burst" figure):
+    # the issue-rate microbenchmark of round 1 (tools/imad_peak.cu, built with the library), rank 0's GPU
+    imad_wide_peak, imad32_peak = measure_imad_peak(local_rank)
     ctxs = [ctx0] + [ctx0.shared() for _ in range(inflight - 1)]
     st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank).pin(bpg)
     ctx0.gens_ensure(st.n)
@@ -283,9 +301,7 @@ def main():
     step_stage_ms = {nm: ctx0.get("stage_ns_%d" % i) * 1e-6 for i, nm in enumerate(MSM_STAGES)}
     step_msms = ctx0.get("timed_msms")
     ctx0.set("time_accum", 0)
-    # ... and again after minutes of load: a multiplier-saturating kernel runs into the 1 kW power cap once the part is
-    # warm (the pool's bf16 GEMM peak shows the same: MEASURED_PEAKS.json burst vs sustained)
-    imad_wide_sustained, _ = ctx0.measure_imad_peak()
+    imad_wide_sustained, _ = measure_imad_peak(local_rank)   # ... and again after the legs (warm part)
     peak_tops = max(imad_wide_peak, imad_wide_sustained) / 1e12
     imad_wide_peak = peak_tops * 1e12
 
@@ -351,9 +367,13 @@ def main():
         e0.record(streams[0])
         for _ in range(reps):
             part = part_call()
-            if ws > 1:
-                parts = [None] * ws
-                dist.all_gather_object(parts, part)       # 32 bytes per rank, host side
+            if ws > 1:   # 32 bytes per rank, host side (gloo): one small tensor all-gather
+                mine_t = torch.frombuffer(bytearray(part), dtype=torch.uint8)
+                if dist.get_backend() == "nccl":
+                    mine_t = mine_t.to(dev)
+                got = [torch.empty_like(mine_t) for _ in range(ws)]
+                dist.all_gather(got, mine_t)
+                parts = [bytes(g.cpu().numpy().tobytes()) for g in got]
             else:
                 parts = [part]
             total_pt = sharding.point_sum(parts) if rank == 0 else None
@@ -423,9 +443,8 @@ def main():
                      "frac": achieved / peak_tops if achieved else None, "traffic": ACC_TRAFFIC_BYTES,
                      "traffic_note": "dram bytes read+write per launch, ncu --set full of this kernel inside a raw MSM of 2^18 "
                                      "points (profiles/r02_msm_kernels_details.csv); algorithmic gather 4.19 M entries x 96 B = 403 MB",
-                     "peak_source": "measured in this run: bpg_measure_imad_peak (register-only IMAD.WIDE.U32 issue-rate kernel) on the "
-                                    "idle GPU before the legs = the burst figure a kernel timed alone should be held against; "
-                                    "not in MEASURED_PEAKS.json.  tools/imad_peak.cu reads 8.157-8.167 T/s on this pool",
+                     "peak_source": "measured in this run by tools/imad_peak.cu --quick (register-only IMAD.WIDE.U32 issue-rate kernel, "
+                                    "the microbenchmark of round 1) before the legs; not in MEASURED_PEAKS.json",
                      "peak_sustained": imad_wide_sustained / 1e12,
                      "peak_sustained_note": "the same kernel after the legs (warm part, power-capped clocks)",
                      "frac_of_int32_imad_peak": achieved * 1e12 / imad32_peak if achieved else None,

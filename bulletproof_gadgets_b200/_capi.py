@@ -78,7 +78,6 @@ PROTOTYPES = {
     "bpg_ctx_set": (c_int, [c_void_p, c_char_p, c_int64]),
     "bpg_ctx_get": (c_int64, [c_void_p, c_char_p]),
     "bpg_selftest_field": (c_int, [c_void_p, c_uint64, c_uint64, POINTER(c_uint64)]),
-    "bpg_measure_imad_peak": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "bpg_msm_gens_range_dev": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p,
                                        c_char_p]),
     "bpg_gens_ensure": (c_int, [c_void_p, c_uint64]),

@@ -137,12 +137,6 @@ class Context:
         check(lib().bpg_msm_gens_range_dev(self._h, d_sG, g_start, nG, d_sH, h_start, nH, None, None, out))
         return out.raw
 
-    def measure_imad_peak(self):
-        """(IMAD.WIDE.U32 per second, 32-bit IMAD per second) sustained on this GPU (register-only microbenchmark)."""
-        w, n = ctypes.c_double(), ctypes.c_double()
-        check(lib().bpg_measure_imad_peak(self._h, ctypes.byref(w), ctypes.byref(n)))
-        return w.value, n.value
-
     def msm(self, scalars, points):
         """vartime_multiscalar_mul over arbitrary compressed points."""
         bs = b"".join(_sb(s) for s in scalars)

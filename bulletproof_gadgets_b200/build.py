@@ -46,6 +46,7 @@ def _stamp():
     h.update(open(os.path.join(ROOT, "include", "bpg.h"), "rb").read())
     for name in ("prover.cpp", "verifier.cpp"):
         h.update(open(os.path.join(HERE, "cli", name), "rb").read())
+    h.update(open(os.path.join(ROOT, "tools", "imad_peak.cu"), "rb").read())
     h.update(" ".join(x.replace(ROOT, ".") for x in NVCC_FLAGS).encode())
     return h.hexdigest()
 
@@ -103,6 +104,12 @@ def _build_locked(stamp_file, stamp, verbose):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("cli build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    # the issue-rate microbenchmark bench.py takes its roofline denominator from (tools/imad_peak.cu)
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", os.path.join(ROOT, "tools", "imad_peak.cu"),
+           "-o", os.path.join(BINDIR, "imad_peak")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("imad_peak build failed:\n%s\n%s" % (r.stdout, r.stderr))
     open(stamp_file, "w").write(stamp)
     return OUT
 

@@ -106,65 +106,9 @@ __global__ void __launch_bounds__(128) k_selftest_field(uint64_t n, uint64_t see
     if (diff || !fe_is_zero(lhs)) atomicAdd(bad, 1u);
 }
 
-// Sustained issue rate of the integer multiplier: 64 independent multiply-adds per thread and iteration, no memory traffic.
-// MODE 0: 32x32 -> 64-bit multiply-add (IMAD.WIDE.U32, what the field multiplication is made of), MODE 1: 32-bit IMAD.
-template <int MODE>
-__global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed, int iters) {
-    const uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-    uint64_t x0 = threadIdx.x, x1 = a, x2 = b, x3 = a ^ b, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
-    uint32_t y0 = 1, y1 = 2, y2 = 3, y3 = 4, y4 = 5, y5 = 6, y6 = 7, y7 = 8;
-    for (int i = 0; i < iters; i++) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            if (MODE == 0) {
-                x0 = (uint64_t)a * (uint32_t)x0 + x0, x1 = (uint64_t)b * (uint32_t)x1 + x1;
-                x2 = (uint64_t)a * (uint32_t)x2 + x2, x3 = (uint64_t)b * (uint32_t)x3 + x3;
-                x4 = (uint64_t)a * (uint32_t)x4 + x4, x5 = (uint64_t)b * (uint32_t)x5 + x5;
-                x6 = (uint64_t)a * (uint32_t)x6 + x6, x7 = (uint64_t)b * (uint32_t)x7 + x7;
-            } else {
-                y0 = a * y0 + b, y1 = b * y1 + a, y2 = a * y2 + b, y3 = b * y3 + a;
-                y4 = a * y4 + b, y5 = b * y5 + a, y6 = a * y6 + b, y7 = b * y7 + a;
-            }
-        }
-    }
-    const uint64_t s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
-    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32) ^ y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7;
-}
-
 extern "C" {
 
 const char* bpg_last_error(void) { return g_err; }
-
-int bpg_measure_imad_peak(bpg_ctx* ctx, double* imad_wide_per_s, double* imad32_per_s) {
-    if (!ctx || !imad_wide_per_s || !imad32_per_s) return BPG_E_ARG;
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    // 20 000 iterations = ~47 ms per launch at full clocks; the first launches of an idle GPU run while the clocks are still
-    // ramping up (8 000 iterations x 4 launches read 5.84 T/s on a part that sustains 8.16), hence six launches, best of the last four
-    const int blocks = ctx->sm_count * 8, iters = 20000;
-    uint32_t* d = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d, (size_t)blocks * 256 * 4));
-    cudaEvent_t e0 = ctx->ev_stage[0], e1 = ctx->ev_stage[1];
-    double best[2] = {0, 0};
-    cudaError_t err = cudaSuccess;
-    for (int mode = 0; mode < 2 && err == cudaSuccess; mode++)
-        for (int rep = 0; rep < 6 && err == cudaSuccess; rep++) {
-            cudaEventRecord(e0, ctx->stream);
-            if (mode == 0) k_imad_peak<0><<<blocks, 256, 0, ctx->stream>>>(d, rep + 1, iters);
-            else k_imad_peak<1><<<blocks, 256, 0, ctx->stream>>>(d, rep + 1, iters);
-            cudaEventRecord(e1, ctx->stream);
-            err = cudaEventSynchronize(e1);
-            float ms = 0;
-            if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
-            const double rate = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
-            if (rep >= 2 && rate > best[mode]) best[mode] = rate;  // first repetitions = warm-up / clock ramp
-        }
-    ctx->launches += 12;
-    cudaFree(d);
-    CUDA_TRY(err);
-    *imad_wide_per_s = best[0];
-    *imad32_per_s = best[1];
-    return BPG_OK;
-}
 
 int bpg_selftest_field(bpg_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches) {
     if (!ctx || !mismatches) return BPG_E_ARG;

@@ -112,15 +112,25 @@ struct ConstraintStore {
         term_coef.push_back(coef);
     }
     void end() { row_start.push_back((uint32_t)term_var.size()); }
+    // all coefficients are checked BEFORE the first term is pushed: a failing call leaves the store untouched
     int add_lc(const uint32_t* vars, const uint8_t* coef32, size_t n) {
-        for (size_t i = 0; i < n; i++) {
+        if (n && (!vars || !coef32)) return BPG_E_ARG;
+        for (size_t i = 0; i < n; i++)
             if (coef32[32 * i + 31] & 0x80) {
                 bpg_set_error("coefficient %zu has bit 255 set", i);
                 return BPG_E_ARG;
             }
-            term(vars[i], Scalar::from_bytes_mod_order(coef32 + 32 * i).s);
-        }
+        for (size_t i = 0; i < n; i++) term(vars[i], Scalar::from_bytes_mod_order(coef32 + 32 * i).s);
         return BPG_OK;
+    }
+    struct Mark {
+        size_t terms, rows;
+    };
+    Mark mark() const { return {term_var.size(), row_start.size()}; }
+    void rollback(const Mark& m) {
+        term_var.resize(m.terms);
+        term_coef.resize(m.terms);
+        row_start.resize(m.rows);
     }
 };
 
@@ -136,7 +146,7 @@ struct bpg_prover {
     bpg::Transcript* T;
     const bpg_circuit* circ = nullptr;
     bpg_circuit* owned = nullptr;
-    bpg::ProvingScope in_flight;                       // from Prover::new until the proof is out
+    bpg::ProvingScope in_flight;                       // while Prover::prove runs
     ConstraintStore cs;
     std::vector<sc> aL, aR, aO, v, vbl;                // canonical
     std::vector<std::array<uint8_t, 32>> vbl_raw;     // as given (rekeys the transcript rng)
@@ -864,7 +874,8 @@ int bpg_prover_new(bpg_ctx* ctx, bpg_transcript* t, bpg_prover** out) {
     p->ctx = ctx;
     p->T = &t->t;
     p->T->append_message("dom-sep", reinterpret_cast<const uint8_t*>("r1cs v1"), 7);
-    p->in_flight.enter();
+    // (the rng batcher sizes its batches by the provers INSIDE prove(): a prover that is merely alive -- created and kept,
+    // or abandoned -- must not make others wait for a partner that never comes)
     *out = p;
     return BPG_OK;
 }
@@ -926,6 +937,7 @@ int bpg_prover_multiply(bpg_prover* p, const uint32_t* lvars, const uint8_t* lco
     if (!p || !vars_out) return BPG_E_ARG;
     const uint32_t i = (uint32_t)p->aL.size();
     ConstraintStore& cs = p->cs;
+    const ConstraintStore::Mark entry = cs.mark();  // every failure below restores the store to this state
     const size_t mark_v = cs.term_var.size();
     int rc;
     // constraint "left - L_i": terms of left, then (-1) L_i ; same for right
@@ -936,13 +948,14 @@ int bpg_prover_multiply(bpg_prover* p, const uint32_t* lvars, const uint8_t* lco
     cs.term(BPG_VAR_LEFT(i), minus_one);
     cs.end();
     const size_t mark_r = cs.term_var.size();
-    if (ok && (rc = cs.add_lc(rvars, rcoef32, rn))) return rc;
+    if (ok && (rc = cs.add_lc(rvars, rcoef32, rn))) {
+        cs.rollback(entry);
+        return rc;
+    }
     const sc rval = ok ? eval_lc(p, rvars, cs.term_coef.data() + mark_r, rn, &ok) : sc_zero();
     if (!ok) {
         bpg_set_error("multiply: linear combination references an unallocated variable");
-        cs.term_var.resize(mark_v);
-        cs.term_coef.resize(mark_v);
-        cs.row_start.pop_back();
+        cs.rollback(entry);
         return BPG_E_ARG;
     }
     cs.term(BPG_VAR_RIGHT(i), minus_one);
@@ -1081,10 +1094,14 @@ int bpg_verifier_multiply(bpg_verifier* v, const uint32_t* lvars, const uint8_t*
     const uint32_t i = (uint32_t)v->num_vars;
     int rc;
     const sc minus_one = sc_neg(sc_one());
+    const ConstraintStore::Mark entry = v->cs.mark();
     if ((rc = v->cs.add_lc(lvars, lcoef32, ln))) return rc;
     v->cs.term(BPG_VAR_LEFT(i), minus_one);
     v->cs.end();
-    if ((rc = v->cs.add_lc(rvars, rcoef32, rn))) return rc;
+    if ((rc = v->cs.add_lc(rvars, rcoef32, rn))) {
+        v->cs.rollback(entry);  // the left row must not stay behind without its multiplier
+        return rc;
+    }
     v->cs.term(BPG_VAR_RIGHT(i), minus_one);
     v->cs.end();
     v->num_vars++;

@@ -56,11 +56,6 @@ int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key);
  * 0 and 2^32-1; checks the dedicated squaring against the general product and (a+1)^2 - a^2 - 2a - 1 == 0. */
 int bpg_selftest_field(bpg_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
-/* Sustained issue rate of the integer multiplier on this GPU, in instructions (thread level) per second: 32x32->64-bit
- * multiply-add (IMAD.WIDE.U32, the unit of the MSM roofline) and 32-bit IMAD.  A ~50 ms register-only kernel; the
- * denominator bench.py reports `roofline.frac` against (no reference counterpart). */
-int bpg_measure_imad_peak(bpg_ctx* ctx, double* imad_wide_per_s, double* imad32_per_s);
-
 /* BulletproofGens::new(capacity, 1) + PedersenGens::default()
  *   -- /root/reference/src/prove.rs:46,78 ; /root/reference/src/verify.rs:45,70.
  * Derives G_i, H_i (SHAKE256 "GeneratorsChain" stream on the host, Elligator on the GPU) and

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../bulletproof_gadgets_b200/csrc/ge25519.cuh"
 
 template <int MODE>
@@ -70,14 +71,15 @@ __global__ void __launch_bounds__(128) k_chain(ge_ext* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = p;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool quick = argc > 1 && !strcmp(argv[1], "--quick");  // IMAD.WIDE.U32 and IMAD only (bench.py: the roofline denominator)
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     void* out; cudaMalloc(&out, (size_t)sms * 16 * 256 * 128);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const char* names[4] = {"IMAD.WIDE.U32", "IMAD", "IMAD.HI.U32", "DFMA"};
     const int iters = 20000;
-    for (int mode = 0; mode < 4; mode++) {
+    for (int mode = 0; mode < (quick ? 2 : 4); mode++) {
         float best = 1e9;
         for (int rep = 0; rep < 5; rep++) {
             cudaEventRecord(e0);
@@ -92,7 +94,7 @@ int main() {
         printf("{\"op\": \"%s\", \"sms\": %d, \"max_clock_khz\": %d, \"ms\": %.3f, \"Tops\": %.3f, \"per_clk_per_sm_at_max_clock\": %.2f}\n",
                names[mode], sms, clk, best, ops / best / 1e9, ops / (best * 1e-3) / ((double)clk * 1e3) / sms);
     }
-    {
+    if (!quick) {
         const int it2 = 2000; float best = 1e9;
         for (int rep = 0; rep < 5; rep++) {
             cudaEventRecord(e0); k_femul<<<sms * 16, 128>>>((fe*)out, it2); cudaEventRecord(e1); cudaEventSynchronize(e1);
@@ -108,7 +110,7 @@ int main() {
         ops = (double)sms * 16 * 128 * it2;
         printf("{\"op\": \"ge_madd\", \"ms\": %.3f, \"Gops\": %.2f, \"sm_cycles_per_thread_op_at_max_clock\": %.3f}\n", best, ops / best / 1e6, (best * 1e-3) * clk * 1e3 * sms / ops);
     }
-    {
+    if (!quick) {
         const char* ops[3] = {"ge_add", "ge_dbl", "ge_dbl_not"};
         const int geo[4][2] = {{1, 32}, {1, 128}, {148, 128}, {148, 512}};
         const int it3 = 2000;
