@@ -169,6 +169,7 @@ static int ctx_init(bpg_ctx* ctx, int device) {
     if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
     if (const char* e = getenv("BPG_SMEM_SORT")) ctx->use_smem_sort = atoi(e) != 0;
+    if (const char* e = getenv("BPG_IPP_FOLD_N")) ctx->ipp_fold_n = atoi(e);
     return BPG_OK;
 }
 
@@ -210,6 +211,7 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
         (*out)->target_chunks = parent->target_chunks;
         (*out)->cl_min = parent->cl_min;
         (*out)->acc_variant = parent->acc_variant;
+        (*out)->ipp_fold_n = parent->ipp_fold_n;
         (*out)->use_tickets = parent->use_tickets;
         (*out)->use_smem_sort = parent->use_smem_sort;
     }
@@ -270,6 +272,9 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "target_chunks") {
         if (value < 0 || value > (1 << 24)) return BPG_E_ARG;
         ctx->target_chunks = (int)value;
+    } else if (k == "ipp_fold_n") {
+        if (value < -1 || value > 4096 || (value > 0 && (value & (value - 1)))) return BPG_E_ARG;  // -1 auto, 0 never, or 2^k
+        ctx->ipp_fold_n = (int)value;
     } else if (k == "acc_variant") {
         if (value < 0 || value > 2) return BPG_E_ARG;
         ctx->acc_variant = (int)value;

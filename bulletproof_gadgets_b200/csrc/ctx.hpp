@@ -53,6 +53,7 @@ struct DevBuf {
 //   mode 0: set_id
 //   mode 1: set_id + ((i mod period) >= period/2 ? 0 : 1)      (IPP G rule: G_R -> L, G_L -> R)
 //   mode 2: set_id + ((i mod period) <  period/2 ? 0 : 1)      (IPP H rule: H_L -> L, H_R -> R)
+//   mode 3: set_id + (i mod period)                            (IPP generator fold: one output point per residue)
 struct MsmSegment {
     const uint32_t* scalars;
     uint32_t point_base;
@@ -86,6 +87,8 @@ struct GensStore {
     std::mutex mu;
     FixedTable table;
     FixedTable small;  // 8-bit windows over the first `small.capacity` generators: MSMs of a few thousand points
+    FixedTable fold;   // 8-bit windows over ALL generators (built on first use): the IPP generator fold, whose 2 n_r bucket
+                       // sets can only afford 128 buckets each
     ge_ext* gens_ext = nullptr;
     ge_niels* ped = nullptr;
     int window_bits = 0;  // 0 = auto
@@ -128,6 +131,7 @@ struct bpg_ctx {
     // snapshots of the store taken by gens_build() at the start of every operation
     FixedTable table;
     FixedTable small_table;
+    FixedTable fold_table;
     ge_ext* gens_ext = nullptr;  // untabulated generators (extended), same order as the table
     MsmWork work;
     ge_ext* h_result = nullptr;  // pinned
@@ -138,6 +142,8 @@ struct bpg_ctx {
     int task_len = 0;         // entries per k_accumulate thread; 0 = derived on the device: one full wave of equal chunks
     int target_chunks = 0;    // chunks aimed at when task_len == 0 (0 = SMs x resident CTAs x threads), at least cl_min entries each
     int cl_min = 8;
+    int ipp_fold_n = -1;      // IPP: fold the generators once the vectors are this short (0 = never, -1 = automatic: 512 while
+                              // several proofs are in flight, never for a lone proof -- it trades latency for GPU time)
     int acc_variant = 0;      // k_accumulate variant (msm.cu): 0 = 4 CTAs/SM, 1 = next row prefetched, 2 = 5 CTAs/SM
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
     bool sort_attr_set = false;
@@ -190,6 +196,7 @@ void* d2h_stage(bpg_ctx* ctx, size_t offset, const void* d_src, size_t bytes);
 void r1cs_release_work(bpg_ctx* ctx);
 // gens.cu
 int gens_build(bpg_ctx* ctx, uint64_t capacity);  // ensures capacity in the shared store and refreshes ctx snapshots
+int gens_build_fold_table(bpg_ctx* ctx);          // 8-bit-window table over all generators of the current capacity
 void gens_store_release(GensStore* g);
 int gens_compress_range(bpg_ctx* ctx, int which, uint64_t start, uint64_t count, uint8_t* out);
 // host_fe.cpp

@@ -79,6 +79,7 @@ static void snapshot(bpg_ctx* ctx) {
     GensStore* g = ctx->store;
     ctx->table = g->table;
     ctx->small_table = g->small;
+    ctx->fold_table = g->fold;
     ctx->gens_ext = g->gens_ext;
     ctx->ped = g->ped;
 }
@@ -170,6 +171,8 @@ int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     g->small.K = Ks;
     g->small.capacity = sc_cap;
     // other contexts of this GPU may still be reading the superseded tables: keep them until the store dies
+    if (g->fold.rows) g->garbage.push_back(g->fold.rows);
+    g->fold = FixedTable();  // rebuilt on demand for the new capacity
     if (g->table.rows) g->garbage.push_back(g->table.rows);
     if (g->gens_ext) g->garbage.push_back(g->gens_ext);
     if (g->ped) g->garbage.push_back(g->ped);
@@ -184,6 +187,38 @@ int gens_build(bpg_ctx* ctx, uint64_t capacity) {
     return BPG_OK;
 }
 
+// 8-bit windows (32 rows per point) over [G | H | B | B~] in the index space of the big table: 805 MB at capacity 2^17.
+int gens_build_fold_table(bpg_ctx* ctx) {
+    GensStore* g = ctx->store;
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (g->fold.rows && g->fold.capacity == g->table.capacity) {
+        ctx->fold_table = g->fold;  // (only this: the caller keeps the snapshot of the other tables it is working with)
+        return BPG_OK;
+    }
+    if (!g->gens_ext || !g->table.rows) return BPG_E_ARG;
+    const uint32_t n = g->table.n_points;
+    const int c = 8, K = 32;
+    cudaStream_t st = ctx->stream;
+    ge_ext* d_tmp = nullptr;
+    ge_niels* d_rows = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_tmp, (size_t)K * n * sizeof(ge_ext)));
+    CUDA_TRY(cudaMalloc((void**)&d_rows, (size_t)K * n * sizeof(ge_niels)));
+    k_window_multiples<<<(n + 127) / 128, 128, 0, st>>>(g->gens_ext, d_tmp, n, c, K);
+    k_to_niels<<<(uint32_t)(((uint64_t)K * n + 127) / 128), 128, 0, st>>>(d_tmp, d_rows, (uint64_t)K * n);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(ctx_sync(ctx));
+    cudaFree(d_tmp);
+    if (g->fold.rows) g->garbage.push_back(g->fold.rows);
+    g->fold.rows = d_rows;
+    g->fold.n_points = n;
+    g->fold.c = c;
+    g->fold.K = K;
+    g->fold.capacity = g->table.capacity;
+    ctx->fold_table = g->fold;
+    return BPG_OK;
+}
+
 void gens_store_release(GensStore* g) {
     bool last;
     {
@@ -193,6 +228,7 @@ void gens_store_release(GensStore* g) {
     if (!last) return;
     if (g->table.rows) cudaFree(g->table.rows);
     if (g->small.rows) cudaFree(g->small.rows);
+    if (g->fold.rows) cudaFree(g->fold.rows);
     if (g->gens_ext) cudaFree(g->gens_ext);
     if (g->ped) cudaFree(g->ped);
     for (void* p : g->garbage) cudaFree(p);

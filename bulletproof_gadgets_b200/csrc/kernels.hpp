@@ -24,6 +24,7 @@ void sk_lr_poly(cudaStream_t st, const sc* aL, const sc* aR, const sc* aO, const
                 sc* partial, sc* t_out, uint32_t n);
 void sk_eval_lr(cudaStream_t st, const sc* l1, const sc* aO, const sc* sL, const sc* r0, const sc* r1, const sc* r3,
                 const sc* ypow, const sc& x, sc* lvec, sc* rvec, uint32_t n, uint32_t npad);
+void sk_fill_one(cudaStream_t st, sc* p, uint32_t n);
 void sk_ipp_init(cudaStream_t st, sc* sG, sc* sH, const sc* yinv, const sc& u, uint32_t n, uint32_t npad);
 void sk_ipp_round_scalars(cudaStream_t st, const sc* a, const sc* b, const sc* sG, const sc* sH, sc* mG, sc* mH,
                           sc* partial, sc* cw_out, const sc& w, uint32_t npad, uint32_t nk);
@@ -50,5 +51,8 @@ void pk_dyn_msm(cudaStream_t st, const ge_ext* pts, const sc* s, uint32_t n, ge_
 void pk_decompress_niels(cudaStream_t st, const uint8_t* in, ge_niels* rows, uint32_t n, uint32_t* fail);
 // out = sum_w 2^(c w) W[w], w < K
 void pk_window_combine(cudaStream_t st, const ge_ext* W, int K, int c, ge_ext* out);
+// late IPP round over folded generators gp[0 .. 2 nb) (G' then H'): out2[0] = L, out2[1] = R; blockres >= 2 * ceil((2 nb + 2) / 64)
+void pk_dyn_msm_lr(cudaStream_t st, const ge_ext* gp, const ge_ext* Bpt, const sc* mG, const sc* mH, const sc* cw, uint32_t nb,
+                   uint32_t nk, ge_ext* blockres, ge_ext* out2);
 // out = a + b
 void pk_add2(cudaStream_t st, const ge_ext* a, const ge_ext* b, ge_ext* out);

@@ -57,6 +57,7 @@ struct TranscriptRng {
 };
 // Marker of a prover that exists and has not produced its proof yet (from Prover::new to the end of Prove::prove):
 // the batcher sizes its batches and its patience by how many of them this process has in flight.
+int proving_now();  // Prover::prove calls executing in this process right now
 struct ProvingScope {
     bool active = false;
     void enter();

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) k_digits(MsmSegments segs, int c, int K, 
     uint32_t set = sg.set_id;
     if (sg.mode == 1) set += ((i % sg.period) >= (sg.period >> 1)) ? 0u : 1u;
     if (sg.mode == 2) set += ((i % sg.period) < (sg.period >> 1)) ? 0u : 1u;
+    if (sg.mode == 3) set += i % sg.period;
     const uint32_t point = sg.point_base + i;
     const uint32_t row_stride = segs.var_base ? 0u : n_points, set_stride = segs.var_base ? 1u : 0u;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
@@ -225,6 +226,7 @@ __device__ __forceinline__ void decode_scalar(const MsmSegments& segs, uint32_t 
     uint32_t set = sg.set_id;
     if (sg.mode == 1) set += ((i % sg.period) >= (sg.period >> 1)) ? 0u : 1u;
     if (sg.mode == 2) set += ((i % sg.period) < (sg.period >> 1)) ? 0u : 1u;
+    if (sg.mode == 3) set += i % sg.period;
     const uint32_t point = sg.point_base + i;
     const uint32_t row_stride = segs.var_base ? 0u : n_points, set_stride = segs.var_base ? 1u : 0u;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);

@@ -144,6 +144,70 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_final(const ge_ext* __restr
 }
 __global__ void k_add2(const ge_ext* a, const ge_ext* b, ge_ext* out) { *out = ge_add(*a, *b); }
 
+// One late IPP round over FOLDED generators (dynamic points): point i < 2 nb is G'_i (i < nb) or H'_{i-nb}, its scalar
+// mG[i] / mH[i-nb]; it belongs to L or to R by the round's rule (G'_j: j mod nk >= nk/2 -> L; H'_j: j mod nk < nk/2 -> L).
+// Points 2 nb and 2 nb + 1 are B with the scalars cw[0] (-> L) and cw[1] (-> R).  blockres[2][gridDim.x].
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_mul_lr(const ge_ext* __restrict__ gp /* [2 nb] */, const ge_ext* __restrict__ Bpt,
+                                                            const sc* __restrict__ mG, const sc* __restrict__ mH,
+                                                            const sc* __restrict__ cw, uint32_t nb, uint32_t nk,
+                                                            ge_ext* __restrict__ blockres) {
+    __shared__ ge_ext sh[DYN_THREADS];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = 2 * nb + 2;
+    ge_ext acc = ge_identity();
+    bool toL = true;
+    if (i < n) {
+        sc s;
+        ge_ext p;
+        if (i < 2 * nb) {
+            const uint32_t j = (i < nb ? i : i - nb) & (nk - 1), h = nk >> 1;
+            toL = i < nb ? j >= h : j < h;
+            s = i < nb ? mG[i] : mH[i - nb];
+            p = gp[i];
+        } else {
+            toL = i == 2 * nb;
+            s = cw[i - 2 * nb];
+            p = *Bpt;
+        }
+        if (!sc_is_zero(s)) {
+            ge_ext tbl[8];
+            tbl[0] = p;
+#pragma unroll 1
+            for (int k = 1; k < 8; k++) tbl[k] = ge_add(tbl[k - 1], tbl[0]);
+            int8_t d[64];
+            sc_radix16(s, d);
+#pragma unroll 1
+            for (int w = 63; w >= 0; w--) {
+                if (w != 63) {
+                    acc = ge_dbl_not(acc);
+                    acc = ge_dbl_not(acc);
+                    acc = ge_dbl_not(acc);
+                    acc = ge_dbl(acc);
+                }
+                const int dv = d[w];
+                if (dv != 0) {
+                    const int mag = dv < 0 ? -dv : dv;
+                    ge_ext q = tbl[mag - 1];
+                    if (dv < 0) q = ge_neg(q);
+                    acc = ge_add(acc, q);
+                }
+            }
+        }
+    }
+    dyn_block_reduce(sh, toL ? acc : ge_identity(), threadIdx.x);
+    if (threadIdx.x == 0) blockres[blockIdx.x] = sh[0];
+    __syncthreads();
+    dyn_block_reduce(sh, toL ? ge_identity() : acc, threadIdx.x);
+    if (threadIdx.x == 0) blockres[gridDim.x + blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_final_lr(const ge_ext* __restrict__ blockres, uint32_t nblocks,
+                                                              ge_ext* __restrict__ out /* [2] */) {
+    __shared__ ge_ext sh[DYN_THREADS];
+    ge_ext acc = ge_identity();
+    for (uint32_t b = threadIdx.x; b < nblocks; b += DYN_THREADS) acc = ge_add(acc, blockres[(size_t)blockIdx.x * nblocks + b]);
+    dyn_block_reduce(sh, acc, threadIdx.x);
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
 // ------------------------------------------------------------------------------------------
 // variable-base Pippenger (bpg_msm above a few hundred points): table rows straight from the encodings, window combine
 // ------------------------------------------------------------------------------------------
@@ -201,3 +265,9 @@ void pk_dyn_msm(cudaStream_t st, const ge_ext* pts, const sc* s, uint32_t n, ge_
     k_dyn_final<<<1, DYN_THREADS, 0, st>>>(blockres, blocks, out);
 }
 void pk_add2(cudaStream_t st, const ge_ext* a, const ge_ext* b, ge_ext* out) { k_add2<<<1, 1, 0, st>>>(a, b, out); }
+void pk_dyn_msm_lr(cudaStream_t st, const ge_ext* gp, const ge_ext* Bpt, const sc* mG, const sc* mH, const sc* cw, uint32_t nb,
+                   uint32_t nk, ge_ext* blockres, ge_ext* out2) {
+    const uint32_t blocks = (2 * nb + 2 + DYN_THREADS - 1) / DYN_THREADS;
+    k_dyn_mul_lr<<<blocks, DYN_THREADS, 0, st>>>(gp, Bpt, mG, mH, cw, nb, nk, blockres);
+    k_dyn_final_lr<<<2, DYN_THREADS, 0, st>>>(blockres, blocks, out2);
+}

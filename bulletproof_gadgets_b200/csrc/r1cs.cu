@@ -41,6 +41,7 @@ struct ProofWork {
     DevBuf<uint8_t> wide, dyn_enc;
     DevBuf<ge_ext> dyn_pts, dyn_blk;
     DevBuf<ge_niels> dyn_rows;  // variable-base Pippenger: one affine Niels row per caller point
+    DevBuf<ge_ext> fold_pts;    // IPP: folded generators G'_j, H'_j once the vectors are short (prover_prove)
     uint8_t* h_pin = nullptr;  // pinned staging
     size_t h_pin_cap = 0;
     int pin(size_t n) {
@@ -67,6 +68,7 @@ void r1cs_release_work(bpg_ctx* ctx) {
     p->dyn_pts.release();
     p->dyn_blk.release();
     p->dyn_rows.release();
+    p->fold_pts.release();
     if (p->h_pin) cudaFreeHost(p->h_pin);
     delete p;
     ctx->pw = nullptr;
@@ -464,16 +466,45 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     ctx->launches += 2;
     std::vector<uint8_t> LR(64 * (size_t)lg);
     uint32_t nk = npad;
+    // Generator fold: the first rounds run over the ORIGINAL generators (one two-bucket-set fixed-base MSM
+    // each, 2 n' points whatever the round).  Once the vectors are short, the folded generators
+    //     G'_j = sum_{i = j mod nk} sG_i G_i ,  H'_j = sum_{i = j mod nk} sH_i H_i        (2 nk bucket sets, 8-bit windows)
+    // are materialised by ONE MSM, and the remaining rounds are thread-per-point multiplications over those 2 nk points:
+    // about as long in latency, next to nothing in GPU time -- the choice while several proofs share the GPU.
+    int fold_n = ctx->ipp_fold_n;
+    if (fold_n < 0) fold_n = bpg::proving_now() >= 4 ? 512 : 0;
+    bool late = false;
+    uint32_t base_n = npad;  // size of the generator basis the round works on
     for (uint32_t round = 0; round < lg; round++, nk >>= 1) {
+        if (!late && fold_n >= 2 && nk >= 2 && nk <= (uint32_t)fold_n && npad >= 16 * nk) {
+            if ((rc = gens_build_fold_table(ctx))) return rc;
+            if (ctx->fold_table.rows && ctx->fold_table.capacity == cap) {  // (a table of another capacity: keep the slow path)
+                if ((rc = pw->fold_pts.ensure(2 * (size_t)nk + 2)) || (rc = pw->dyn_blk.ensure(2 * ((2 * (size_t)nk + 2) / 64 + 2)))) return rc;
+                memset(&segs, 0, sizeof segs);
+                seg_push(segs, pw->sG.p, 0, npad, 0, 3, nk);
+                seg_push(segs, pw->sH.p, cap, npad, nk, 3, nk);
+                if ((rc = msm_run_table(ctx, ctx->fold_table, segs, 2 * nk, pw->fold_pts.p))) return rc;
+                sk_fill_one(st, pw->sG.p, nk);
+                sk_fill_one(st, pw->sH.p, nk);
+                ctx->launches += 2;
+                late = true;
+                base_n = nk;
+            }
+        }
         sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
-                             small + 20, w.s, npad, nk);
+                             small + 20, w.s, base_n, nk);
         ctx->launches += 3;
-        memset(&segs, 0, sizeof segs);
-        seg_push(segs, pw->mG.p, 0, npad, 0, 1, nk);
-        seg_push(segs, pw->mH.p, cap, npad, 0, 2, nk);
-        seg_push(segs, small + 20, iB, 1, 0, 0, 1);  // c_L * w on B  (Q = w*B)
-        seg_push(segs, small + 21, iB, 1, 1, 0, 1);  // c_R * w on B
-        if ((rc = msm_run(ctx, segs, 2, slots + 4))) return rc;
+        if (!late) {
+            memset(&segs, 0, sizeof segs);
+            seg_push(segs, pw->mG.p, 0, npad, 0, 1, nk);
+            seg_push(segs, pw->mH.p, cap, npad, 0, 2, nk);
+            seg_push(segs, small + 20, iB, 1, 0, 0, 1);  // c_L * w on B  (Q = w*B)
+            seg_push(segs, small + 21, iB, 1, 1, 0, 1);  // c_R * w on B
+            if ((rc = msm_run(ctx, segs, 2, slots + 4))) return rc;
+        } else {
+            pk_dyn_msm_lr(st, pw->fold_pts.p, ctx->gens_ext + iB, pw->mG.p, pw->mH.p, small + 20, base_n, nk, pw->dyn_blk.p, slots + 4);
+            ctx->launches += 2;
+        }
         if ((rc = fetch_points(ctx, slots + 4, 2, hp))) return rc;
         uint8_t* Lc = LR.data() + 64 * (size_t)round;
         host_ristretto_compress(Lc, hp[0]);
@@ -482,7 +513,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         T.append_message("R", Lc + 32, 32);
         const Scalar uk = challenge_scalar(T, "u");
         const Scalar uk_inv = uk.invert();
-        sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, npad, nk);
+        sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, base_n, nk);
         ctx->launches++;
     }
     trace.mark("ipp rounds");

@@ -324,6 +324,13 @@ void sk_eval_lr(cudaStream_t st, const sc* l1, const sc* aO, const sc* sL, const
                 const sc* ypow, const sc& x, sc* lvec, sc* rvec, uint32_t n, uint32_t npad) {
     k_eval_lr<<<nblk(npad), SK_THREADS, 0, st>>>(l1, aO, sL, r0, r1, r3, ypow, x, lvec, rvec, n, npad);
 }
+__global__ void __launch_bounds__(SK_THREADS) k_fill_one(sc* p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_sc(p + i, sc_one());
+}
+void sk_fill_one(cudaStream_t st, sc* p, uint32_t n) {
+    if (n) k_fill_one<<<nblk(n), SK_THREADS, 0, st>>>(p, n);
+}
 void sk_ipp_init(cudaStream_t st, sc* sG, sc* sH, const sc* yinv, const sc& u, uint32_t n, uint32_t npad) {
     k_ipp_init<<<nblk(npad), SK_THREADS, 0, st>>>(sG, sH, yinv, u, n, npad);
 }

@@ -64,6 +64,30 @@ def test_config2_full_size_bytes(eng):
     assert ncons == g["q"] and bpg.verify(ctx, "bench-bound", inst, p2, text, gad) is True
 
 
+@pytest.mark.parametrize("fold_n", [2, 64, 512, 4096])
+def test_ipp_generator_fold_gives_the_same_bytes(eng, fold_n):
+    """The prover may materialise the folded generators once the vectors are `ipp_fold_n` long and finish the inner-product
+    argument over those 2 n_r points (the throughput schedule, chosen automatically while several proofs are in flight).
+    Same group elements, so the same proof bytes: full config-2 statement against the golden hash, small ones against the
+    oracle."""
+    bpg, W, ctx = eng
+    from oracle import coracle
+    ctx.set("ipp_fold_n", fold_n)
+    try:
+        g = GOLD["config2_bound_x1024"]
+        st = W.bounds_check_statement(1024)
+        proof, coms = W.prove_statement(bpg, ctx, st, SEED_P)
+        assert sha(proof) == g["proof_sha256"] and sha(b"".join(coms)) == g["coms_sha256"]
+        for count, nbytes in ((1, 2), (3, 8), (40, 8)):          # n = 32, 384 (-> 512), 5120 (-> 8192)
+            small = W.bounds_check_statement(count, max_bytes=nbytes, label=b"fold-%d" % count)
+            p2, c2 = W.prove_statement(bpg, ctx, small, SEED_P)
+            want, _ = coracle.prove_flat(small, SEED_P)
+            assert p2 == want, (fold_n, count)
+            assert W.verify_statement(bpg, ctx, small, p2, c2) is True
+    finally:
+        ctx.set("ipp_fold_n", -1)
+
+
 @pytest.mark.parametrize("variant", ["instance", "witness"])
 def test_config3_merkle_depth32_bytes(eng, variant):
     """Merkle membership, depth 32, MiMC: siblings as instance values (n = 63 180 -> 2^16) and as witnesses

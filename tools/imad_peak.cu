@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../bulletproof_gadgets_b200/csrc/ge25519.cuh"
 
@@ -73,8 +74,10 @@ __global__ void __launch_bounds__(128) k_chain(ge_ext* out, int iters) {
 
 int main(int argc, char** argv) {
     const bool quick = argc > 1 && !strcmp(argv[1], "--quick");  // IMAD.WIDE.U32 and IMAD only (bench.py: the roofline denominator)
-    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    const int dev = argc > 2 ? atoi(argv[2]) : 0;                // index among the VISIBLE devices (one rank per GPU)
+    if (cudaSetDevice(dev) != cudaSuccess) { printf("cannot select device %d\n", dev); return 1; }
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
     void* out; cudaMalloc(&out, (size_t)sms * 16 * 256 * 128);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const char* names[4] = {"IMAD.WIDE.U32", "IMAD", "IMAD.HI.U32", "DFMA"};
