@@ -476,7 +476,8 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     bool late = false;
     uint32_t base_n = npad;  // size of the generator basis the round works on
     for (uint32_t round = 0; round < lg; round++, nk >>= 1) {
-        if (!late && fold_n >= 2 && nk >= 2 && nk <= (uint32_t)fold_n && npad >= 16 * nk) {
+        // (automatic mode folds large statements only: below 2^16 multipliers a round's MSM is cheaper than a thread-per-point round)
+        if (!late && fold_n >= 2 && nk >= 2 && nk <= (uint32_t)fold_n && npad >= 16 * nk && (ctx->ipp_fold_n > 0 || npad >= (1u << 16))) {
             if ((rc = gens_build_fold_table(ctx))) return rc;
             if (ctx->fold_table.rows && ctx->fold_table.capacity == cap) {  // (a table of another capacity: keep the slow path)
                 if ((rc = pw->fold_pts.ensure(2 * (size_t)nk + 2)) || (rc = pw->dyn_blk.ensure(2 * ((2 * (size_t)nk + 2) / 64 + 2)))) return rc;
