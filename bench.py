@@ -176,7 +176,7 @@ def run_reference(args, ws, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8, help="batches of %d statements" % PROOFS_PER_STEP)
+    ap.add_argument("--steps", type=int, default=16, help="batches of %d statements" % PROOFS_PER_STEP)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--count", type=int, default=1024, help="BOUND statements per proof (1024 = BASELINE config 2)")

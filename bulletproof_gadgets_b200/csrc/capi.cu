@@ -167,6 +167,7 @@ static int ctx_init(bpg_ctx* ctx, int device) {
     CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
     if (const char* e = getenv("BPG_TASK_LEN")) ctx->task_len = atoi(e) > 0 && atoi(e) < (1 << 20) ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char* e = getenv("BPG_ACC_VARIANT")) ctx->acc_variant = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
     if (const char* e = getenv("BPG_SMEM_SORT")) ctx->use_smem_sort = atoi(e) != 0;
     if (const char* e = getenv("BPG_IPP_FOLD_N")) ctx->ipp_fold_n = atoi(e);
@@ -324,6 +325,10 @@ int64_t bpg_ctx_get(bpg_ctx* ctx, const char* key) {
     if (k.rfind("stage_ns_", 0) == 0) {  // stage_ns_0 .. stage_ns_6: see MSM_STAGES (ctx.hpp)
         const int i = atoi(k.c_str() + 9);
         return i >= 0 && i < MSM_STAGES ? (int64_t)(ctx->sum_stage_ms[i] * 1e6) : -1;
+    }
+    if (k.rfind("phase_ns_", 0) == 0) {  // wall time per prove / verify phase (ctx.hpp PH_*)
+        const int i = atoi(k.c_str() + 9);
+        return i >= 0 && i < PH_COUNT ? (int64_t)ctx->phase_wall_ns[i] : -1;
     }
     if (k == "task_len") return ctx->task_len;
     if (k == "last_chunk_len") return (int64_t)ctx->last_chunk_len;

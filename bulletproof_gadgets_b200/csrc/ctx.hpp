@@ -1,6 +1,7 @@
 // Per-GPU context: streams, generator tables, MSM work buffers.  One context per GPU; contexts
 // are independent (thread-per-GPU safe); a single context is not re-entrant.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -166,6 +167,36 @@ struct bpg_ctx {
     bool time_accum = false;
     // host CPU accounting (thread CPU time, ns): inside ctx_sync, and inside the C-ABI calls commit / prove / verify / load
     uint64_t cpu_sync_ns = 0, cpu_commit_ns = 0, cpu_prove_ns = 0, cpu_verify_ns = 0, cpu_load_ns = 0, cpu_rng_ns = 0;
+    // WALL time of the calling thread between the phase boundaries of prove / verify (no added synchronisation: a phase
+    // ends where the driver waits for the stream anyway), summed over the statements of this context; see PHASE_NAMES
+    uint64_t phase_wall_ns[16] = {0};
+};
+// phases of phase_wall_ns (bpg_ctx_get "phase_ns_<i>")
+enum {
+    PH_SETUP = 0, PH_RNG, PH_PHASE1, PH_POLY, PH_TCOMMIT, PH_IPP_EARLY, PH_IPP_FOLD, PH_IPP_LATE, PH_FINAL,
+    PH_V_HEAD, PH_V_SCALARS, PH_V_MSM, PH_COUNT
+};
+// BPG_X_SKIP (measurement only, results are WRONG): bit mask of kernels NOT launched, to read the marginal cost of a stage
+// in the concurrent regime (tools/gpu_timeline.py): 1 bucket reduce, 2 accumulate, 4 sort stage, 8 late IPP rounds'
+// point kernels, 16 IPP scalar kernels
+inline int x_skip() {
+    static const int v = [] { const char* e = getenv("BPG_X_SKIP"); return e ? atoi(e) : 0; }();
+    return v;
+}
+struct PhaseClock {  // lap(i): everything since the previous lap goes to phase i
+    uint64_t* acc;
+    uint64_t last;
+    static uint64_t now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+    }
+    explicit PhaseClock(uint64_t* a) : acc(a), last(now()) {}
+    void lap(int i) {
+        const uint64_t t = now();
+        acc[i] += t - last;
+        last = t;
+    }
 };
 struct CpuTimer {  // adds the calling thread's CPU time between construction and destruction to *acc
     uint64_t* acc;

@@ -1113,7 +1113,9 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
     const uint32_t nbins = G / 256, sort_ctas = (uint32_t)((total + SORT_PTS - 1) / SORT_PTS);
     const bool smem_sort = ctx->use_smem_sort && tb.K <= 16 && nb >= 256 && G <= 65536 && total > 0 &&
                            (uint64_t)nbins * sort_ctas < (1ull << 26);
-    if (smem_sort) {
+    const int xs = x_skip();
+    if (xs & 4) {
+    } else if (smem_sort) {
         const size_t ncnt = (size_t)nbins * sort_ctas;
         if ((rc = w.sort_cnt.ensure(ncnt + 16)) || (rc = w.sort_base.ensure(ncnt + 16)) || (rc = w.sort_val.ensure(max_entries + 1)) || (rc = w.sort_fine.ensure(max_entries + 16)) ||
             (rc = w.sort_small.ensure(1024)))
@@ -1167,7 +1169,8 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
     }
     CUDA_TRY(mark());
     }
-    if (ctx->acc_variant == 2)
+    if (xs & 2) {
+    } else if (ctx->acc_variant == 2)
         k_accumulate<2><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
     else if (ctx->acc_variant == 1)
         k_accumulate<1><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
@@ -1184,7 +1187,7 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
         CUDA_TRY(cudaMemsetAsync(w.reduce_dbg.p, 0, (size_t)br_blocks * 64, st));
         rs.dbg = w.reduce_dbg.p;
     }
-    k_bucket_reduce<<<br_blocks, BR_THREADS, 0, st>>>(w.partials.p, w.bucket_off.p, w.meta.p, bpb, lv, nblk, gsize, rs, d_out);
+    if (!(xs & 1)) k_bucket_reduce<<<br_blocks, BR_THREADS, 0, st>>>(w.partials.p, w.bucket_off.p, w.meta.p, bpb, lv, nblk, gsize, rs, d_out);
     CUDA_TRY(mark());
     CUDA_TRY(mark());
     ctx->launches += 2;

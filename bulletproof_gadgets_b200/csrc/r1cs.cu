@@ -53,6 +53,31 @@ struct ProofWork {
         h_pin_cap = n + n / 8 + 4096;
         return BPG_OK;
     }
+    // Uploads of more than a few KB from pageable caller memory make cudaMemcpyAsync BLOCK until the stream reaches the
+    // copy (measured with 48 statements in flight: 17-43 ms per call, tools/gpu_timeline.py); they go through this
+    // second pinned buffer instead.  A region is written once per prove / verify / commit, and each of those ends with
+    // a wait for the stream, so the next operation of the context finds it free.
+    uint8_t* h_up = nullptr;
+    size_t h_up_cap = 0;
+    const void* stage_up(bpg_ctx* ctx, size_t offset, const void* src, size_t bytes) {
+        if (bytes <= 16384) return src;  // copied inline by the driver
+        if (offset + bytes > h_up_cap) {
+            if (h_up) {
+                if (ctx_sync(ctx) != cudaSuccess) return src;  // copies out of the old buffer may be in flight
+                cudaFreeHost(h_up);
+            }
+            h_up = nullptr;
+            h_up_cap = 0;
+            const size_t want = (offset + bytes) * 2 + 4096;
+            if (cudaMallocHost((void**)&h_up, want) != cudaSuccess) {
+                cudaGetLastError();
+                return src;  // (pageable copy: slower, still correct)
+            }
+            h_up_cap = want;
+        }
+        memcpy(h_up + offset, src, bytes);
+        return h_up + offset;
+    }
 };
 void r1cs_release_work(bpg_ctx* ctx) {
     ProofWork* p = ctx->pw;
@@ -70,6 +95,7 @@ void r1cs_release_work(bpg_ctx* ctx) {
     p->dyn_rows.release();
     p->fold_pts.release();
     if (p->h_pin) cudaFreeHost(p->h_pin);
+    if (p->h_up) cudaFreeHost(p->h_up);
     delete p;
     ctx->pw = nullptr;
 }
@@ -257,8 +283,8 @@ static int pedersen_batch(bpg_ctx* ctx, const sc* v, const sc* r, uint64_t k, ui
     cudaStream_t st = ctx->stream;
     if ((rc = pw->ped_in.ensure(2 * k)) || (rc = pw->dyn_pts.ensure(k)) || (rc = pw->dyn_enc.ensure(32 * k)))
         return rc;
-    CUDA_TRY(cudaMemcpyAsync(pw->ped_in.p, v, 32 * k, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pw->ped_in.p + k, r, 32 * k, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->ped_in.p, pw->stage_up(ctx, 0, v, 32 * k), 32 * k, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->ped_in.p + k, pw->stage_up(ctx, 32 * k, r, 32 * k), 32 * k, cudaMemcpyHostToDevice, st));
     pk_pedersen(st, ctx->ped, pw->ped_in.p, pw->ped_in.p + k, pw->dyn_pts.p, (uint32_t)k);
     ctx->launches++;
     if (k <= 8) {  // latency path: finish the serial inverse-square-root chain on the host
@@ -318,6 +344,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     while ((1u << lg) < npad) lg++;
 
     Trace trace(st);
+    PhaseClock phase(ctx->phase_wall_ns);
     P->in_flight.enter();
     struct Leave {
         bpg::ProvingScope& s;
@@ -350,7 +377,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     ge_ext* slots = ctx->d_points.p;
 
     const sc *d_aL = circ->d_aL, *d_aR = circ->d_aR, *d_aO = circ->d_aO;
-    if (m) CUDA_TRY(cudaMemcpyAsync(pw->vbl.p, P->vbl.data(), 32 * (size_t)m, cudaMemcpyHostToDevice, st));
+    if (m) CUDA_TRY(cudaMemcpyAsync(pw->vbl.p, pw->stage_up(ctx, 0, P->vbl.data(), 32 * (size_t)m), 32 * (size_t)m, cudaMemcpyHostToDevice, st));
 
     // rng order: i, o, s blindings, then s_L[0..n), s_R[0..n)
     const Scalar i_bl = rng_scalar(rng), o_bl = rng_scalar(rng), s_bl = rng_scalar(rng);
@@ -369,6 +396,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     if ((rc = msm_run(ctx, segs, 1, slots + 1))) return rc;  // A_O1
 
     trace.mark("upload+A_I1+A_O1 launched");
+    phase.lap(PH_SETUP);
     // the sequential STROBE stream runs on the host while the two MSMs above execute
     if (n) {
         if ((rc = pw->pin(128 * (size_t)n))) return rc;
@@ -382,6 +410,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         ctx->launches += 2;
     }
     trace.mark("rng s_L,s_R (host keccak)");
+    phase.lap(PH_RNG);
     memset(&segs, 0, sizeof segs);
     seg_push(segs, pw->sL.p, 0, n, 0, 0, 1);
     seg_push(segs, pw->sR.p, cap, n, 0, 0, 1);
@@ -407,6 +436,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     T.append_message("S2", ZERO32, 32);
     const Scalar y = challenge_scalar(T, "y"), z = challenge_scalar(T, "z");
     trace.mark("fetch+compress A,S; y,z");
+    phase.lap(PH_PHASE1);
     const Scalar y_inv = y.invert();
 
     sk_powers(st, pw->ypow.p, pow_table(y), npad, 0);
@@ -428,6 +458,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     const sc* th = static_cast<const sc*>(d2h_stage(ctx, 0, small + 8, 9 * 32));
     if (!th) return BPG_E_CUDA;
     CUDA_TRY(ctx_sync(ctx));
+    phase.lap(PH_POLY);
     const Scalar t1 = Scalar::from_sc(th[0]), t2 = Scalar::from_sc(th[1]), t3 = Scalar::from_sc(th[2]),
                  t4 = Scalar::from_sc(th[3]), t5 = Scalar::from_sc(th[4]), t6 = Scalar::from_sc(th[5]);
     const Scalar tb2 = Scalar::from_sc(th[8]);
@@ -443,6 +474,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     T.append_message("T_5", Tc[3], 32);
     T.append_message("T_6", Tc[4], 32);
     trace.mark("T commitments");
+    phase.lap(PH_TCOMMIT);
     const Scalar u = challenge_scalar(T, "u"), x = challenge_scalar(T, "x");
 
     auto poly6 = [&](const Scalar& c1, const Scalar& c2, const Scalar& c3, const Scalar& c4, const Scalar& c5,
@@ -490,9 +522,10 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
                 ctx->launches += 2;
                 late = true;
                 base_n = nk;
+                phase.lap(PH_IPP_EARLY);
             }
         }
-        sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
+        if (!(x_skip() & 16)) sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
                              small + 20, w.s, base_n, nk);
         ctx->launches += 3;
         if (!late) {
@@ -503,7 +536,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
             seg_push(segs, small + 21, iB, 1, 1, 0, 1);  // c_R * w on B
             if ((rc = msm_run(ctx, segs, 2, slots + 4))) return rc;
         } else {
-            pk_dyn_msm_lr(st, pw->fold_pts.p, ctx->gens_ext + iB, pw->mG.p, pw->mH.p, small + 20, base_n, nk, pw->dyn_blk.p, slots + 4);
+            if (!(x_skip() & 8)) pk_dyn_msm_lr(st, pw->fold_pts.p, ctx->gens_ext + iB, pw->mG.p, pw->mH.p, small + 20, base_n, nk, pw->dyn_blk.p, slots + 4);
             ctx->launches += 2;
         }
         if ((rc = fetch_points(ctx, slots + 4, 2, hp))) return rc;
@@ -514,10 +547,11 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         T.append_message("R", Lc + 32, 32);
         const Scalar uk = challenge_scalar(T, "u");
         const Scalar uk_inv = uk.invert();
-        sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, base_n, nk);
+        if (!(x_skip() & 16)) sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, base_n, nk);
         ctx->launches++;
     }
     trace.mark("ipp rounds");
+    phase.lap(late ? PH_IPP_LATE : PH_IPP_EARLY);
     const sc* ab0 = static_cast<const sc*>(d2h_stage(ctx, 0, pw->lvec.p, 32));
     const sc* ab1 = static_cast<const sc*>(d2h_stage(ctx, 32, pw->rvec.p, 32));
     if (!ab0 || !ab1) return BPG_E_CUDA;
@@ -526,6 +560,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     CUDA_TRY(cudaGetLastError());
 
     trace.mark("final a,b");
+    phase.lap(PH_FINAL);
     // ---- R1CSProof::to_bytes (1-phase) ----
     std::vector<uint8_t>& o = *proof_out;
     o.clear();
@@ -643,6 +678,7 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     while ((1u << lg) < npad) lg++;
 
     Trace trace(st);
+    PhaseClock phase(ctx->phase_wall_ns);
     T.append_u64("m", m);
 #define VALIDATE_APPEND(label, pt)                     \
     do {                                               \
@@ -765,8 +801,9 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
             memcpy(&henc[32 * (11 + m + lg + k)], pr.Rv[k].data(), 32);
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(pw->dyn_s.p, hs.data(), 32 * (size_t)ndyn, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pw->dyn_enc.p, henc.data(), 32 * (size_t)ndyn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->dyn_s.p, pw->stage_up(ctx, 0, hs.data(), 32 * (size_t)ndyn), 32 * (size_t)ndyn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pw->dyn_enc.p, pw->stage_up(ctx, 32 * (size_t)ndyn, henc.data(), 32 * (size_t)ndyn), 32 * (size_t)ndyn,
+                             cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(small + 2, &sBb.s, 32, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(pw->fail.p, 0, 4, st));
     sk_ver_head(st, wV, wc, small + 0, rxx.s, r.s, xx.s, w_tab.s, pr.t_x.s, pw->dyn_s.p + 6, small + 1, m);
@@ -786,10 +823,12 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     pk_add2(st, slots + 8, slots + 9, slots + 10);
     ctx->launches++;
     trace.mark("v: fixed msm");
+    phase.lap(PH_V_HEAD);  // host work + launches of the whole verification
     const uint32_t* failp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, pw->fail.p, 4));
     ge_ext res;
     if (!failp) return BPG_E_CUDA;
     if ((rc = fetch_points(ctx, slots + 10, 1, &res))) return rc;
+    phase.lap(PH_V_MSM);  // the wait for its kernels
     CUDA_TRY(cudaGetLastError());
     if (*failp) return BPG_E_VERIFY;  // a point did not decode
     return host_is_ristretto_identity(res) ? BPG_OK : BPG_E_VERIFY;
