@@ -39,6 +39,11 @@ cudaError_t ctx_sync(bpg_ctx* ctx) {
     const int mode = sync_mode();
     const int w = ++g_waiters;
     int polls = 0;
+    if (mode == 0 && w > 4) {  // many statements in flight: every driver call costs a turn at a lock they all share -- no polling at all
+        e = cudaEventSynchronize(ctx->ev_sync);
+        --g_waiters;
+        return e;
+    }
     for (;;) {
         e = cudaEventQuery(ctx->ev_sync);
         if (e != cudaErrorNotReady) break;
@@ -48,8 +53,9 @@ cudaError_t ctx_sync(bpg_ctx* ctx) {
             if (polls >= 8) sched_yield();
             continue;
         }
-        // under load every driver call contends with the other threads of the process: go to sleep almost at once
-        if (polls >= ((w > 4 || mode == 3) ? 2 : 32) && (mode == 3 || w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
+        // under load every driver call contends with the other threads of the process (a call costs ~3 us of a lock all
+        // threads share, and small statements are bound by exactly that): go to sleep at once
+        if (polls >= ((w > 4 || mode == 3) ? 1 : 32) && (mode == 3 || w > 2 || g_waiters.load(std::memory_order_relaxed) > 2)) {
             e = cudaEventSynchronize(ctx->ev_sync);
             break;
         }
@@ -169,6 +175,7 @@ static int ctx_init(bpg_ctx* ctx, int device) {
     if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_ACC_VARIANT")) ctx->acc_variant = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
+    if (const char* e = getenv("BPG_SMALL_KERNEL")) ctx->use_small_kernel = atoi(e) != 0;
     if (const char* e = getenv("BPG_SMEM_SORT")) ctx->use_smem_sort = atoi(e) != 0;
     if (const char* e = getenv("BPG_IPP_FOLD_N")) ctx->ipp_fold_n = atoi(e);
     return BPG_OK;

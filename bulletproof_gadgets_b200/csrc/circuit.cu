@@ -133,17 +133,44 @@ static void dfree(bpg_ctx* ctx, bool pooled, void* p) {
 void circuit_free(bpg_circuit* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->slab) {  // per-proof circuit: one stream-ordered free (it dies with its prover, before the context)
+        cudaFreeAsync(c->slab, c->ctx->stream);
+        delete c;
+        return;
+    }
     void* ps[] = {c->d_col_start, c->d_col_row, c->d_col_coef, c->d_long, c->d_aL, c->d_aR, c->d_aO};
     for (void* p : ps) {
         if (!p) continue;
-        if (c->pooled) cudaFreeAsync(p, c->ctx->stream);  // per-proof circuits die with their prover, before the context
+        if (c->pooled) cudaFreeAsync(p, c->ctx->stream);
         else cudaFree(p);
     }
     delete c;
 }
 
+// carves 256-byte aligned pieces out of one allocation
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    }
+};
+static int circuit_status(bpg_circuit* c, const uint32_t* flags) {
+    if (flags[0] & 1u) {
+        bpg_set_error("constraint term references an unknown variable (n=%u, m=%u)", c->n, c->m);
+        return BPG_E_ARG;
+    }
+    if (flags[0] & 2u) {
+        bpg_set_error("constraint coefficient with bit 255 set (not a valid Scalar)");
+        return BPG_E_ARG;
+    }
+    c->n_long = flags[1] < c->long_cap ? flags[1] : c->long_cap;
+    return BPG_OK;
+}
+
 int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const uint32_t* row_start, const uint32_t* term_var,
-                  const uint8_t* term_coef32, bool pooled, bpg_circuit** out) {
+                  const uint8_t* term_coef32, bool pooled, bpg_circuit** out, bool defer_check) {
     *out = nullptr;
     if (n64 >= (1u << 29) || m64 >= (1u << 29) || q64 >= (1ull << 31)) {
         bpg_set_error("circuit: n, m or q out of range");
@@ -171,29 +198,54 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
     c->device = ctx->device;
     c->n = n, c->m = m, c->q = q, c->nt = nt, c->nnz = nnz, c->pooled = pooled;
     const uint32_t long_cap = nnz / FLATTEN_LONG + 1;
-    uint32_t *d_row_start = nullptr, *d_term_var = nullptr, *d_cursor = nullptr, *d_scratch = nullptr, *d_flags = nullptr;
-    sc* d_coef = nullptr;
+    c->long_cap = long_cap;
+    // temporaries of the transposition: one pool allocation ([cursor | flags] first: one memset clears both)
+    Carver tc;
+    const size_t o_cursor = tc.take(4 * (size_t)(nt + 1) + 16), o_rows = tc.take(4 * (size_t)(q + 1)), o_tvar = tc.take(4 * (size_t)(nnz + 1)),
+                 o_coef = tc.take(32 * (size_t)(nnz + 1)), o_scratch = tc.take(4 * (size_t)(nt / 2048 + 4));
+    uint8_t* tmp = nullptr;
     int rc = BPG_OK;
     auto fail = [&](int code) {
-        void* tmp[] = {d_row_start, d_term_var, d_cursor, d_scratch, d_flags, d_coef};
-        for (void* p : tmp) dfree(ctx, true, p);
+        if (tmp) cudaFreeAsync(tmp, st);
         circuit_free(c);
         return code;
     };
 #define TRY_RC(x) do { if ((rc = (x))) return fail(rc); } while (0)
 #define TRY_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bpg_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return fail(BPG_E_CUDA); } } while (0)
-    TRY_RC(dalloc(ctx, pooled, (void**)&c->d_col_start, 4 * (size_t)(nt + 1)));
-    TRY_RC(dalloc(ctx, pooled, (void**)&c->d_col_row, 4 * (size_t)(nnz + 1)));
-    TRY_RC(dalloc(ctx, pooled, (void**)&c->d_col_coef, 32 * (size_t)(nnz + 1)));
-    TRY_RC(dalloc(ctx, pooled, (void**)&c->d_long, 4 * (size_t)long_cap));
-    TRY_RC(dalloc(ctx, true, (void**)&d_row_start, 4 * (size_t)(q + 1)));
-    TRY_RC(dalloc(ctx, true, (void**)&d_term_var, 4 * (size_t)(nnz + 1)));
-    TRY_RC(dalloc(ctx, true, (void**)&d_coef, 32 * (size_t)(nnz + 1)));
-    TRY_RC(dalloc(ctx, true, (void**)&d_cursor, 4 * (size_t)(nt + 1)));
-    TRY_RC(dalloc(ctx, true, (void**)&d_scratch, 4 * (size_t)(nt / 2048 + 4)));
-    TRY_RC(dalloc(ctx, true, (void**)&d_flags, 8));
-    TRY_CU(cudaMemsetAsync(d_flags, 0, 8, st));
-    TRY_CU(cudaMemsetAsync(d_cursor, 0, 4 * (size_t)(nt + 1), st));
+    TRY_RC(dalloc(ctx, true, (void**)&tmp, tc.off));
+    uint32_t* d_cursor = reinterpret_cast<uint32_t*>(tmp + o_cursor);
+    uint32_t* d_row_start = reinterpret_cast<uint32_t*>(tmp + o_rows);
+    uint32_t* d_term_var = reinterpret_cast<uint32_t*>(tmp + o_tvar);
+    sc* d_coef = reinterpret_cast<sc*>(tmp + o_coef);
+    uint32_t* d_scratch = reinterpret_cast<uint32_t*>(tmp + o_scratch);
+    uint32_t* d_flags;
+    if (pooled) {  // per-proof circuit: everything that outlives this call in one allocation, the witness arrays included
+        Carver pc;
+        const size_t o_flags = pc.take(16), o_cs = pc.take(4 * (size_t)(nt + 1)), o_cr = pc.take(4 * (size_t)(nnz + 1)),
+                     o_cc = pc.take(32 * (size_t)(nnz + 1)), o_long = pc.take(4 * (size_t)long_cap), o_aL = pc.take(32 * ((size_t)n + 1)),
+                     o_aR = pc.take(32 * ((size_t)n + 1)), o_aO = pc.take(32 * ((size_t)n + 1));
+        uint8_t* slab = nullptr;
+        TRY_RC(dalloc(ctx, true, (void**)&slab, pc.off));
+        c->slab = slab;
+        c->d_flags = reinterpret_cast<uint32_t*>(slab + o_flags);
+        c->d_col_start = reinterpret_cast<uint32_t*>(slab + o_cs);
+        c->d_col_row = reinterpret_cast<uint32_t*>(slab + o_cr);
+        c->d_col_coef = reinterpret_cast<sc*>(slab + o_cc);
+        c->d_long = reinterpret_cast<uint32_t*>(slab + o_long);
+        c->d_aL = reinterpret_cast<sc*>(slab + o_aL);
+        c->d_aR = reinterpret_cast<sc*>(slab + o_aR);
+        c->d_aO = reinterpret_cast<sc*>(slab + o_aO);
+        d_flags = c->d_flags;
+        TRY_CU(cudaMemsetAsync(d_flags, 0, 16, st));
+        TRY_CU(cudaMemsetAsync(d_cursor, 0, 4 * (size_t)(nt + 1), st));
+    } else {
+        TRY_RC(dalloc(ctx, false, (void**)&c->d_col_start, 4 * (size_t)(nt + 1)));
+        TRY_RC(dalloc(ctx, false, (void**)&c->d_col_row, 4 * (size_t)(nnz + 1)));
+        TRY_RC(dalloc(ctx, false, (void**)&c->d_col_coef, 32 * (size_t)(nnz + 1)));
+        TRY_RC(dalloc(ctx, false, (void**)&c->d_long, 4 * (size_t)long_cap));
+        d_flags = d_cursor + (nt + 1);  // the 16 bytes behind the cursor
+        TRY_CU(cudaMemsetAsync(d_cursor, 0, 4 * (size_t)(nt + 1) + 16, st));
+    }
     if (nnz) {
         TRY_CU(cudaMemcpyAsync(d_row_start, row_start, 4 * (size_t)(q + 1), cudaMemcpyHostToDevice, st));
         TRY_CU(cudaMemcpyAsync(d_term_var, term_var, 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
@@ -211,25 +263,42 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
         k_csc_long<<<(nt + 255) / 256, 256, 0, st>>>(c->d_col_start, nt, long_cap, c->d_long, d_flags + 1);
         ctx->launches += 2;
     }
-    const uint32_t* flags = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_flags, 8));
-    if (!flags) return fail(BPG_E_CUDA);
-    TRY_CU(ctx_sync(ctx));
-    TRY_CU(cudaGetLastError());
-    if (flags[0] & 1u) {
-        bpg_set_error("constraint term references an unknown variable (n=%u, m=%u)", n, m);
-        return fail(BPG_E_ARG);
+    if (defer_check && c->slab) {
+        c->check_pending = true;  // the caller's circuit_set_witness* reads the status words back with its own
+    } else {
+        const uint32_t* flags = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_flags, 8));
+        if (!flags) return fail(BPG_E_CUDA);
+        TRY_CU(ctx_sync(ctx));
+        TRY_CU(cudaGetLastError());
+        TRY_RC(circuit_status(c, flags));
     }
-    if (flags[0] & 2u) {
-        bpg_set_error("constraint coefficient with bit 255 set (not a valid Scalar)");
-        return fail(BPG_E_ARG);
-    }
-    c->n_long = flags[1] < long_cap ? flags[1] : long_cap;
-    void* tmp[] = {d_row_start, d_term_var, d_cursor, d_scratch, d_flags, d_coef};
-    for (void* p : tmp) dfree(ctx, true, p);
+    cudaFreeAsync(tmp, st);
     *out = c;
     return BPG_OK;
 #undef TRY_RC
 #undef TRY_CU
+}
+
+// the read-back shared by the two witness loaders: [0..1] circuit_build's status when it was deferred, [2] invalid multiplier
+static int witness_status(bpg_circuit* c, uint32_t* d_err /* 3 words when c->d_flags, else 1 */) {
+    bpg_ctx* ctx = c->ctx;
+    const uint32_t* h = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_err, c->d_flags ? 12 : 4));
+    if (!h) return BPG_E_CUDA;
+    CUDA_TRY(ctx_sync(ctx));  // the host arrays may be released by the caller after this returns
+    CUDA_TRY(cudaGetLastError());
+    if (c->d_flags) {
+        if (c->check_pending) {
+            c->check_pending = false;
+            int rc = circuit_status(c, h);
+            if (rc) return rc;
+        }
+        h += 2;
+    }
+    if (*h) {
+        bpg_set_error("multiplier assignment with bit 255 set (not a valid Scalar)");
+        return BPG_E_ARG;
+    }
+    return BPG_OK;
 }
 
 int circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR32n) {
@@ -243,23 +312,24 @@ int circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR3
             (rc = dalloc(ctx, c->pooled, (void**)&c->d_aO, 32 * (n + 1))))
             return rc;
     }
-    if (n) {
+    if (n || c->check_pending) {
         uint32_t* d_err = nullptr;
-        if ((rc = dalloc(ctx, true, (void**)&d_err, 4))) return rc;
-        CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, st));
-        CUDA_TRY(cudaMemcpyAsync(c->d_aL, aL32n, 32 * n, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->d_aR, aR32n, 32 * n, cudaMemcpyHostToDevice, st));
-        k_witness<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(c->d_aL, c->d_aR, c->d_aO, (uint32_t)n, d_err);
-        ctx->launches++;
-        const uint32_t* errp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_err, 4));
-        if (!errp) return BPG_E_CUDA;
-        CUDA_TRY(ctx_sync(ctx));
-        const uint32_t err = *errp;
-        dfree(ctx, true, d_err);
-        if (err) {
-            bpg_set_error("multiplier assignment with bit 255 set (not a valid Scalar)");
-            return BPG_E_ARG;
+        if (c->d_flags) {
+            d_err = c->d_flags;
+            if (c->has_witness) CUDA_TRY(cudaMemsetAsync(d_err + 2, 0, 4, st));  // (a second assignment of the same circuit)
+        } else {
+            if ((rc = dalloc(ctx, true, (void**)&d_err, 4))) return rc;
+            CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, st));
         }
+        if (n) {
+            CUDA_TRY(cudaMemcpyAsync(c->d_aL, aL32n, 32 * n, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(c->d_aR, aR32n, 32 * n, cudaMemcpyHostToDevice, st));
+            k_witness<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(c->d_aL, c->d_aR, c->d_aO, (uint32_t)n, c->d_flags ? d_err + 2 : d_err);
+            ctx->launches++;
+        }
+        rc = witness_status(c, d_err);
+        if (!c->d_flags) dfree(ctx, true, d_err);
+        if (rc) return rc;
     }
     c->has_witness = true;
     return BPG_OK;
@@ -302,40 +372,39 @@ int circuit_set_witness_bits(bpg_circuit* c, const bpg_bit_run* runs, uint64_t n
             (rc = dalloc(ctx, c->pooled, (void**)&c->d_aO, 32 * (n + 1))))
             return rc;
     }
-    bpg_bit_run* d_runs = nullptr;
-    sc *d_hL = nullptr, *d_hR = nullptr;
-    uint32_t *d_idx = nullptr, *d_err = nullptr;
-    if ((rc = dalloc(ctx, true, (void**)&d_err, 4))) return rc;
-    CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, st));
+    // temporaries: one pool allocation
+    Carver tc;
+    const size_t o_err = tc.take(16), o_runs = tc.take(sizeof(bpg_bit_run) * n_runs), o_hL = tc.take(32 * h), o_hR = tc.take(32 * h),
+                 o_idx = tc.take(4 * h);
+    uint8_t* tmp = nullptr;
+    if ((rc = dalloc(ctx, true, (void**)&tmp, tc.off))) return rc;
+    uint32_t* d_err;
+    if (c->d_flags) {
+        d_err = c->d_flags;
+        if (c->has_witness) CUDA_TRY(cudaMemsetAsync(d_err + 2, 0, 4, st));
+    } else {
+        d_err = reinterpret_cast<uint32_t*>(tmp + o_err);
+        CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, st));
+    }
+    uint32_t* d_bad = c->d_flags ? d_err + 2 : d_err;
     if (n_runs) {
-        if ((rc = dalloc(ctx, true, (void**)&d_runs, sizeof(bpg_bit_run) * n_runs))) return rc;
+        bpg_bit_run* d_runs = reinterpret_cast<bpg_bit_run*>(tmp + o_runs);
         CUDA_TRY(cudaMemcpyAsync(d_runs, runs, sizeof(bpg_bit_run) * n_runs, cudaMemcpyHostToDevice, st));
         k_witness_bits<<<(uint32_t)n_runs, 64, 0, st>>>(d_runs, c->d_aL, c->d_aR, c->d_aO);
         ctx->launches++;
     }
     if (h) {
-        if ((rc = dalloc(ctx, true, (void**)&d_hL, 32 * h)) || (rc = dalloc(ctx, true, (void**)&d_hR, 32 * h)) ||
-            (rc = dalloc(ctx, true, (void**)&d_idx, 4 * h)))
-            return rc;
+        sc *d_hL = reinterpret_cast<sc*>(tmp + o_hL), *d_hR = reinterpret_cast<sc*>(tmp + o_hR);
+        uint32_t* d_idx = reinterpret_cast<uint32_t*>(tmp + o_idx);
         CUDA_TRY(cudaMemcpyAsync(d_hL, aL32h, 32 * h, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_hR, aR32h, 32 * h, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_idx, host_index, 4 * h, cudaMemcpyHostToDevice, st));
-        k_witness_scatter<<<(uint32_t)((h + 255) / 256), 256, 0, st>>>(d_hL, d_hR, d_idx, (uint32_t)h, c->d_aL, c->d_aR, c->d_aO, d_err);
+        k_witness_scatter<<<(uint32_t)((h + 255) / 256), 256, 0, st>>>(d_hL, d_hR, d_idx, (uint32_t)h, c->d_aL, c->d_aR, c->d_aO, d_bad);
         ctx->launches++;
     }
-    const uint32_t* errp = static_cast<const uint32_t*>(d2h_stage(ctx, 0, d_err, 4));
-    if (!errp) return BPG_E_CUDA;
-    CUDA_TRY(ctx_sync(ctx));  // the host arrays may be released by the caller after this returns
-    const uint32_t err = *errp;
-    dfree(ctx, true, d_err);
-    dfree(ctx, true, d_runs);
-    dfree(ctx, true, d_hL);
-    dfree(ctx, true, d_hR);
-    dfree(ctx, true, d_idx);
-    if (err) {
-        bpg_set_error("multiplier assignment with bit 255 set (not a valid Scalar)");
-        return BPG_E_ARG;
-    }
+    rc = witness_status(c, d_err);
+    cudaFreeAsync(tmp, st);
+    if (rc) return rc;
     c->has_witness = true;
     return BPG_OK;
 }

@@ -13,13 +13,20 @@ struct bpg_circuit {
     sc *d_col_coef = nullptr, *d_aL = nullptr, *d_aR = nullptr, *d_aO = nullptr;
     bool has_witness = false;
     bool pooled = false;  // storage comes from the stream-ordered pool (per-proof circuits)
+    // Per-proof circuits: ONE pool allocation holds every array above plus the four status words below (small statements are
+    // bound by the number of driver calls, ~250 per statement before this: tools/gpu_timeline.py TIMELINE_MODE=c4)
+    void* slab = nullptr;
+    uint32_t* d_flags = nullptr;  // [0] invalid variable / coefficient bits, [1] long columns, [2] invalid multiplier; zeroed by circuit_build
+    uint32_t long_cap = 0;
+    bool check_pending = false;   // circuit_build left its status read-back to circuit_set_witness* (one wait instead of two)
 };
 
 // Builds the transposed form ON THE DEVICE from a host CSR term list (row_start[q+1], term_var[nnz],
 // 32-byte little-endian coefficients, < 2^255, reduced mod l by the kernel).  The uploads and kernels
 // are queued on ctx->stream; one 8-byte read-back reports invalid variables / coefficients.
+// defer_check (pooled circuits only): the caller follows up with circuit_set_witness*, which reads the status back.
 int circuit_build(bpg_ctx* ctx, uint64_t n, uint64_t m, uint64_t q, const uint32_t* row_start, const uint32_t* term_var,
-                  const uint8_t* term_coef32, bool pooled, bpg_circuit** out);
+                  const uint8_t* term_coef32, bool pooled, bpg_circuit** out, bool defer_check = false);
 // multiplier assignments: raw 32-byte scalars (< 2^255), reduced on the device; a_O = a_L * a_R
 int circuit_set_witness(bpg_circuit* c, const uint8_t* aL32n, const uint8_t* aR32n);
 // f3: multipliers of range-proof bit runs are generated on the device; the `h` others come as compact host arrays with

@@ -31,13 +31,20 @@ struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;  // elements
     bool fresh = false;  // (re)allocated since the owner last cleared the flag: contents undefined
+    size_t cap_hint = 0;  // capacity before the last reallocation
     int ensure(size_t n) {
         if (n <= cap) return BPG_OK;
         if (p) cudaFree(p);
         p = nullptr;
+        cap_hint = cap;
         cap = 0;
+        // cudaFree / cudaMalloc synchronise the whole device and hold the driver lock for milliseconds while other
+        // statements are in flight (tools/gpu_timeline.py): grow by at least half so that statements of slightly
+        // different sizes settle after a few reallocations instead of one per new maximum
         size_t want = n + n / 8 + 64;
+        if (want < cap_hint + cap_hint / 2) want = cap_hint + cap_hint / 2;
         CUDA_TRY(cudaMalloc((void**)&p, want * sizeof(T)));
+        cap_hint = want;
         cap = want;
         fresh = true;
         return BPG_OK;
@@ -121,6 +128,7 @@ struct MsmWork {
     DevBuf<uint32_t> sort_small;           // arrival counter, bin totals, bin starts
     DevBuf<uint32_t> sort_val;             // row|sign of every entry, grouped by coarse bin
     DevBuf<uint8_t> sort_fine;             // its fine bucket (bucket & 255)
+    DevBuf<uint32_t> small_cnt;     // one-kernel small MSM: arrival counter per bucket set (zero between launches)
     DevBuf<uint32_t> tickets;       // [16][points] rank of each entry inside its bucket (histogram pass -> scatter pass)
 };
 
@@ -148,6 +156,8 @@ struct bpg_ctx {
     int acc_variant = 0;      // k_accumulate variant (msm.cu): 0 = 4 CTAs/SM, 1 = next row prefetched, 2 = 5 CTAs/SM
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
     bool sort_attr_set = false;
+    bool small_attr_set = false;
+    int use_small_kernel = 1;  // MSMs of at most SMALL_KERNEL_MAX_POINTS points on the 8-bit table: ONE launch (msm.cu k_msm_small)
     int use_smem_sort = 1;  // two-level shared-memory counting sort where it applies (msm.cu k_sort_*), else k_digits
     int sm_count = 148;
     // counters for bench.py ("gpu_launches")

@@ -1017,6 +1017,189 @@ __global__ void __launch_bounds__(BR_THREADS)
 // ------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// One-kernel MSM for small statements (at most SMALL_KERNEL_MAX_POINTS points, 8-bit-window table, 128 buckets per set,
+// one or two bucket sets).  A statement of a few hundred multipliers runs ~11 MSMs, and with six launches (+ a memset) each
+// the whole proof is bound by the NUMBER of driver calls, not by the GPU (tools/gpu_timeline.py TIMELINE_MODE=c4: ~250
+// calls per statement at ~3 us of a process-wide lock each).
+//   CTA = a slice of SMK_SLICE scalars: digits -> counting sort of the slice's <= 32 x SMK_SLICE entries by bucket in shared
+//   memory -> thread per bucket adds its rows -> the CTA's own weighted sum  T_cta = sum_b (b + 1) S_b = sum_k U_k,
+//   U_k = sum_{b >= k} S_b  (suffix scan + tree over the 128 positions of a set: 14 dependent additions, no doublings).
+//   The sum is linear in the bucket contents, so the CTAs never exchange buckets: the last CTA to arrive adds the T_cta.
+// (A first version with one CTA per bucket, every CTA decoding every scalar, spent 8.4 M digit steps per MSM of 1026
+// points: 230 us under load.)
+// ------------------------------------------------------------------------------------------
+#define SMALL_KERNEL_MAX_POINTS 2050u
+#define SMK_THREADS 256
+#define SMK_SLICE 32u                    // scalars per CTA
+#define SMK_MAXE (SMK_SLICE * 32u)       // entries per CTA (K <= 32 windows)
+#define SMK_HEAVY 64u                    // entries a bucket's own thread adds alone; the rest is shared by the whole CTA
+#define SMK_MAX_CTAS ((SMALL_KERNEL_MAX_POINTS + SMK_SLICE - 1) / SMK_SLICE)
+#define SMK_SMEM (2 * SMK_THREADS * sizeof(ge_ext) + SMK_MAXE * 4)
+// digits of the slice's scalar `g` (g < segs.total): f(bucket in [0, nsets * nb), row | sign << 31) per non-zero digit
+template <typename F>
+__device__ __forceinline__ void smk_decode(const MsmSegments& segs, uint32_t g, int c, int K, uint32_t nb, uint32_t n_points, F&& f) {
+    uint32_t si = 0, base = 0, end = 0;
+#pragma unroll
+    for (int k = 0; k < MSM_MAX_SEGMENTS; k++) {
+        if (k < (int)segs.nseg) {
+            end += segs.seg[k].count;
+            if (g >= end) {
+                base = end;
+                si = k + 1;
+            }
+        }
+    }
+    const MsmSegment sg = segs.seg[si];
+    const uint32_t i = g - base;
+    uint32_t set = sg.set_id;
+    if (sg.mode == 1) set += ((i % sg.period) >= (sg.period >> 1)) ? 0u : 1u;
+    if (sg.mode == 2) set += ((i % sg.period) < (sg.period >> 1)) ? 0u : 1u;
+    if (sg.mode == 3) set += i % sg.period;
+    const uint4* sp = reinterpret_cast<const uint4*>(sg.scalars) + 2 * (size_t)i;
+    const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    const uint32_t point = sg.point_base + i;
+    const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int w = 0; w < K; w++) {
+        const uint32_t raw = (s[0] & mask) + carry;
+#pragma unroll
+        for (int k = 0; k < 7; k++) s[k] = __funnelshift_r(s[k], s[k + 1], c);
+        s[7] >>= c;
+        const uint32_t neg = raw > half;
+        const uint32_t mag = neg ? ((1u << c) - raw) : raw;
+        carry = neg;
+        if (mag != 0) f(set * nb + (mag - 1), ((uint32_t)w * n_points + point) | (neg << 31));
+        if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7] | carry) == 0) break;  // short scalars (0/1 witness bits)
+    }
+}
+__global__ void __launch_bounds__(SMK_THREADS)
+    k_msm_small(MsmSegments segs, const ge_niels* __restrict__ rows, uint32_t n_points, int c, int K, uint32_t nb, uint32_t nsets,
+                ge_ext* __restrict__ cta_sums /* [nsets][gridDim.x] */, uint32_t* __restrict__ arrive, ge_ext* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smk_raw[];
+    ge_ext* A0 = reinterpret_cast<ge_ext*>(smk_raw);
+    ge_ext* A1 = A0 + SMK_THREADS;
+    uint32_t* ent = reinterpret_cast<uint32_t*>(A1 + SMK_THREADS);
+    __shared__ uint32_t cnt[SMK_THREADS], off[SMK_THREADS + 1], cur[SMK_THREADS], heavy[SMK_MAXE / SMK_HEAVY + 1];
+    __shared__ uint32_t n_heavy, sh_last;
+    const uint32_t tid = threadIdx.x, G = nsets * nb;  // G <= SMK_THREADS
+    const uint32_t g0 = blockIdx.x * SMK_SLICE;
+    const uint32_t g = g0 + tid;
+    const bool has = tid < SMK_SLICE && g < segs.total;
+    cnt[tid] = 0;
+    if (tid == 0) n_heavy = 0;
+    __syncthreads();
+    if (has) smk_decode(segs, g, c, K, nb, n_points, [&](uint32_t gb, uint32_t) { atomicAdd(&cnt[gb], 1u); });
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 256 counts: 8 per lane
+        uint32_t v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = sum;
+            sum += cnt[tid * 8 + k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)tid >= o) incl += up;
+        }
+        const uint32_t excl = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            off[tid * 8 + k] = excl + v[k];
+            cur[tid * 8 + k] = excl + v[k];
+        }
+        if (tid == 31) off[SMK_THREADS] = incl;
+    }
+    __syncthreads();
+    if (has) smk_decode(segs, g, c, K, nb, n_points, [&](uint32_t gb, uint32_t e) { ent[atomicAdd(&cur[gb], 1u)] = e; });
+    __syncthreads();
+    // thread per bucket
+    {
+        ge_ext acc = ge_identity();
+        if (tid < G) {
+            const uint32_t lo = off[tid], n = cnt[tid], own = min(n, SMK_HEAVY);
+#pragma unroll 1
+            for (uint32_t e = 0; e < own; e++) {
+                const uint32_t x = ent[lo + e];
+                acc = ge_madd(acc, load_niels(rows, x & 0x7fffffffu), (x >> 31) != 0);
+            }
+            if (n > SMK_HEAVY) heavy[atomicAdd(&n_heavy, 1u)] = tid;
+        }
+        store_ext(A0 + tid, acc);
+    }
+    __syncthreads();
+    // buckets with more than SMK_HEAVY entries in this slice (structured scalars): the whole CTA adds the remainder
+    const uint32_t nh = n_heavy;
+#pragma unroll 1
+    for (uint32_t hk = 0; hk < nh; hk++) {
+        const uint32_t gb = heavy[hk], lo = off[gb] + SMK_HEAVY, hi_ = off[gb] + cnt[gb];
+        ge_ext acc = ge_identity();
+#pragma unroll 1
+        for (uint32_t e = lo + tid; e < hi_; e += SMK_THREADS) {
+            const uint32_t x = ent[e];
+            acc = ge_madd(acc, load_niels(rows, x & 0x7fffffffu), (x >> 31) != 0);
+        }
+        store_ext(A1 + tid, acc);
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t o = SMK_THREADS / 2; o > 0; o >>= 1) {
+            if (tid < o) pt_add(A1 + tid, A1 + tid, A1 + tid + o);
+            __syncthreads();
+        }
+        if (tid == 0) pt_add(A0 + gb, A0 + gb, A1);
+        __syncthreads();
+    }
+    // per set: suffix sums over the 128 bucket positions (double buffered), then their tree sum
+    const uint32_t p = tid & (nb - 1);
+    ge_ext *src = A0, *dst = A1;
+#pragma unroll 1
+    for (uint32_t o = 1; o < nb; o <<= 1) {
+        if (tid < G) {
+            if (p + o < nb) pt_add(dst + tid, src + tid, src + tid + o);
+            else store_ext(dst + tid, load_ext(src + tid));
+        }
+        __syncthreads();
+        ge_ext* t = src;
+        src = dst;
+        dst = t;
+    }
+#pragma unroll 1
+    for (uint32_t o = nb / 2; o > 0; o >>= 1) {
+        if (tid < G && p < o) pt_add(src + tid, src + tid, src + tid + o);
+        __syncthreads();
+    }
+    if (tid < G && p == 0) store_ext(cta_sums + (size_t)(tid / nb) * gridDim.x + blockIdx.x, load_ext(src + tid));
+    if (gridDim.x == 1) {
+        if (tid < G && p == 0) store_ext(out + tid / nb, load_ext(src + tid));
+        return;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh_last = atomicAdd(arrive, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!sh_last) return;
+    if (tid == 0) *arrive = 0;  // zero between launches
+    __threadfence();
+    // the last CTA adds the CTA sums of every set: positions [set * 128 + k], k < gridDim.x <= SMK_MAX_CTAS <= 128
+    if (tid < G) {
+        if (p < gridDim.x) store_ext(A0 + tid, load_ext_cg(cta_sums + (size_t)(tid / nb) * gridDim.x + p));
+        else store_ext(A0 + tid, ge_identity());
+    }
+    __syncthreads();
+    uint32_t top = 1;
+    while (top < gridDim.x) top <<= 1;
+#pragma unroll 1
+    for (uint32_t o = top / 2; o > 0; o >>= 1) {
+        if (tid < G && p < o && p + o < gridDim.x) pt_add(A0 + tid, A0 + tid, A0 + tid + o);
+        __syncthreads();
+    }
+    if (tid < G && p == 0) store_ext(out + tid / nb, load_ext(A0 + tid));
+}
+
 // Segments address points in the index space of the big table ([G | H | B | B~] with H at `capacity`).  MSMs whose points
 // all lie in the small table's prefix use it instead: 8-bit windows, 128 buckets per set.
 static bool to_small_table(const FixedTable& big, const FixedTable& sm, MsmSegments* segs) {
@@ -1110,6 +1293,33 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
     const bool timed = ctx->time_accum;
     int stage = 0;
     auto mark = [&]() -> cudaError_t { return timed ? cudaEventRecord(ctx->ev_stage[stage++], st) : cudaSuccess; };
+    if (ctx->use_small_kernel && tb.c == 8 && nb == 128 && tb.K <= 32 && !segs.var_base && total > 0 && total <= SMALL_KERNEL_MAX_POINTS &&
+        nsets <= 2 && !x_skip()) {
+        const uint32_t ctas = (uint32_t)((total + SMK_SLICE - 1) / SMK_SLICE);
+        if ((rc = w.small_cnt.ensure(64)) || (rc = w.partials.ensure(2 * (size_t)SMK_MAX_CTAS + 1))) return rc;
+        if (w.small_cnt.fresh) {
+            CUDA_TRY(cudaMemsetAsync(w.small_cnt.p, 0, w.small_cnt.cap * 4, st));
+            w.small_cnt.fresh = false;
+        }
+        if (!ctx->small_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_SMEM));
+            ctx->small_attr_set = true;
+        }
+        for (int k = 0; k < 4; k++) CUDA_TRY(mark());
+        k_msm_small<<<ctas, SMK_THREADS, SMK_SMEM, st>>>(segs, tb.rows, tb.n_points, tb.c, tb.K, nb, nsets, w.partials.p, w.small_cnt.p, d_out);
+        for (int k = 0; k < 3; k++) CUDA_TRY(mark());
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (timed) {
+            CUDA_TRY(ctx_sync(ctx));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_stage[3], ctx->ev_stage[4]));
+            ctx->sum_stage_ms[3] += ms;
+            ctx->sum_stage_ms[MSM_STAGES - 1] += ms;
+            ctx->timed_msms++;
+        }
+        return BPG_OK;
+    }
     const uint32_t nbins = G / 256, sort_ctas = (uint32_t)((total + SORT_PTS - 1) / SORT_PTS);
     const bool smem_sort = ctx->use_smem_sort && tb.K <= 16 && nb >= 256 && G <= 65536 && total > 0 &&
                            (uint64_t)nbins * sort_ctas < (1ull << 26);

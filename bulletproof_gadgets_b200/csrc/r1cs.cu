@@ -49,8 +49,9 @@ struct ProofWork {
         if (h_pin) cudaFreeHost(h_pin);
         h_pin = nullptr;
         h_pin_cap = 0;
-        CUDA_TRY(cudaMallocHost((void**)&h_pin, n + n / 8 + 4096));
-        h_pin_cap = n + n / 8 + 4096;
+        const size_t want = n + n / 2 + 4096;  // (re-pinning costs tens of milliseconds of driver lock: grow generously)
+        CUDA_TRY(cudaMallocHost((void**)&h_pin, want));
+        h_pin_cap = want;
         return BPG_OK;
     }
     // Uploads of more than a few KB from pageable caller memory make cudaMemcpyAsync BLOCK until the stream reaches the
@@ -226,9 +227,9 @@ static CscView csc_view(const bpg_circuit* circ) {
     return v;
 }
 // per-proof circuit of the op-by-op path: uploads the host store and transposes it on the device
-static int circuit_from_store(bpg_ctx* ctx, const ConstraintStore& cs, uint64_t n, uint64_t m, bpg_circuit** out) {
+static int circuit_from_store(bpg_ctx* ctx, const ConstraintStore& cs, uint64_t n, uint64_t m, bpg_circuit** out, bool defer_check = false) {
     return circuit_build(ctx, n, m, cs.num_constraints(), cs.row_start.data(), cs.term_var.data(),
-                         reinterpret_cast<const uint8_t*>(cs.term_coef.data()), true, out);
+                         reinterpret_cast<const uint8_t*>(cs.term_coef.data()), true, out, defer_check);
 }
 struct CircuitGuard {  // frees a per-proof circuit on every exit path
     bpg_circuit* c = nullptr;
@@ -331,7 +332,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     }
     CircuitGuard per_proof;
     if (!circ) {  // op-by-op path: upload + transpose the host store now
-        if ((rc = circuit_from_store(ctx, P->cs, P->aL.size(), P->v.size(), &per_proof.c))) return rc;
+        if ((rc = circuit_from_store(ctx, P->cs, P->aL.size(), P->v.size(), &per_proof.c, true))) return rc;
         if ((rc = circuit_set_witness(per_proof.c, reinterpret_cast<const uint8_t*>(P->aL.data()),
                                       reinterpret_cast<const uint8_t*>(P->aR.data()))))
             return rc;
@@ -507,6 +508,9 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     if (fold_n < 0) fold_n = bpg::proving_now() >= 4 ? 512 : 0;
     bool late = false;
     uint32_t base_n = npad;  // size of the generator basis the round works on
+    // small statements are bound by the number of driver calls: their rounds run one fused scalar kernel (and one MSM kernel)
+    const bool small_ipp = npad <= IPP_SMALL_MAX && ctx->ipp_fold_n <= 0 && !x_skip();
+    Scalar prev_u(1), prev_uinv(1);
     for (uint32_t round = 0; round < lg; round++, nk >>= 1) {
         // (automatic mode folds large statements only: below 2^16 multipliers a round's MSM is cheaper than a thread-per-point round)
         if (!late && fold_n >= 2 && nk >= 2 && nk <= (uint32_t)fold_n && npad >= 16 * nk && (ctx->ipp_fold_n > 0 || npad >= (1u << 16))) {
@@ -525,9 +529,15 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
                 phase.lap(PH_IPP_EARLY);
             }
         }
-        if (!(x_skip() & 16)) sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
+        if (small_ipp) {  // previous round's fold + cross terms + MSM scalars: one launch
+            sk_ipp_round_small(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, small + 20, w.s, prev_u.s, prev_uinv.s,
+                               round > 0, base_n, nk);
+            ctx->launches++;
+        } else {
+            if (!(x_skip() & 16)) sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
                              small + 20, w.s, base_n, nk);
-        ctx->launches += 3;
+            ctx->launches += 3;
+        }
         if (!late) {
             memset(&segs, 0, sizeof segs);
             seg_push(segs, pw->mG.p, 0, npad, 0, 1, nk);
@@ -547,8 +557,17 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         T.append_message("R", Lc + 32, 32);
         const Scalar uk = challenge_scalar(T, "u");
         const Scalar uk_inv = uk.invert();
-        if (!(x_skip() & 16)) sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, base_n, nk);
-        ctx->launches++;
+        if (small_ipp) {  // folded by the next round's kernel (after the last round: below)
+            prev_u = uk;
+            prev_uinv = uk_inv;
+            if (round + 1 == lg) {
+                sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, base_n, nk);
+                ctx->launches++;
+            }
+        } else {
+            if (!(x_skip() & 16)) sk_ipp_fold(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, uk.s, uk_inv.s, base_n, nk);
+            ctx->launches++;
+        }
     }
     trace.mark("ipp rounds");
     phase.lap(late ? PH_IPP_LATE : PH_IPP_EARLY);
@@ -1057,7 +1076,7 @@ int bpg_prover_load_cs(bpg_prover* p, const uint8_t* aL32n, const uint8_t* aR32n
     CUDA_TRY(cudaSetDevice(p->ctx->device));
     // straight from the caller's arrays to HBM: upload, reduce mod l, a_O = a_L*a_R and the transposition all
     // run on the device (no host-side constraint store)
-    int rc = circuit_build(p->ctx, n, p->v.size(), q, row_start, term_var, term_coef32, true, &p->owned);
+    int rc = circuit_build(p->ctx, n, p->v.size(), q, row_start, term_var, term_coef32, true, &p->owned, true);
     if (rc) return rc;
     if ((rc = circuit_set_witness(p->owned, aL32n, aR32n))) {
         circuit_free(p->owned);
@@ -1076,7 +1095,7 @@ int bpg_prover_load_cs_bits(bpg_prover* p, uint64_t n, const bpg_bit_run* runs, 
         return BPG_E_ARG;
     }
     CUDA_TRY(cudaSetDevice(p->ctx->device));
-    int rc = circuit_build(p->ctx, n, p->v.size(), q, row_start, term_var, term_coef32, true, &p->owned);
+    int rc = circuit_build(p->ctx, n, p->v.size(), q, row_start, term_var, term_coef32, true, &p->owned, true);
     if (rc) return rc;
     if ((rc = circuit_set_witness_bits(p->owned, runs, n_runs, aL32h, aR32h, host_index, h))) {
         circuit_free(p->owned);

@@ -238,6 +238,46 @@ __global__ void __launch_bounds__(SK_THREADS) k_ipp_fold(sc* a, sc* b, sc* sG, s
     }
 }
 
+// Small statements (npad <= IPP_SMALL_MAX): the previous round's fold and this round's cross terms and MSM scalars in ONE
+// single-CTA launch instead of four (a small proof is bound by its driver calls).  Same arithmetic, element for element.
+__global__ void __launch_bounds__(SK_THREADS)
+    k_ipp_round_small(sc* a, sc* b, sc* sG, sc* sH, sc* mG, sc* mH, sc* cw_out, sc w, sc u, sc uinv, int do_fold,
+                      uint32_t npad, uint32_t nk) {
+    __shared__ sc sh[SK_THREADS];
+    if (do_fold) {  // k_ipp_fold of the round before (vector length 2 nk then)
+        const uint32_t nkp = nk << 1, hp = nk;
+        for (uint32_t i = threadIdx.x; i < npad; i += SK_THREADS) {
+            const bool hi = (i & (nkp - 1)) >= hp;
+            st_sc(sG + i, sc_mul(ld_sc(sG + i), hi ? u : uinv));
+            st_sc(sH + i, sc_mul(ld_sc(sH + i), hi ? uinv : u));
+        }
+        // in place: element i < hp is read and written by its own thread only, elements >= hp are only read
+        for (uint32_t i = threadIdx.x; i < hp; i += SK_THREADS) {
+            const sc na = sc_add(sc_mul(ld_sc(a + i), u), sc_mul(ld_sc(a + i + hp), uinv));
+            const sc nb_ = sc_add(sc_mul(ld_sc(b + i), uinv), sc_mul(ld_sc(b + i + hp), u));
+            st_sc(a + i, na);
+            st_sc(b + i, nb_);
+        }
+        __syncthreads();  // the block's own global stores are visible to all of its threads below
+    }
+    const uint32_t h = nk >> 1;
+    sc cl = sc_zero(), cr = sc_zero();
+    for (uint32_t j = threadIdx.x; j < h; j += SK_THREADS) {
+        cl = sc_add(cl, sc_mul(ld_sc(a + j), ld_sc(b + j + h)));
+        cr = sc_add(cr, sc_mul(ld_sc(a + j + h), ld_sc(b + j)));
+    }
+    const sc s0 = block_sum(cl, sh);
+    if (threadIdx.x == 0) st_sc(cw_out, sc_mul(s0, w));
+    const sc s1 = block_sum(cr, sh);
+    if (threadIdx.x == 0) st_sc(cw_out + 1, sc_mul(s1, w));
+    for (uint32_t i = threadIdx.x; i < npad; i += SK_THREADS) {
+        const uint32_t j = i & (nk - 1);
+        const uint32_t partner = j >= h ? j - h : j + h;
+        st_sc(mG + i, sc_mul(ld_sc(a + partner), ld_sc(sG + i)));
+        st_sc(mH + i, sc_mul(ld_sc(b + partner), ld_sc(sH + i)));
+    }
+}
+
 // ---------------------------------------------------------------------------- verifier
 // s_i = prod_j (bit_{lg-1-j}(i) ? u_j : u_j^-1);  g_i = uf_i (x yinv^i wR_i - a s_i);
 // h_i = uf_i (yinv^i (x wL_i + wO_i - b s_{npad-1-i}) - 1);  partial[block] = sum yinv^i wR_i wL_i
@@ -341,6 +381,10 @@ void sk_ipp_round_scalars(cudaStream_t st, const sc* a, const sc* b, const sc* s
     k_ipp_cross<<<blocks, SK_THREADS, 0, st>>>(a, b, h, partial);
     k_sum_sc<<<1, SK_THREADS, 0, st>>>(partial, blocks, 2, w, cw_out);
     k_ipp_scalars<<<nblk(npad), SK_THREADS, 0, st>>>(a, b, sG, sH, mG, mH, npad, nk);
+}
+void sk_ipp_round_small(cudaStream_t st, sc* a, sc* b, sc* sG, sc* sH, sc* mG, sc* mH, sc* cw_out, const sc& w, const sc& u,
+                        const sc& uinv, bool do_fold, uint32_t npad, uint32_t nk) {
+    k_ipp_round_small<<<1, SK_THREADS, 0, st>>>(a, b, sG, sH, mG, mH, cw_out, w, u, uinv, do_fold ? 1 : 0, npad, nk);
 }
 void sk_ipp_fold(cudaStream_t st, sc* a, sc* b, sc* sG, sc* sH, const sc& u, const sc& uinv, uint32_t npad,
                  uint32_t nk) {
