@@ -78,6 +78,102 @@ __global__ void __launch_bounds__(256) k_csc_long(const uint32_t* __restrict__ c
     }
 }
 
+// The whole transposition in ONE single-CTA launch for small circuits (at most CSC_SMALL_NT targets): count, exclusive scan,
+// fill and the long-column list, with the counters in shared memory.  Replaces two memsets and six launches -- small
+// statements are bound by the number of driver calls.  Same outputs as the kernels above (the order of the terms inside a
+// column is arbitrary there too).
+#define CSC_SMALL_NT 8191u
+#define CSC_SMALL_THREADS 1024
+__global__ void __launch_bounds__(CSC_SMALL_THREADS)
+    k_csc_small(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ term_var, const sc* __restrict__ coef, uint32_t nnz,
+                uint32_t q, uint32_t n, uint32_t m, uint32_t nt, uint32_t long_cap, uint32_t* __restrict__ col_start,
+                uint32_t* __restrict__ col_row, sc* __restrict__ col_coef, uint32_t* __restrict__ long_targets, uint32_t* __restrict__ flags) {
+    __shared__ uint32_t cnt[CSC_SMALL_NT + 1];
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t sh_err, sh_nlong;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (uint32_t t = tid; t <= nt; t += CSC_SMALL_THREADS) cnt[t] = 0;
+    if (tid == 0) sh_err = 0, sh_nlong = 0;
+    __syncthreads();
+    const uint32_t* cw = reinterpret_cast<const uint32_t*>(coef);
+    for (uint32_t e = tid; e < nnz; e += CSC_SMALL_THREADS) {
+        uint32_t t;
+        if (!csc_target(term_var[e], n, m, &t)) {
+            atomicOr(&sh_err, 1u);
+            continue;
+        }
+        if (cw[8 * (size_t)e + 7] >> 31) atomicOr(&sh_err, 2u);
+        atomicAdd(&cnt[t], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0 .. nt]: 8 consecutive counters per thread, then warps, then the 32 warp totals
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t i = tid * 8 + k;
+        v[k] = sum;
+        sum += i <= nt ? cnt[i] : 0u;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t wt = warp_tot[lane], wi = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((int)lane >= o) wi += up;
+        }
+        warp_tot[lane] = wi - wt;
+    }
+    __syncthreads();
+    const uint32_t base = warp_tot[wid] + incl - sum;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t i = tid * 8 + k;
+        if (i <= nt) {
+            const uint32_t start = base + v[k];
+            const uint32_t len = cnt[i];
+            col_start[i] = start;
+            cnt[i] = start;  // from here on: the cursor of column i
+            if (i < nt && len > FLATTEN_LONG) {
+                const uint32_t at = atomicAdd(&sh_nlong, 1u);
+                if (at < long_cap) long_targets[at] = i;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < nnz; e += CSC_SMALL_THREADS) {
+        uint32_t t;
+        if (!csc_target(term_var[e], n, m, &t)) continue;
+        uint32_t lo = 0, hi = q;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (row_start[mid] <= e) lo = mid; else hi = mid;
+        }
+        const uint32_t pos = atomicAdd(&cnt[t], 1u);
+        col_row[pos] = lo;
+        const uint4* p = reinterpret_cast<const uint4*>(coef + e);
+        const uint4 a = p[0], b = p[1];
+        sc s;
+        s.v[0] = a.x, s.v[1] = a.y, s.v[2] = a.z, s.v[3] = a.w, s.v[4] = b.x, s.v[5] = b.y, s.v[6] = b.z, s.v[7] = b.w;
+        s = sc_reduce(s);
+        uint4* o = reinterpret_cast<uint4*>(col_coef + pos);
+        o[0] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]);
+        o[1] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
+    }
+    if (tid == 0) {
+        flags[0] = sh_err;  // (read after the barrier above)
+        flags[1] = sh_nlong;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_witness(sc* __restrict__ aL, sc* __restrict__ aR, sc* __restrict__ aO, uint32_t n,
                                                  uint32_t* __restrict__ err) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,6 +315,7 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
     sc* d_coef = reinterpret_cast<sc*>(tmp + o_coef);
     uint32_t* d_scratch = reinterpret_cast<uint32_t*>(tmp + o_scratch);
     uint32_t* d_flags;
+    const bool one_launch = nt <= CSC_SMALL_NT && nnz > 0;  // k_csc_small: no cursor / scan scratch to clear
     if (pooled) {  // per-proof circuit: everything that outlives this call in one allocation, the witness arrays included
         Carver pc;
         const size_t o_flags = pc.take(16), o_cs = pc.take(4 * (size_t)(nt + 1)), o_cr = pc.take(4 * (size_t)(nnz + 1)),
@@ -237,7 +334,7 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
         c->d_aO = reinterpret_cast<sc*>(slab + o_aO);
         d_flags = c->d_flags;
         TRY_CU(cudaMemsetAsync(d_flags, 0, 16, st));
-        TRY_CU(cudaMemsetAsync(d_cursor, 0, 4 * (size_t)(nt + 1), st));
+        if (!one_launch) TRY_CU(cudaMemsetAsync(d_cursor, 0, 4 * (size_t)(nt + 1), st));
     } else {
         TRY_RC(dalloc(ctx, false, (void**)&c->d_col_start, 4 * (size_t)(nt + 1)));
         TRY_RC(dalloc(ctx, false, (void**)&c->d_col_row, 4 * (size_t)(nnz + 1)));
@@ -246,6 +343,14 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
         d_flags = d_cursor + (nt + 1);  // the 16 bytes behind the cursor
         TRY_CU(cudaMemsetAsync(d_cursor, 0, 4 * (size_t)(nt + 1) + 16, st));
     }
+    if (one_launch) {
+        TRY_CU(cudaMemcpyAsync(d_row_start, row_start, 4 * (size_t)(q + 1), cudaMemcpyHostToDevice, st));
+        TRY_CU(cudaMemcpyAsync(d_term_var, term_var, 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        TRY_CU(cudaMemcpyAsync(d_coef, term_coef32, 32 * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        k_csc_small<<<1, CSC_SMALL_THREADS, 0, st>>>(d_row_start, d_term_var, d_coef, nnz, q, n, m, nt, long_cap, c->d_col_start,
+                                                     c->d_col_row, c->d_col_coef, c->d_long, d_flags);
+        ctx->launches++;
+    } else {
     if (nnz) {
         TRY_CU(cudaMemcpyAsync(d_row_start, row_start, 4 * (size_t)(q + 1), cudaMemcpyHostToDevice, st));
         TRY_CU(cudaMemcpyAsync(d_term_var, term_var, 4 * (size_t)nnz, cudaMemcpyHostToDevice, st));
@@ -262,6 +367,7 @@ int circuit_build(bpg_ctx* ctx, uint64_t n64, uint64_t m64, uint64_t q64, const 
                                                       d_cursor, c->d_col_row, c->d_col_coef);
         k_csc_long<<<(nt + 255) / 256, 256, 0, st>>>(c->d_col_start, nt, long_cap, c->d_long, d_flags + 1);
         ctx->launches += 2;
+    }
     }
     if (defer_check && c->slab) {
         c->check_pending = true;  // the caller's circuit_set_witness* reads the status words back with its own

@@ -15,6 +15,13 @@ struct VerChallenges {
 };
 
 void sk_powers(cudaStream_t st, sc* out, const PowTable& tbl, uint32_t n, uint32_t start);
+struct PowJobs {  // up to three power vectors in one launch (y^i, y^-i, z^(1+i) of a proof)
+    sc* out[3];
+    PowTable tbl[3];
+    uint32_t n[3], start[3], lgT[3];
+    uint32_t count;
+};
+void sk_powers_multi(cudaStream_t st, PowJobs& jobs);
 #define FLATTEN_LONG 128u  // columns with more terms than this get a whole CTA
 void sk_flatten(cudaStream_t st, const uint32_t* col_start, const uint32_t* col_row, const sc* col_coef,
                 const sc* zpow, sc* out, uint32_t nt, uint32_t neg_from, const uint32_t* long_targets,

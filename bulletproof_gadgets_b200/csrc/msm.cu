@@ -231,6 +231,22 @@ __device__ __forceinline__ void decode_scalar(const MsmSegments& segs, uint32_t 
     const uint32_t row_stride = segs.var_base ? 0u : n_points, set_stride = segs.var_base ? 1u : 0u;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
     uint32_t carry = 0;
+    if (c == 16) {  // the big table's window: digit w is a half word of limb w / 2 -- no shifting of the whole scalar per window
+#pragma unroll
+        for (int w = 0; w < 16; w++) {
+            if (w < K) {
+                const uint32_t raw = ((w & 1) ? (s[w >> 1] >> 16) : (s[w >> 1] & 0xffffu)) + carry;
+                const uint32_t neg = raw > 0x8000u;
+                const uint32_t mag = neg ? (0x10000u - raw) : raw;
+                carry = neg;
+                if (mag != 0) {
+                    gbv[w] = (set + (uint32_t)w * set_stride) * nb + (mag - 1);
+                    entv[w] = ((uint32_t)w * row_stride + point) | (neg << 31);
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int w = 0; w < 16; w++) {
         if (w < K) {

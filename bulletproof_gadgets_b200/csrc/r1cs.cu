@@ -106,9 +106,11 @@ static ProofWork* work(bpg_ctx* ctx) {
 }
 
 // wide (64-byte) draws -> canonical scalars on the device
-__global__ void __launch_bounds__(256) k_wide_reduce(const uint8_t* __restrict__ wide, sc* __restrict__ out, uint32_t n) {
+// wide[0 .. n) -> out0, wide[n .. 2n) -> out1 (s_L and s_R of the prover: one launch)
+__global__ void __launch_bounds__(256) k_wide_reduce(const uint8_t* __restrict__ wide, sc* __restrict__ out0, sc* __restrict__ out1, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= 2 * n) return;
+    sc* out = i < n ? out0 : out1 - n;
     const uint4* p = reinterpret_cast<const uint4*>(wide + 64 * (size_t)i);
     uint4 a = p[0], b = p[1], c = p[2], d = p[3];
     sc lo, hi;
@@ -406,9 +408,8 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
             rng.fill_many64(pw->h_pin, 2 * (size_t)n);  // 2n x fill_bytes(64); batched across proofs in flight
         }
         CUDA_TRY(cudaMemcpyAsync(pw->wide.p, pw->h_pin, 128 * (size_t)n, cudaMemcpyHostToDevice, st));
-        k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p, pw->sL.p, n);
-        k_wide_reduce<<<(n + 255) / 256, 256, 0, st>>>(pw->wide.p + 64 * (size_t)n, pw->sR.p, n);
-        ctx->launches += 2;
+        k_wide_reduce<<<(2 * n + 255) / 256, 256, 0, st>>>(pw->wide.p, pw->sL.p, pw->sR.p, n);
+        ctx->launches++;
     }
     trace.mark("rng s_L,s_R (host keccak)");
     phase.lap(PH_RNG);
@@ -440,9 +441,14 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     phase.lap(PH_PHASE1);
     const Scalar y_inv = y.invert();
 
-    sk_powers(st, pw->ypow.p, pow_table(y), npad, 0);
-    sk_powers(st, pw->yinv.p, pow_table(y_inv), npad, 0);
-    sk_powers(st, pw->zpow.p, pow_table(z), q, 1);
+    {
+        PowJobs pj;
+        pj.count = 3;
+        pj.out[0] = pw->ypow.p, pj.tbl[0] = pow_table(y), pj.n[0] = npad, pj.start[0] = 0;
+        pj.out[1] = pw->yinv.p, pj.tbl[1] = pow_table(y_inv), pj.n[1] = npad, pj.start[1] = 0;
+        pj.out[2] = pw->zpow.p, pj.tbl[2] = pow_table(z), pj.n[2] = q, pj.start[2] = 1;
+        sk_powers_multi(st, pj);
+    }
     sc* wL = pw->w.p;
     sc* wR = wL + n;
     sc* wO = wR + n;
@@ -454,7 +460,7 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
     sk_lr_poly(st, d_aL, d_aR, d_aO, pw->sL.p, pw->sR.p, wL, wR, wO, pw->ypow.p, pw->yinv.p, pw->l1.p,
                pw->r0.p, pw->r1.p, pw->r3.p, pw->partial.p, small + 8, n);
     sk_dot(st, wV, pw->vbl.p, m, small + 16);
-    ctx->launches += 7;
+    ctx->launches += 5;
     trace.mark("powers+flatten+lr_poly");
     const sc* th = static_cast<const sc*>(d2h_stage(ctx, 0, small + 8, 9 * 32));
     if (!th) return BPG_E_CUDA;
@@ -767,8 +773,13 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
         (rc = ctx->d_points.ensure(64)))
         return rc;
     sc* small = pw->small.p;  // [0] delta, [1] sB, [2] sBb
-    sk_powers(st, pw->yinv.p, pow_table(y_inv), npad, 0);
-    sk_powers(st, pw->zpow.p, pow_table(z), q, 1);
+    {
+        PowJobs pj;
+        pj.count = 2;
+        pj.out[0] = pw->yinv.p, pj.tbl[0] = pow_table(y_inv), pj.n[0] = npad, pj.start[0] = 0;
+        pj.out[1] = pw->zpow.p, pj.tbl[1] = pow_table(z), pj.n[1] = q, pj.start[1] = 1;
+        sk_powers_multi(st, pj);
+    }
     sc* wL = pw->w.p;
     sc* wR = wL + n;
     sc* wO = wR + n;
@@ -830,7 +841,7 @@ static int verifier_verify(bpg_verifier* Vf, const uint8_t* proof, size_t proof_
     trace.mark("v: head+decompress");
     ge_ext* slots = ctx->d_points.p;
     pk_dyn_msm(st, pw->dyn_pts.p, pw->dyn_s.p, ndyn, pw->dyn_blk.p, slots + 8);
-    ctx->launches += 10;
+    ctx->launches += 9;
     trace.mark("v: dyn msm");
     MsmSegments segs;
     memset(&segs, 0, sizeof segs);

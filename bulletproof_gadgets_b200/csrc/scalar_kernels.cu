@@ -61,6 +61,28 @@ __global__ void __launch_bounds__(SK_THREADS) k_powers(sc* out, PowTable tbl, ui
     }
 }
 
+__global__ void __launch_bounds__(SK_THREADS) k_powers_multi(const __grid_constant__ PowJobs jobs) {
+    const uint32_t w = blockIdx.y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = jobs.n[w], lgT = jobs.lgT[w], T = 1u << lgT;
+    if (t >= T || t >= n) return;
+    uint32_t e = jobs.start[w] + t;
+    sc acc = sc_one();
+    bool first = true;
+    for (int k = 0; k < 32 && (e >> k); k++) {
+        if ((e >> k) & 1u) {
+            acc = first ? jobs.tbl[w].p[k] : sc_mul(acc, jobs.tbl[w].p[k]);
+            first = false;
+        }
+    }
+    const sc step = jobs.tbl[w].p[lgT];
+    sc* out = jobs.out[w];
+    for (uint32_t i = t; i < n; i += T) {
+        st_sc(out + i, acc);
+        if (i + T < n) acc = sc_mul(acc, step);
+    }
+}
+
 __global__ void __launch_bounds__(SK_THREADS) k_flatten(const uint32_t* __restrict__ col_start,
                                                         const uint32_t* __restrict__ col_row,
                                                         const sc* __restrict__ col_coef, const sc* __restrict__ zpow,
@@ -344,6 +366,19 @@ void sk_powers(cudaStream_t st, sc* out, const PowTable& tbl, uint32_t n, uint32
     if (lgT > 14) lgT = lgT >= 17 ? lgT - 3 : 14;   // ... until there are enough threads: then 8 outputs (or more) each
     const uint32_t T = 1u << lgT;
     k_powers<<<nblk(T < n ? T : n), SK_THREADS, 0, st>>>(out, tbl, n, start, lgT);
+}
+void sk_powers_multi(cudaStream_t st, PowJobs& jobs) {
+    uint32_t blocks = 0;
+    for (uint32_t w = 0; w < jobs.count; w++) {
+        const uint32_t n = jobs.n[w];
+        uint32_t lgT = 0;
+        while ((1u << lgT) < n && lgT < 31) lgT++;
+        if (lgT > 14) lgT = lgT >= 17 ? lgT - 3 : 14;
+        jobs.lgT[w] = lgT;
+        const uint32_t T = 1u << lgT;
+        blocks = max(blocks, nblk(T < n ? T : n));
+    }
+    if (blocks) k_powers_multi<<<dim3(blocks, jobs.count), SK_THREADS, 0, st>>>(jobs);
 }
 void sk_flatten(cudaStream_t st, const uint32_t* col_start, const uint32_t* col_row, const sc* col_coef,
                 const sc* zpow, sc* out, uint32_t nt, uint32_t neg_from, const uint32_t* long_targets,

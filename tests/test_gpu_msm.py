@@ -74,6 +74,24 @@ def test_msm_gens_matches_c_oracle(ctx, n):
     assert ctx.msm_gens_bytes(bits, bits, None, sBb) == coracle.msm_gens(bits, bits, None, sBb)
 
 
+@pytest.mark.parametrize("n", [31, 32, 33, 64, 511, 1024])
+def test_small_msm_kernel_structured_scalars_vs_c_oracle(ctx, n):
+    """k_msm_small (one launch, <= 2050 points): slices of 32 scalars, buckets with more than 64 entries of one slice shared by
+    the whole CTA -- scalars whose 32 byte digits all fall into ONE bucket, -1 (a_R of a range proof), and runs of equal values."""
+    rnd = random.Random(1000 + n)
+    one_bucket = bytes([1] * 31 + [0])                       # digit 1 in windows 0..30
+    minus_one = (L - 1).to_bytes(32, "little")
+    top = (L - 1 - 2**200).to_bytes(32, "little")
+    pick = [one_bucket, minus_one, top, (2**252).to_bytes(32, "little"), bytes(32)]
+    sG = b"".join(one_bucket for _ in range(n))
+    sH = b"".join(minus_one if i % 3 else one_bucket for i in range(n))
+    sBb = rnd.randrange(L).to_bytes(32, "little")
+    assert ctx.msm_gens_bytes(sG, sH, None, sBb) == coracle.msm_gens(sG, sH, None, sBb)
+    sG = b"".join(pick[rnd.randrange(len(pick))] for _ in range(n))
+    sH = b"".join(pick[(i // 7) % len(pick)] for i in range(n - 1))
+    assert ctx.msm_gens_bytes(sG, sH, sBb, None) == coracle.msm_gens(sG, sH, sBb, None)
+
+
 def test_msm_arbitrary_points_vs_oracle(ctx):
     rnd = random.Random(77)
     pts = [ed.from_uniform_bytes(hashlib.shake_256(b"dyn-%d" % i).digest(64)).compress() for i in range(40)]
