@@ -173,6 +173,7 @@ static int ctx_init(bpg_ctx* ctx, int device) {
     CUDA_TRY(cudaMallocHost((void**)&ctx->h_result, 64 * sizeof(ge_ext)));
     if (const char* e = getenv("BPG_TASK_LEN")) ctx->task_len = atoi(e) > 0 && atoi(e) < (1 << 20) ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char* e = getenv("BPG_ACC_SMEM_PAD")) ctx->acc_smem_pad = atoi(e) > 0 && atoi(e) <= 200 * 1024 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_ACC_VARIANT")) ctx->acc_variant = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
     if (const char* e = getenv("BPG_SMALL_KERNEL")) ctx->use_small_kernel = atoi(e) != 0;
@@ -219,6 +220,7 @@ int bpg_ctx_create_shared(bpg_ctx* parent, bpg_ctx** out) {
         (*out)->target_chunks = parent->target_chunks;
         (*out)->cl_min = parent->cl_min;
         (*out)->acc_variant = parent->acc_variant;
+        (*out)->acc_smem_pad = parent->acc_smem_pad;
         (*out)->ipp_fold_n = parent->ipp_fold_n;
         (*out)->use_tickets = parent->use_tickets;
         (*out)->use_smem_sort = parent->use_smem_sort;

@@ -157,6 +157,8 @@ struct bpg_ctx {
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
     bool sort_attr_set = false;
     bool small_attr_set = false;
+    bool acc_attr_set = false;
+    int acc_smem_pad = 0;      // bytes of unused dynamic shared memory per k_accumulate CTA (occupancy cap, see msm.cu)
     int use_small_kernel = 1;  // MSMs of at most SMALL_KERNEL_MAX_POINTS points on the 8-bit table: ONE launch (msm.cu k_msm_small)
     int use_smem_sort = 1;  // two-level shared-memory counting sort where it applies (msm.cu k_sort_*), else k_digits
     int sm_count = 148;

@@ -1400,8 +1400,16 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
         k_accumulate<2><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
     else if (ctx->acc_variant == 1)
         k_accumulate<1><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
-    else
-        k_accumulate<0><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
+    else {
+        // acc_smem_pad > 0: unused dynamic shared memory that caps the resident CTAs per SM (57 KB -> 3), so that the sort
+        // kernels of OTHER statements find registers while this kernel runs (it takes every register of the GPU otherwise)
+        const size_t pad = (size_t)ctx->acc_smem_pad;
+        if (pad > 48 * 1024 && !ctx->acc_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+            ctx->acc_attr_set = true;
+        }
+        k_accumulate<0><<<acc_blocks, ACC_THREADS, pad, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
+    }
     CUDA_TRY(mark());
     ReduceScratch rs;
     rs.cta = w.blockres.p;

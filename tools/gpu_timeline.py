@@ -46,12 +46,17 @@ PHASES = ["setup", "rng", "phase1", "poly", "t_commit", "ipp_early", "ipp_fold",
 run(0, 4 * inflight if C4 else max(inflight, 32))
 torch.cuda.synchronize()
 ph0 = [sum(c.get("phase_ns_%d" % i) for c in ctxs) for i in range(len(PHASES))]
+CPU_KEYS = ("sync", "commit", "prove", "verify", "rng", "load")
+cpu0 = {k: sum(c.get("cpu_%s_ns" % k) for c in ctxs) for k in CPU_KEYS}
+pcpu0 = time.process_time()
 t0 = time.perf_counter()
 acts = [ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if os.environ.get("TIMELINE_DUMP") else [])
 with profile(activities=acts) as prof:
     run(1000, n)
     torch.cuda.synchronize()
 wall = time.perf_counter() - t0
+pcpu = time.process_time() - pcpu0
+cpu = {k: round((sum(c.get("cpu_%s_ns" % k) for c in ctxs) - cpu0[k]) / 1e6 / n, 3) for k in CPU_KEYS}
 ph = {nm: round((sum(c.get("phase_ns_%d" % i) for c in ctxs) - ph0[i]) / 1e6 / n, 2) for i, nm in enumerate(PHASES)}
 kev = [e for e in prof.profiler.kineto_results.events() if e.device_type() == torch.autograd.DeviceType.CUDA]
 raw = [(e.start_ns() / 1e3, (e.start_ns() + e.duration_ns()) / 1e3, re.sub(r"\(.*", "", e.name()).replace("void ", ""),
@@ -98,6 +103,7 @@ top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]
 print(json.dumps({
     "statements": n, "inflight": inflight, "wall_ms": wall * 1e3, "kernel_span_ms": span / 1e3,
     "per_statement_ms": span / 1e3 / n, "union_busy_frac": union / span, "accumulate_running_frac": acc_cov / span,
+    "host_cpu_ms_per_statement": {"process": round(pcpu * 1e3 / n, 3), "inside_library_calls": cpu, "cores": os.cpu_count()},
     "wall_ms_per_statement_by_phase": ph, "phase_sum_ms": round(sum(ph.values()), 1),
     "kernels": len(ev), "sum_kernel_ms_per_statement": sum(v[1] for v in agg.values()) / 1e3 / n,
     "concurrency_time_frac": {str(k): round(v / span, 4) for k, v in sorted(hist.items(), key=lambda kv: str(kv[0]))},
