@@ -26,6 +26,10 @@ data-path collective); value = all ranks' statements / max-over-ranks time.
 import argparse
 import json
 import os
+# 48-96 statements in flight = as many streams: with the default of 8 hardware work queues every stream waits behind the
+# unfinished kernel chains of the streams that share its queue (profiles/r02_summary.md, r02_ab5.jsonl).  Read by the CUDA
+# driver when the process creates its context, so it is set before anything touches CUDA (the library does the same).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
@@ -208,7 +212,8 @@ def main():
     from bulletproof_gadgets_b200 import build, sharding, workloads as W
     build.build_lib()
     warmup = max(args.warmup, 3)
-    inflight = args.inflight or (48 if (os.cpu_count() or 1) // ws >= 12 else 32)
+    cores_per_rank = (os.cpu_count() or 1) // ws
+    inflight = args.inflight or (96 if cores_per_rank >= 16 else 48 if cores_per_rank >= 12 else 32)
     ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
     # roofline denominator, measured in this run BEFORE the load (a kernel timed alone sees these clocks: the "burst" figure):
     # the issue-rate microbenchmark of round 1 (tools/imad_peak.cu, built with the library), rank 0's GPU
@@ -241,7 +246,8 @@ def main():
 
     def run_statement(first, n, use=None):
         sd = seeds(first, n)
-        out = bpg.prove_text_batch(use or ctxs, [(name_txt, inst_txt, wtns_txt, gad_txt)] * n, sd, sd, verify=True)
+        # (the text front end costs ~35 ms of host CPU per side: more than 48 threads only oversubscribe a 16-core host)
+        out = bpg.prove_text_batch(use or ctxs[:48], [(name_txt, inst_txt, wtns_txt, gad_txt)] * n, sd, sd, verify=True)
         if not all(o[0] == 0 and o[3] for o in out):
             raise SystemExit("GPU proof did not verify")
         return out
@@ -359,7 +365,7 @@ def main():
         sd = [(i + 1).to_bytes(32, "little") for i in mine]
 
         def run_c4(first, n, use=None):
-            out = bpg.prove_text_batch(ctxs, jobs[:n], sd[:n], sd[:n], verify=True)
+            out = bpg.prove_text_batch(ctxs[:48], jobs[:n], sd[:n], sd[:n], verify=True)   # small statements: bound by driver calls, not by streams
             if not all(o[0] == 0 and o[3] for o in out):
                 raise SystemExit("config 4: a proof did not verify")
 
@@ -433,7 +439,8 @@ def main():
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
-                   "proofs_per_step": PROOFS_PER_STEP, "inflight": inflight, "dist_backend": (dist_backend if ws > 1 else None),
+                   "proofs_per_step": PROOFS_PER_STEP, "inflight": inflight, "inflight_text_legs": min(inflight, 48),
+                   "hardware_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "dist_backend": (dist_backend if ws > 1 else None),
                    "api": "bpg_r1cs_prove_batch (BPG_JOB_VERIFY): library-owned host threads, one context per statement in flight",
                    "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
                    "rng": "transcript rng seeded per statement; proofs byte-identical to the CPU oracle",
