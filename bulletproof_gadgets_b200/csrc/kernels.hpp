@@ -35,6 +35,9 @@ void sk_fill_one(cudaStream_t st, sc* p, uint32_t n);
 void sk_ipp_init(cudaStream_t st, sc* sG, sc* sH, const sc* yinv, const sc& u, uint32_t n, uint32_t npad);
 void sk_ipp_round_scalars(cudaStream_t st, const sc* a, const sc* b, const sc* sG, const sc* sH, sc* mG, sc* mH,
                           sc* partial, sc* cw_out, const sc& w, uint32_t npad, uint32_t nk);
+// the same three kernels in one launch (the last cross-term CTA to finish adds the block sums); *ticket zero between launches
+void sk_ipp_round_fused(cudaStream_t st, const sc* a, const sc* b, const sc* sG, const sc* sH, sc* mG, sc* mH, sc* partial,
+                        uint32_t* ticket, sc* cw_out, const sc& w, uint32_t npad, uint32_t nk);
 #define IPP_SMALL_MAX 2048u  // statements up to this many (padded) multipliers use the single-launch round kernel
 void sk_ipp_round_small(cudaStream_t st, sc* a, sc* b, sc* sG, sc* sH, sc* mG, sc* mH, sc* cw_out, const sc& w, const sc& u,
                         const sc& uinv, bool do_fold, uint32_t npad, uint32_t nk);

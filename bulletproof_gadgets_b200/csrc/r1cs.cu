@@ -36,7 +36,7 @@ static inline uint32_t var_idx(uint32_t v) { return v & ((1u << 29) - 1); }
 struct ProofWork {
     DevBuf<sc> sL, sR, w, ypow, yinv, zpow, l1, r0, r1, r3, lvec, rvec, sG, sH, mG, mH, partial, small;
     DevBuf<sc> vbl, dyn_s, ped_in;
-    DevBuf<uint32_t> fail, fl_tickets;
+    DevBuf<uint32_t> fail, fl_tickets, ipp_ticket;
     DevBuf<sc> fl_part;
     DevBuf<uint8_t> wide, dyn_enc;
     DevBuf<ge_ext> dyn_pts, dyn_blk;
@@ -88,6 +88,7 @@ void r1cs_release_work(bpg_ctx* ctx) {
     for (auto* b : bs) b->release();
     p->fail.release();
     p->fl_tickets.release();
+    p->ipp_ticket.release();
     p->fl_part.release();
     p->wide.release();
     p->dyn_enc.release();
@@ -374,8 +375,12 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
         (rc = pw->sH.ensure(nn)) || (rc = pw->mG.ensure(nn)) || (rc = pw->mH.ensure(nn)) ||
         (rc = pw->partial.ensure(SK_PARTIAL_SCALARS)) || (rc = pw->small.ensure(64)) ||
         (rc = pw->vbl.ensure(m + 1)) || (rc = pw->wide.ensure(128 * (size_t)n + 64)) ||
-        (rc = ctx->d_points.ensure(64)))
+        (rc = ctx->d_points.ensure(64)) || (rc = pw->ipp_ticket.ensure(4)))
         return rc;
+    if (pw->ipp_ticket.fresh) {  // ticket of the fused IPP round kernel: zero between launches
+        CUDA_TRY(cudaMemsetAsync(pw->ipp_ticket.p, 0, pw->ipp_ticket.cap * 4, st));
+        pw->ipp_ticket.fresh = false;
+    }
     sc* small = pw->small.p;  // [0..2] blindings, [8..13] t1..t6, [16] t2_blinding, [20..21] cw, [24..25] a,b
     ge_ext* slots = ctx->d_points.p;
 
@@ -540,9 +545,9 @@ static int prover_prove(bpg_prover* P, const uint8_t* seed32, std::vector<uint8_
                                round > 0, base_n, nk);
             ctx->launches++;
         } else {
-            if (!(x_skip() & 16)) sk_ipp_round_scalars(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
-                             small + 20, w.s, base_n, nk);
-            ctx->launches += 3;
+            if (!(x_skip() & 16)) sk_ipp_round_fused(st, pw->lvec.p, pw->rvec.p, pw->sG.p, pw->sH.p, pw->mG.p, pw->mH.p, pw->partial.p,
+                                                     pw->ipp_ticket.p, small + 20, w.s, base_n, nk);
+            ctx->launches++;
         }
         if (!late) {
             memset(&segs, 0, sizeof segs);

@@ -260,6 +260,47 @@ __global__ void __launch_bounds__(SK_THREADS) k_ipp_fold(sc* a, sc* b, sc* sG, s
     }
 }
 
+// Cross terms, their sum and the MSM scalars of a round in ONE launch (three before): the first `cb` CTAs also accumulate the
+// cross terms, and the last of them to finish (ticket) adds the block sums and writes c_L w, c_R w.
+__global__ void __launch_bounds__(SK_THREADS)
+    k_ipp_round_big(const sc* a, const sc* b, const sc* sG, const sc* sH, sc* mG, sc* mH, sc* partial, uint32_t* ticket, sc* cw_out, sc w,
+                    uint32_t cb, uint32_t npad, uint32_t nk) {
+    __shared__ sc sh[SK_THREADS];
+    __shared__ bool last;
+    const uint32_t h = nk >> 1, tid = threadIdx.x;
+    const uint32_t i = blockIdx.x * blockDim.x + tid;
+    if (i < npad) {
+        const uint32_t j = i & (nk - 1);
+        const uint32_t partner = j >= h ? j - h : j + h;
+        st_sc(mG + i, sc_mul(ld_sc(a + partner), ld_sc(sG + i)));
+        st_sc(mH + i, sc_mul(ld_sc(b + partner), ld_sc(sH + i)));
+    }
+    if (blockIdx.x >= cb) return;  // (uniform per block)
+    sc cl = sc_zero(), cr = sc_zero();
+    for (uint32_t j = blockIdx.x * blockDim.x + tid; j < h; j += cb * blockDim.x) {
+        cl = sc_add(cl, sc_mul(ld_sc(a + j), ld_sc(b + j + h)));
+        cr = sc_add(cr, sc_mul(ld_sc(a + j + h), ld_sc(b + j)));
+    }
+    const sc s0 = block_sum(cl, sh);
+    const sc s1 = block_sum(cr, sh);
+    if (tid == 0) {
+        st_sc(partial + blockIdx.x * 2, s0);
+        st_sc(partial + blockIdx.x * 2 + 1, s1);
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == cb - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (uint32_t k = 0; k < 2; k++) {
+        sc acc = sc_zero();
+        for (uint32_t q = tid; q < cb; q += SK_THREADS) acc = sc_add(acc, ld_sc(partial + q * 2 + k));
+        const sc t = block_sum(acc, sh);
+        if (tid == 0) st_sc(cw_out + k, sc_mul(t, w));
+    }
+    if (tid == 0) *ticket = 0;  // ready for the next launch
+}
+
 // Small statements (npad <= IPP_SMALL_MAX): the previous round's fold and this round's cross terms and MSM scalars in ONE
 // single-CTA launch instead of four (a small proof is bound by its driver calls).  Same arithmetic, element for element.
 __global__ void __launch_bounds__(SK_THREADS)
@@ -408,6 +449,12 @@ void sk_fill_one(cudaStream_t st, sc* p, uint32_t n) {
 }
 void sk_ipp_init(cudaStream_t st, sc* sG, sc* sH, const sc* yinv, const sc& u, uint32_t n, uint32_t npad) {
     k_ipp_init<<<nblk(npad), SK_THREADS, 0, st>>>(sG, sH, yinv, u, n, npad);
+}
+void sk_ipp_round_fused(cudaStream_t st, const sc* a, const sc* b, const sc* sG, const sc* sH, sc* mG, sc* mH, sc* partial,
+                        uint32_t* ticket, sc* cw_out, const sc& w, uint32_t npad, uint32_t nk) {
+    const uint32_t h = nk >> 1;
+    const uint32_t cb = max(1u, min(nblk(h), (uint32_t)SK_REDUCE_BLOCKS));  // <= nblk(npad): h < npad
+    k_ipp_round_big<<<nblk(npad), SK_THREADS, 0, st>>>(a, b, sG, sH, mG, mH, partial, ticket, cw_out, w, cb, npad, nk);
 }
 void sk_ipp_round_scalars(cudaStream_t st, const sc* a, const sc* b, const sc* sG, const sc* sH, sc* mG, sc* mH,
                           sc* partial, sc* cw_out, const sc& w, uint32_t npad, uint32_t nk) {
