@@ -174,7 +174,7 @@ static int ctx_init(bpg_ctx* ctx, int device) {
     if (const char* e = getenv("BPG_TASK_LEN")) ctx->task_len = atoi(e) > 0 && atoi(e) < (1 << 20) ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TARGET_CHUNKS")) ctx->target_chunks = atoi(e) > 0 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_ACC_SMEM_PAD")) ctx->acc_smem_pad = atoi(e) > 0 && atoi(e) <= 200 * 1024 ? atoi(e) : 0;
-    if (const char* e = getenv("BPG_ACC_VARIANT")) ctx->acc_variant = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
+    if (const char* e = getenv("BPG_ACC_VARIANT")) ctx->acc_variant = atoi(e) >= 0 && atoi(e) <= 3 ? atoi(e) : 0;
     if (const char* e = getenv("BPG_TICKETS")) ctx->use_tickets = atoi(e) != 0;
     if (const char* e = getenv("BPG_SMALL_KERNEL")) ctx->use_small_kernel = atoi(e) != 0;
     if (const char* e = getenv("BPG_SMEM_SORT")) ctx->use_smem_sort = atoi(e) != 0;
@@ -291,7 +291,7 @@ int bpg_ctx_set(bpg_ctx* ctx, const char* key, int64_t value) {
         if (value < -1 || value > 4096 || (value > 0 && (value & (value - 1)))) return BPG_E_ARG;  // -1 auto, 0 never, or 2^k
         ctx->ipp_fold_n = (int)value;
     } else if (k == "acc_variant") {
-        if (value < 0 || value > 2) return BPG_E_ARG;
+        if (value < 0 || value > 3) return BPG_E_ARG;
         ctx->acc_variant = (int)value;
     } else if (k == "cl_min") {
         if (value < 1 || value > 4096) return BPG_E_ARG;

@@ -153,7 +153,7 @@ struct bpg_ctx {
     int cl_min = 8;
     int ipp_fold_n = -1;      // IPP: fold the generators once the vectors are this short (0 = never, -1 = automatic: 512 while
                               // several proofs are in flight, never for a lone proof -- it trades latency for GPU time)
-    int acc_variant = 0;      // k_accumulate variant (msm.cu): 0 = 4 CTAs/SM, 1 = next row prefetched, 2 = 5 CTAs/SM
+    int acc_variant = 0;      // k_accumulate variant (msm.cu): 0 = 4 CTAs/SM, 1 = next row prefetched (registers), 2 = 5 CTAs/SM, 3 = next row by cp.async
     int use_tickets = 1;  // scatter pass without atomics (msm.cu k_digits)
     bool sort_attr_set = false;
     bool small_attr_set = false;

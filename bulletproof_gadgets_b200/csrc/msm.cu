@@ -583,6 +583,26 @@ __device__ __forceinline__ uint32_t bucket_upper(const uint32_t* __restrict__ bu
 // the CTA; k_bucket_reduce derives the same predicates from bucket_off and skips the other slots.
 // VARIANT 0: 4 CTAs per SM (<= 128 registers); 1: the next Niels row in flight during the addition, 3 CTAs per SM;
 // 2: 5 CTAs per SM (<= 96 registers, a few spilled words outside the inner loop)
+// (MEASURED, not the default: 320.7 vs 322.8 us at 2^18 points, 1274 vs 1297 at 2^20 with cp.async.ca -- the kernel is bound by
+// the multiplier pipe, not by the gather; with cp.async.cg, past L1, it LOSES 27 %: the six granules of a row share 128-byte
+// lines with each other and with the neighbouring rows, and L1 serves half of them.)
+// VARIANT 3: the next Niels row travels global -> shared memory with cp.async (LDGSTS: no registers while in flight, so the
+// kernel keeps its 4 CTAs per SM) while the current addition runs; every thread owns two 96-byte slots, laid out granule-major
+// ([buffer][16-byte granule][thread]) so that neither the asynchronous stores nor the LDS.128 reads conflict.
+__device__ __forceinline__ void acc_prefetch_row(uint4* slot /* &pre[buf][0][tid] */, const ge_niels* __restrict__ rows, uint32_t row) {
+    const uint4* g = reinterpret_cast<const uint4*>(rows + row);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(slot + k * ACC_THREADS);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g + k) : "memory");
+    }
+}
+__device__ __forceinline__ fe acc_lds_fe(const uint4* slot, int g0) {
+    const uint4 a = slot[g0 * ACC_THREADS], b = slot[(g0 + 1) * ACC_THREADS];
+    fe r;
+    r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+    return r;
+}
 template <int VARIANT>
 __global__ void __launch_bounds__(ACC_THREADS, VARIANT == 1 ? 3 : VARIANT == 2 ? 5 : 4)
     k_accumulate(const ge_niels* __restrict__ rows, const uint32_t* __restrict__ entries,
@@ -590,6 +610,7 @@ __global__ void __launch_bounds__(ACC_THREADS, VARIANT == 1 ? 3 : VARIANT == 2 ?
                  ge_ext* __restrict__ partials) {
     __shared__ ge_ext sh[ACC_THREADS / 32];
     __shared__ uint32_t sh_b0;
+    __shared__ uint4 pre[VARIANT == 3 ? 2 * 6 * ACC_THREADS : 1];
     const uint32_t E = meta->E, CL = meta->CL;
     const uint64_t blk_e0 = (uint64_t)blockIdx.x * ACC_THREADS * CL;
     if (blk_e0 >= E) return;
@@ -639,6 +660,37 @@ __global__ void __launch_bounds__(ACC_THREADS, VARIANT == 1 ? 3 : VARIANT == 2 ?
                 q = load_niels(rows, ent & 0x7fffffffu);
             }
             acc = ge_madd(acc, cur, neg);
+        }
+    } else if (active && VARIANT == 3) {
+        uint32_t ent = __ldg(entries + e0);
+        acc_prefetch_row(pre + threadIdx.x, rows, ent & 0x7fffffffu);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        uint32_t buf = 0;
+#pragma unroll 1
+        for (uint32_t e = e0; e < e1; e++) {
+            if (e == next) {
+                store_ext(partials + t + b, acc);
+                acc = ge_identity();
+                b++;
+                next = bucket_off[b + 1];
+                if (next == e) {
+                    const uint32_t j = bucket_upper(bucket_off, b + 1, G, e);
+                    b = j - 1;
+                    next = bucket_off[j];
+                }
+            }
+            const bool neg = ent >> 31;
+            if (e + 1 < e1) {
+                ent = __ldg(entries + e + 1);
+                acc_prefetch_row(pre + (buf ^ 1) * 6 * ACC_THREADS + threadIdx.x, rows, ent & 0x7fffffffu);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // the row of entry e has landed (the next one may still fly)
+            const uint4* slot = pre + buf * 6 * ACC_THREADS + threadIdx.x;
+            const int oa = neg ? 0 : 2;
+            const fe qa = acc_lds_fe(slot, oa), qb = acc_lds_fe(slot, 2 - oa), t2d = acc_lds_fe(slot, 4);
+            acc = ge_madd_swapped(acc, qa, qb, t2d, neg);
+            buf ^= 1;
         }
     } else if (active) {
         uint32_t ent = __ldg(entries + e0);
@@ -1400,6 +1452,8 @@ int msm_run_table(bpg_ctx* ctx, const FixedTable& tb, const MsmSegments& segs, u
         k_accumulate<2><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
     else if (ctx->acc_variant == 1)
         k_accumulate<1><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
+    else if (ctx->acc_variant == 3)
+        k_accumulate<3><<<acc_blocks, ACC_THREADS, 0, st>>>(tb.rows, w.entries.p, w.bucket_off.p, w.meta.p, G, w.partials.p);
     else {
         // acc_smem_pad > 0: unused dynamic shared memory that caps the resident CTAs per SM (57 KB -> 3), so that the sort
         // kernels of OTHER statements find registers while this kernel runs (it takes every register of the GPU otherwise)
