@@ -216,7 +216,7 @@ def main():
     # (one rank of an 8-GPU box emulated with `taskset -c 0-3`: 16 / 32 / 48 / 64 in flight = 81 / 113 / 131 / 128 per second,
     # profiles/r02_ab7.jsonl -- 48 even where a rank has four cores)
     # and with `taskset -c 0-11` (a rank of the 2-GPU box): 48 / 64 / 96 in flight = 124 / 132 / 137 per second (r02_ab8.jsonl)
-    inflight = args.inflight or (96 if cores_per_rank >= 12 else 48)
+    inflight = args.inflight or (96 if cores_per_rank >= 12 else 64 if cores_per_rank >= 6 else 48)
     ctx0 = bpg.Context(local_rank)  # raises loudly without an sm_100a device: there is no CPU path
     # roofline denominator, measured in this run BEFORE the load (a kernel timed alone sees these clocks: the "burst" figure):
     # the issue-rate microbenchmark of round 1 (tools/imad_peak.cu, built with the library), rank 0's GPU
