@@ -267,10 +267,10 @@ struct LC {
 // A recorded operation.  Its linear combinations live in the owning buffer's term arena (offset, length) and the
 // assignment of an allocate_multiplier in the buffer's `vals`, so an Op is 24 bytes and recording one is two appends.
 struct Op {
-    enum Kind : uint8_t { MUL, ALLOC, CON, COMMIT } kind;
-    bool has = false;          // ALLOC: assignment present
-    uint32_t a_off = 0, a_len = 0, b_off = 0, b_len = 0;  // MUL: left, right ; CON: a
-    uint32_t val = 0;          // ALLOC: vals[val], vals[val + 1] = left, right
+    enum Kind : uint8_t { MUL, ALLOC, CON, COMMIT, RANGE } kind;
+    bool has = false;          // ALLOC / RANGE: assignment present
+    uint32_t a_off = 0, a_len = 0, b_off = 0, b_len = 0;  // MUL: left, right ; CON: a ; RANGE: x's terms, b_len = bits
+    uint32_t val = 0;          // ALLOC: vals[val], vals[val + 1] = left, right ; RANGE: vals[val] = the value
 };
 struct Vars3 {
     Var l, r, o;
@@ -284,6 +284,10 @@ struct Buffer {
     std::vector<Term> arena;  // shared by `ops` and every rewound clause in `cache`
     std::vector<S> vals;
     uint32_t n_mult = 0;
+    // Top-level buffer only: a whole range proof (utils.rs:5-35: n allocate_multiplier + 2 n + 1 constraints) is recorded as
+    // ONE operation and expanded by Flat::replay straight into the flat arrays -- 2^17 multipliers were ~45 MB of recorded
+    // operations before.  Clause buffers of an OR block keep the expanded form (or_combine works on single constraints).
+    bool compact = false;
     explicit Buffer(bool p) : proving(p) {}
     LCView a_of(const Op& o) const { return {arena.data() + o.a_off, o.a_len}; }
     LCView b_of(const Op& o) const { return {arena.data() + o.b_off, o.b_len}; }
@@ -332,10 +336,25 @@ struct Buffer {
         o.kind = Op::COMMIT;
         ops.push_back(o);
     }
+    void range(const LCView& x, unsigned n, bool has, const S& x_assignment) {  // compact buffers only
+        if (proving && !has && n) throw Panic("MissingAssignment");
+        Op o;
+        o.kind = Op::RANGE;
+        o.has = proving;
+        o.a_off = stash(x);
+        o.a_len = x.n;
+        o.b_len = n;
+        o.val = (uint32_t)vals.size();
+        if (proving) vals.push_back(x_assignment);
+        ops.push_back(o);
+        n_mult += n;
+    }
     void initialize_from(const std::vector<const std::vector<Op>*>& init) {
         for (auto* v : init)
-            for (auto& o : *v)
+            for (auto& o : *v) {
                 if (o.kind == Op::MUL || o.kind == Op::ALLOC) n_mult++;
+                else if (o.kind == Op::RANGE) n_mult += o.b_len;
+            }
     }
     void rewind() {
         cache.push_back(std::move(ops));
@@ -351,22 +370,27 @@ struct Derived {
 };
 
 // ---------------------------------------------------------------------------------------- gadgets
+const std::vector<S>& neg_pow2() {  // -(1 * 2^i) along the reference's doubling chain exp2 = exp2 + exp2
+    static const std::vector<S> t = [] {
+        std::vector<S> v;
+        S exp2 = s_one();
+        for (int i = 0; i < 256; i++) {
+            v.push_back(s_neg(s_mul(s_one(), exp2)));
+            exp2 = s_add(exp2, exp2);
+        }
+        return v;
+    }();
+    return t;
+}
 void range_proof(Buffer& cs, LC x, unsigned n, bool has, const S& x_assignment) {  // utils.rs:5-35
     // Term lists are written out directly; they are the ones the operator forms would build:
     //   o                          LC::var(o)
     //   l + (r - 1)                (l, 1) (r, 1) (One, -1)
     //   x - r * 2^i                x ... (r, -(1 * 2^i))
     static const S ONE = s_one(), MINUS_ONE = s_neg(s_one());
-    static const std::vector<S> NEG_POW2 = [] {  // -(1 * 2^i) along the reference's doubling chain exp2 = exp2 + exp2
-        std::vector<S> t;
-        S exp2 = s_one();
-        for (int i = 0; i < 256; i++) {
-            t.push_back(s_neg(s_mul(s_one(), exp2)));
-            exp2 = s_add(exp2, exp2);
-        }
-        return t;
-    }();
+    const std::vector<S>& NEG_POW2 = neg_pow2();
     if (n > NEG_POW2.size()) throw Panic("range proof wider than 256 bits");
+    if (cs.compact) return cs.range(LCView{x.t.begin(), (uint32_t)x.t.size()}, n, has, x_assignment);
     uint8_t xb[32] = {0};
     if (has) s_bytes(x_assignment, xb);
     x.t.reserve(x.t.size() + n);
@@ -838,6 +862,7 @@ struct Flat {
             if (o.kind == Op::MUL) n_total++, q_total += 2, nnz_total += (size_t)o.a_len + o.b_len + 2;
             else if (o.kind == Op::ALLOC) n_total++;
             else if (o.kind == Op::CON) q_total++, nnz_total += o.a_len;
+            else if (o.kind == Op::RANGE) n_total += o.b_len, q_total += 2 * (size_t)o.b_len + 1, nnz_total += 5 * (size_t)o.b_len + o.a_len;
         }
         if (nnz_total >= (1ull << 32) || n_total >= (1u << 29)) throw Panic("constraint system too large");
         row_start.alloc(q_total + 1);
@@ -866,6 +891,41 @@ struct Flat {
                 n++;
             } else if (o.kind == Op::CON) {
                 constrain(buf.a_of(o));
+            } else if (o.kind == Op::RANGE) {
+                // range_proof, expanded in place: per bit i  allocate_multiplier((1 - b_i, b_i)), [o_i], [l_i + r_i - 1];
+                // then  [x - sum_i r_i 2^i]   -- the rows and terms the expanded recording would produce, in its order
+                static const S ONE = s_one(), MINUS_ONE = s_neg(s_one());
+                const std::vector<S>& NEG_POW2 = neg_pow2();
+                const uint32_t first = n, nbits = o.b_len;
+                uint8_t xb[32] = {0};
+                if (proving) s_bytes(buf.vals[o.val], xb);
+                for (uint32_t i = 0; i < nbits; i++) {
+                    if (proving) {
+                        const uint32_t bit = (xb[i / 8] >> (i % 8)) & 1u;
+                        assign_alloc(s_u64(1 - bit), s_u64(bit));
+                    }
+                    const uint32_t m = n++;
+                    term_var.p[nnz] = mkvar(K_OUT, m);
+                    term_coef.p[nnz] = ONE;
+                    row_start.p[++rows] = (uint32_t)++nnz;
+                    term_var.p[nnz] = mkvar(K_LEFT, m), term_coef.p[nnz] = ONE;
+                    term_var.p[nnz + 1] = mkvar(K_RIGHT, m), term_coef.p[nnz + 1] = ONE;
+                    term_var.p[nnz + 2] = ONE_VAR, term_coef.p[nnz + 2] = MINUS_ONE;
+                    nnz += 3;
+                    row_start.p[++rows] = (uint32_t)nnz;
+                }
+                const LCView x = buf.a_of(o);
+                for (uint32_t k = 0; k < x.n; k++) {
+                    term_var.p[nnz + k] = x.p[k].first;
+                    term_coef.p[nnz + k] = x.p[k].second;
+                }
+                nnz += x.n;
+                for (uint32_t i = 0; i < nbits; i++) {
+                    term_var.p[nnz + i] = mkvar(K_RIGHT, first + i);
+                    term_coef.p[nnz + i] = NEG_POW2[i];
+                }
+                nnz += nbits;
+                row_start.p[++rows] = (uint32_t)nnz;
             }
         }
     }
@@ -1289,6 +1349,7 @@ void compile_prover(const char* instance, const char* witness, const char* gadge
         side->witness[kv.first] = w;
     }
     Buffer top(true);
+    top.compact = true;
     ScratchLease lease(top);
     Walker wk{*side, split_lines(gadgets)};
     auto T0 = std::chrono::steady_clock::now();
@@ -1314,6 +1375,7 @@ void compile_verifier(const char* instance, const char* commitments, const char*
         side->st.com_names.push_back(kv.first);
     }
     Buffer top(false);
+    top.compact = true;
     ScratchLease lease(top);
     Walker wk{*side, split_lines(gadgets)};
     auto T0 = std::chrono::steady_clock::now();
