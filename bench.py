@@ -222,6 +222,7 @@ def main():
     # the issue-rate microbenchmark of round 1 (tools/imad_peak.cu, built with the library), rank 0's GPU
     imad_wide_peak, imad32_peak = measure_imad_peak(local_rank)
     ctxs = [ctx0] + [ctx0.shared() for _ in range(inflight - 1)]
+    text_inflight = min(inflight, int(os.environ.get("BPG_BENCH_TEXT_INFLIGHT", "48")))
     st = W.bounds_check_statement(args.count, seed=20261018 + rank, label=b"bench-bound-%d" % rank).pin(bpg)
     ctx0.gens_ensure(st.n)
     circuit = bpg.Circuit(ctx0, st.n, st.m, st.row_start, st.term_var, st.term_coef, st.q).set_witness(st.aL, st.aR)
@@ -250,7 +251,7 @@ def main():
     def run_statement(first, n, use=None):
         sd = seeds(first, n)
         # (the text front end costs ~35 ms of host CPU per side: more than 48 threads only oversubscribe a 16-core host)
-        out = bpg.prove_text_batch(use or ctxs[:48], [(name_txt, inst_txt, wtns_txt, gad_txt)] * n, sd, sd, verify=True)
+        out = bpg.prove_text_batch(use or ctxs[:text_inflight], [(name_txt, inst_txt, wtns_txt, gad_txt)] * n, sd, sd, verify=True)
         if not all(o[0] == 0 and o[3] for o in out):
             raise SystemExit("GPU proof did not verify")
         return out
@@ -442,7 +443,7 @@ def main():
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if args.count == 1024 else "bounds_check 64-bit x%d" % args.count,
-                   "proofs_per_step": PROOFS_PER_STEP, "inflight": inflight, "inflight_text_legs": min(inflight, 48),
+                   "proofs_per_step": PROOFS_PER_STEP, "inflight": inflight, "inflight_text_legs": text_inflight,
                    "hardware_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "dist_backend": (dist_backend if ws > 1 else None),
                    "api": "bpg_r1cs_prove_batch (BPG_JOB_VERIFY): library-owned host threads, one context per statement in flight",
                    "l2": "per-step working set (fixed-base tables 403 MB + entries) exceeds the 126 MB L2",
